@@ -1,0 +1,155 @@
+/*
+ * jpdse_b200 -- C ABI of the B200-native (sm_100a) hot path of SenseBrain/JPD-SE.
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; every entry point below replaces
+ * the ATen/cuDNN dispatch behind one reference call site (cited as file:line relative to the
+ * reference tree) and is what a ctypes binding inside `ctu` would bind.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller; nothing is allocated or freed here;
+ *   - every function enqueues on `stream` (a cudaStream_t passed as void*) and never synchronises;
+ *   - return value 0 = success, negative = error; jpdse_last_error() gives the message of the last
+ *     failure on the calling thread;
+ *   - activations between kernels are NHWC bf16 ("pixel-major"); `stats` buffers are
+ *     double[batch][channels][2] = (sum, sum of squares) accumulated by the conv epilogue and must be
+ *     zeroed by the caller before the conv that fills them.
+ */
+#ifndef JPDSE_B200_H_
+#define JPDSE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPDSE_OK 0
+#define JPDSE_ERR_INVALID (-1)
+#define JPDSE_ERR_CUDA (-2)
+#define JPDSE_ERR_UNSUPPORTED (-3)
+
+/* ABI version of this header; bumped on any signature change. */
+int jpdse_abi_version(void);
+/* Message of the last error on this thread ("" if none). Never NULL. */
+const char* jpdse_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input build: one-hot + instance edges + concat (+ reflect pad, NHWC bf16).
+ * Replaces Pix2PixHDModel.preprocess one-hot scatter_ (ctu/models/pix2pixHD_model.py:376-382),
+ * get_edges (:774-783), cat(label, edge) (:394) and cat(input_label, image) (:595), and the first
+ * ReflectionPad2d(3) of GlobalGenerator (ctu/models/pix2pixHD_networks/networks.py:210).
+ *
+ *   label     : class ids, (B,1,H,W); label_dtype 0 = float32 (truncated like .long()), 1 = uint8,
+ *               2 = int64
+ *   instance  : instance ids, (B,1,H,W); inst_dtype 0 = int32, 1 = int16, 2 = int64, 3 = float32
+ *   image     : float32 (B,3,H,W) NCHW, already normalised
+ *   num_labels: number of one-hot channels (35 on Cityscapes); ids outside [0,num_labels) are an
+ *               error in the reference (scatter_ raises); here they set no channel and bump
+ *               *bad_label_count (int32 device counter, may be NULL)
+ *   out_nhwc  : bf16 (B, H+2*pad, W+2*pad, c_pad) reflect-padded, channel order
+ *               [num_labels one-hot, 1 edge, 3 image, zeros up to c_pad]; may be NULL
+ *   out_nchw  : float32 (B, num_labels+4, H, W), the reference's `input_concat`; may be NULL
+ */
+int jpdse_build_input(const void* label, int label_dtype, const void* instance, int inst_dtype,
+                      const float* image, int batch, int height, int width, int num_labels,
+                      void* out_nhwc, int pad, int c_pad, float* out_nchw, int* bad_label_count,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolutions as tcgen05/TMEM implicit GEMM fed by TMA.
+ * Replace nn.Conv2d / nn.ConvTranspose2d inside GlobalGenerator and ResnetBlock
+ * (ctu/models/pix2pixHD_networks/networks.py:210,215,244,246,283-299) and the Binarizer's 1x1 conv
+ * (ctu/quantizers/binarize.py:47,51).
+ */
+enum jpdse_conv_kind {
+  JPDSE_CONV3X3_PAD1 = 0,   /* 3x3 stride 1 on an input already padded by 1: x is (B,H+2,W+2,Cin)   */
+  JPDSE_CONV3X3_S2 = 1,     /* 3x3 stride 2, zero pad 1: x is (B,H,W,Cin) unpadded, out (B,H/2,W/2)  */
+  JPDSE_CONVT3X3_S2 = 2,    /* ConvTranspose 3x3 s2 p1 op1: x is (B,H,W,Cin), out (B,2H,2W,Cout)     */
+  JPDSE_CONV7X7_PAD3 = 3,   /* 7x7 stride 1 on an input already padded by 3: x is (B,H+6,W+6,Cin);   */
+                            /* Cin*2 bytes must be a multiple of 16 (Cin = 40 for the stem, 64 head) */
+  JPDSE_CONV1X1 = 4         /* 1x1: x is (B,H,W,Cin)                                                 */
+};
+enum jpdse_conv_epilogue {
+  JPDSE_EPI_RAW_STATS = 0,      /* y = bf16 NHWC raw conv output, stats += (sum, sumsq) per (b,c)    */
+  JPDSE_EPI_BIAS_TANH_NCHW = 1, /* y = float32 NCHW tanh(conv + bias)            (networks.py:246)   */
+  JPDSE_EPI_SIGN_NCHW = 2       /* y = float32 NCHW sign(tanh(conv))             (binarize.py:51-54) */
+};
+typedef struct jpdse_conv_desc {
+  int kind;      /* enum jpdse_conv_kind */
+  int epilogue;  /* enum jpdse_conv_epilogue */
+  int batch;
+  int in_h, in_w; /* logical (unpadded) input height / width */
+  int in_pad;     /* border (pixels) physically present around x: must be 1 / 3 for the PAD1 / PAD3  */
+                  /* kinds (it is the conv's padding); for the other kinds it is skipped over        */
+  int cin;        /* input channels as stored (multiple of 64, or 40 for the stem) */
+  int cin_real;   /* channels of the torch weight (<= cin); extra stored channels multiply zero weights */
+  int cout;       /* output channels */
+} jpdse_conv_desc;
+
+/* Bytes of the packed (bf16, K-major, tap-blocked) weight buffer for this conv. 0 on error. */
+size_t jpdse_conv_packed_weight_bytes(const jpdse_conv_desc* d);
+/* Pack a float32 torch-layout weight -- Conv2d (Cout,Cin,kh,kw) or ConvTranspose2d (Cin,Cout,kh,kw)
+ * -- into the layout jpdse_conv_forward expects. */
+int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w, void* w_packed, void* stream);
+/* y = conv(x). `bias` is only read by JPDSE_EPI_BIAS_TANH_NCHW; `stats` only by RAW_STATS. */
+int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const void* w_packed,
+                       const float* bias, void* y, double* stats, void* stream);
+/* FLOPs (2*MAC, algorithmic: real taps and real channels only) of one jpdse_conv_forward. */
+double jpdse_conv_flops(const jpdse_conv_desc* d);
+
+/* ---------------------------------------------------------------------------------------------
+ * InstanceNorm apply (+ReLU) (+residual) (+reflect pad) -- the second half of
+ * nn.InstanceNorm2d(affine=False, eps=1e-5) (networks.py:27-36) whose statistics were reduced by
+ * the producing conv's epilogue; ReLU (networks.py:204), ResnetBlock skip add (:303-305) and the
+ * ReflectionPad2d in front of the next conv (:210,246,275-276,291-292) are fused in.
+ *
+ *   raw      : bf16 (B,H,W,C) raw conv output
+ *   stats    : double (B,C,2)
+ *   residual : bf16 (B,H+2*pad,W+2*pad,C) or NULL; added after normalisation (no ReLU after the add)
+ *   out      : bf16 (B,H+2*pad,W+2*pad,C); pad > 0 => reflect padding of the normalised tensor
+ */
+int jpdse_instnorm_apply(const void* raw, const double* stats, const void* residual, void* out,
+                         int batch, int height, int width, int channels, int pad, int relu,
+                         float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout helpers used at the boundary (reference tensors are NCHW float32).
+ * nchw->nhwc: y is bf16 (B, H+2*pad_reflect, W+2*pad_reflect, c_pad), channels >= `channels` are 0.
+ */
+int jpdse_nchw_f32_to_nhwc_bf16(const float* x, void* y, int batch, int channels, int height,
+                                int width, int pad_reflect, int c_pad, void* stream);
+int jpdse_nhwc_bf16_to_nchw_f32(const void* x, float* y, int batch, int channels, int height,
+                                int width, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * ctu/quantizers forward passes.
+ */
+/* RoundedIdentity.forward = torch.round, ties to even (ctu/quantizers/round.py:10-11). */
+int jpdse_round_f32(const float* x, float* y, size_t n, void* stream);
+/* DifferentiableSign eval = x.sign() (ctu/quantizers/binarize.py:41); sign(0)=0, NaN stays NaN. */
+int jpdse_sign_f32(const float* x, float* y, size_t n, void* stream);
+/* SoftSignFunction.forward with the uniform noise given: y = +1 if (1-x)/2 <= u else -1
+ * (ctu/quantizers/binarize.py:20-24). */
+int jpdse_softsign_f32(const float* x, const float* u, float* y, size_t n, void* stream);
+/* Binary codes exported as bytes: (x+1)/2 for x in {-1,+1} (pix2pixHD_model.py:614, test.py:103-110). */
+int jpdse_sign_to_bits_u8(const float* x, uint8_t* y, size_t n, void* stream);
+/* S2HVQ (ctu/quantizers/s2h_vq.py): x is (rows, center_size) float32 = x_mtrx flattened over
+ * (n, code_len); code_book is (n_center, center_size) float32.
+ *   scores  : optional (rows, n_center) squared-L2 scores            (_get_score_mtrx, :72-89)
+ *   index   : optional int64 (rows): argmin of scores, first index on ties (_hard_quantize :124)
+ *   one_hot : optional (rows, n_center) float32 one-hot of index     (:125-129)
+ *   soft    : optional (rows, n_center) softmax(-sigma*scores)       (_soft_quantize :107-108)
+ */
+int jpdse_s2hvq_encode(const float* x, const float* code_book, size_t rows, int center_size,
+                       int n_center, float sigma, float* scores, int64_t* index, float* one_hot,
+                       float* soft, void* stream);
+/* S2HVQ.decode: argmax over the last dim of code_raw (rows, n_center) -> code_book gather
+ * (s2h_vq.py:182-183); out is (rows, center_size); index optional int64 (rows). */
+int jpdse_s2hvq_decode(const float* code_raw, const float* code_book, size_t rows, int center_size,
+                       int n_center, float* out, int64_t* index, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JPDSE_B200_H_ */

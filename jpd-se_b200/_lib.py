@@ -1,0 +1,75 @@
+"""ctypes binding of libjpdse_b200.so (include/jpdse_b200.h).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjpdse_b200.so")
+
+c_void_p, c_int, c_float, c_size_t, c_double = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t, ctypes.c_double)
+
+
+class ConvDesc(ctypes.Structure):
+    """struct jpdse_conv_desc"""
+    _fields_ = [("kind", c_int), ("epilogue", c_int), ("batch", c_int), ("in_h", c_int), ("in_w", c_int),
+                ("in_pad", c_int), ("cin", c_int), ("cin_real", c_int), ("cout", c_int)]
+
+
+# enum jpdse_conv_kind / jpdse_conv_epilogue
+CONV3X3_PAD1, CONV3X3_S2, CONVT3X3_S2, CONV7X7_PAD3, CONV1X1 = range(5)
+EPI_RAW_STATS, EPI_BIAS_TANH_NCHW, EPI_SIGN_NCHW = range(3)
+
+# symbol -> (restype, argtypes); also the list the CPU test checks against the header
+SIGNATURES = {
+    "jpdse_abi_version": (c_int, []),
+    "jpdse_last_error": (ctypes.c_char_p, []),
+    "jpdse_build_input": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "jpdse_conv_packed_weight_bytes": (c_size_t, [ctypes.POINTER(ConvDesc)]),
+    "jpdse_conv_pack_weights": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p]),
+    "jpdse_conv_forward": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
+    "jpdse_conv_flops": (c_double, [ctypes.POINTER(ConvDesc)]),
+    "jpdse_instnorm_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                     c_int, c_float, c_void_p]),
+    "jpdse_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "jpdse_nhwc_bf16_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "jpdse_round_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "jpdse_sign_f32": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "jpdse_softsign_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "jpdse_sign_to_bits_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "jpdse_s2hvq_encode": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_float, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p]),
+    "jpdse_s2hvq_decode": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class JpdseError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once). Raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise JpdseError(
+                "libjpdse_b200.so is missing (%s); build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "There is no CPU or PyTorch fallback for this path." % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise JpdseError("jpdse_b200 error %d: %s" % (rc, load().jpdse_last_error().decode()))

@@ -1,0 +1,540 @@
+// HBM-bound kernels of the JPD-SE hot path: input build (one-hot + edges + concat + reflect pad),
+// InstanceNorm apply (+ReLU, +residual, +reflect pad), layout converts and the ctu/quantizers
+// forward passes. All are coalesced, 16-byte-vectorised, grid sized from the SM count.
+#include <cuda_bf16.h>
+
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace jpdse {
+
+__device__ __forceinline__ int reflect_index(int i, int n) {
+  // ReflectionPad2d: -k -> k, (n-1+k) -> (n-1-k); edge sample not repeated
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------ input build
+// label id with the reference's `.long()` semantics (truncate toward zero); -1 = not a valid channel
+__device__ __forceinline__ int load_label(const void* p, int dtype, size_t i, int num_labels) {
+  long long v;
+  if (dtype == 0) {
+    const float f = static_cast<const float*>(p)[i];
+    if (!(f > -9.0e18f && f < 9.0e18f)) return -1;  // NaN / inf / out of int64 range
+    v = static_cast<long long>(f);
+  } else if (dtype == 1) {
+    v = static_cast<const uint8_t*>(p)[i];
+  } else {
+    v = static_cast<const long long*>(p)[i];
+  }
+  return (v >= 0 && v < num_labels) ? static_cast<int>(v) : -1;
+}
+
+template <typename T>
+__device__ __forceinline__ bool edge_at(const T* t, int h, int w, int H, int W) {
+  // Pix2PixHDModel.get_edges: both pixels of every horizontally / vertically differing pair
+  const T* row = t + static_cast<size_t>(h) * W;
+  const T c = row[w];
+  bool e = false;
+  if (w > 0) e |= (c != row[w - 1]);
+  if (w < W - 1) e |= (c != row[w + 1]);
+  if (h > 0) e |= (c != row[w - W]);
+  if (h < H - 1) e |= (c != row[w + W]);
+  return e;
+}
+
+__device__ __forceinline__ bool load_edge(const void* inst, int dtype, size_t img_off, int h, int w, int H, int W) {
+  switch (dtype) {
+    case 0: return edge_at(static_cast<const int*>(inst) + img_off, h, w, H, W);
+    case 1: return edge_at(static_cast<const short*>(inst) + img_off, h, w, H, W);
+    case 2: return edge_at(static_cast<const long long*>(inst) + img_off, h, w, H, W);
+    default: return edge_at(static_cast<const float*>(inst) + img_off, h, w, H, W);
+  }
+}
+
+constexpr int kBuildThreads = 256;
+
+// One thread per padded output pixel; rows are staged in shared memory so the NHWC write is a
+// contiguous stream of 16-byte vectors.
+__global__ void __launch_bounds__(kBuildThreads)
+build_input_nhwc_kernel(const void* __restrict__ label, int label_dtype, const void* __restrict__ inst, int inst_dtype,
+                        const float* __restrict__ image, int B, int H, int W, int num_labels, int pad, int c_pad,
+                        __nv_bfloat16* __restrict__ out, int* __restrict__ bad) {
+  extern __shared__ uint4 s_rows[];  // [kBuildThreads][c_pad/8]
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const size_t total = static_cast<size_t>(B) * Hp * Wp;
+  const int vpp = c_pad / 8;
+  for (size_t base = static_cast<size_t>(blockIdx.x) * kBuildThreads; base < total;
+       base += static_cast<size_t>(gridDim.x) * kBuildThreads) {
+    const size_t pix = base + threadIdx.x;
+    if (pix < total) {
+      const int pw = static_cast<int>(pix % Wp);
+      const int ph = static_cast<int>((pix / Wp) % Hp);
+      const int b = static_cast<int>(pix / (static_cast<size_t>(Wp) * Hp));
+      const int h = reflect_index(ph - pad, H), w = reflect_index(pw - pad, W);
+      const size_t img_off = static_cast<size_t>(b) * H * W;
+      const size_t src = img_off + static_cast<size_t>(h) * W + w;
+      const int lab = load_label(label, label_dtype, src, num_labels);
+      if (lab < 0 && bad != nullptr && ph >= pad && ph < H + pad && pw >= pad && pw < W + pad) atomicAdd(bad, 1);
+      const float edge = load_edge(inst, inst_dtype, img_off, h, w, H, W) ? 1.f : 0.f;
+      const size_t plane = static_cast<size_t>(H) * W;
+      const float* ip = image + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(h) * W + w;
+      const float r = ip[0], g = ip[plane], bl = ip[2 * plane];
+      for (int v = 0; v < vpp; ++v) {
+        uint32_t wds[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float e[2];
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int ch = v * 8 + j * 2 + k;
+            float x = 0.f;
+            if (ch < num_labels) x = (ch == lab) ? 1.f : 0.f;
+            else if (ch == num_labels) x = edge;
+            else if (ch == num_labels + 1) x = r;
+            else if (ch == num_labels + 2) x = g;
+            else if (ch == num_labels + 3) x = bl;
+            e[k] = x;
+          }
+          wds[j] = pack_bf16x2(e[0], e[1]);
+        }
+        s_rows[threadIdx.x * vpp + v] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+      }
+    }
+    __syncthreads();
+    const size_t nvec_total = total * vpp;
+    const size_t vbase = base * vpp;
+    uint4* dst = reinterpret_cast<uint4*>(out);
+    for (int i = threadIdx.x; i < kBuildThreads * vpp; i += kBuildThreads)
+      if (vbase + i < nvec_total) dst[vbase + i] = s_rows[i];
+    __syncthreads();
+  }
+}
+
+// Reference layout: float32 NCHW `input_concat` (B, num_labels + 4, H, W); thread per pixel, plane-coalesced.
+__global__ void __launch_bounds__(256)
+build_input_nchw_kernel(const void* __restrict__ label, int label_dtype, const void* __restrict__ inst, int inst_dtype,
+                        const float* __restrict__ image, int B, int H, int W, int num_labels, float* __restrict__ out,
+                        int* __restrict__ bad, int count_bad) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * plane;
+  const int C = num_labels + 4;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(pix / plane);
+    const size_t hw = pix % plane;
+    const int h = static_cast<int>(hw / W), w = static_cast<int>(hw % W);
+    const int lab = load_label(label, label_dtype, pix, num_labels);
+    if (lab < 0 && bad != nullptr && count_bad) atomicAdd(bad, 1);
+    const float edge = load_edge(inst, inst_dtype, static_cast<size_t>(b) * plane, h, w, H, W) ? 1.f : 0.f;
+    float* o = out + static_cast<size_t>(b) * C * plane + hw;
+    for (int ch = 0; ch < num_labels; ++ch) o[ch * plane] = (ch == lab) ? 1.f : 0.f;
+    o[num_labels * plane] = edge;
+    const float* ip = image + static_cast<size_t>(b) * 3 * plane + hw;
+    o[(num_labels + 1) * plane] = ip[0];
+    o[(num_labels + 2) * plane] = ip[plane];
+    o[(num_labels + 3) * plane] = ip[2 * plane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ InstanceNorm apply
+constexpr int kNormThreads = 256;
+constexpr int kNormIters = 16;
+
+template <bool kRelu, bool kResidual>
+__global__ void __launch_bounds__(kNormThreads)
+instnorm_apply_kernel(const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
+                      const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int H, int W, int C,
+                      int pad, float eps) {
+  const int vpp = C >> 3;                 // 16-byte vectors per pixel
+  const int ppi = kNormThreads / vpp;     // pixels per block iteration
+  const int vec = threadIdx.x % vpp;
+  const int psub = threadIdx.x / vpp;
+  const int b = blockIdx.y;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int npix = Hp * Wp;
+
+  float mean[8], rstd[8];
+  {
+    const double inv_n = 1.0 / (static_cast<double>(H) * W);
+    const double* st = stats + (static_cast<size_t>(b) * C + vec * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double m = st[2 * j] * inv_n;
+      double var = st[2 * j + 1] * inv_n - m * m;  // biased variance, fp64 so E[x^2]-E[x]^2 does not cancel
+      if (var < 0.0) var = 0.0;
+      mean[j] = static_cast<float>(m);
+      rstd[j] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+  const int pix0 = blockIdx.x * (ppi * kNormIters);
+  const uint4* raw4 = reinterpret_cast<const uint4*>(raw) + static_cast<size_t>(b) * H * W * vpp;
+  const uint4* res4 = reinterpret_cast<const uint4*>(residual) + static_cast<size_t>(b) * npix * vpp;
+  uint4* out4 = reinterpret_cast<uint4*>(out) + static_cast<size_t>(b) * npix * vpp;
+  if (psub >= ppi) return;  // only when vpp does not divide the block (never for power-of-two C)
+#pragma unroll 4
+  for (int it = 0; it < kNormIters; ++it) {
+    const int pp = pix0 + it * ppi + psub;
+    if (pp >= npix) break;
+    const int ph = pp / Wp, pw = pp - ph * Wp;
+    const int h = reflect_index(ph - pad, H), w = reflect_index(pw - pad, W);
+    const uint4 x = __ldg(raw4 + (static_cast<size_t>(h) * W + w) * vpp + vec);
+    uint4 rs = make_uint4(0, 0, 0, 0);
+    if (kResidual) rs = __ldg(res4 + static_cast<size_t>(pp) * vpp + vec);
+    const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
+    const uint32_t rw[4] = {rs.x, rs.y, rs.z, rs.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 xv = *reinterpret_cast<const __nv_bfloat162*>(&xw[j]);
+      float lo = (__low2float(xv) - mean[2 * j]) * rstd[2 * j];
+      float hi = (__high2float(xv) - mean[2 * j + 1]) * rstd[2 * j + 1];
+      if (kRelu) {
+        lo = fmaxf(lo, 0.f);
+        hi = fmaxf(hi, 0.f);
+      }
+      if (kResidual) {
+        const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rw[j]);
+        lo += __low2float(rv);
+        hi += __high2float(rv);
+      }
+      ow[j] = pack_bf16x2(lo, hi);
+    }
+    out4[static_cast<size_t>(pp) * vpp + vec] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ layout converts
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int B, int C,
+                                             int H, int W, int pad, int c_pad) {
+  // 32 channels x 32 pixels transposed through shared memory: reads coalesced along W, writes along C
+  __shared__ float tile[32][33];
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const size_t npix = static_cast<size_t>(Hp) * Wp;
+  const size_t p0 = static_cast<size_t>(blockIdx.x) * 32;
+  {
+    const size_t pp = p0 + threadIdx.x;
+    const int c = c0 + threadIdx.y;
+    float v = 0.f;
+    if (pp < npix && c < C) {
+      const int ph = static_cast<int>(pp / Wp), pw = static_cast<int>(pp % Wp);
+      const int h = reflect_index(ph - pad, H), w = reflect_index(pw - pad, W);
+      v = x[((static_cast<size_t>(b) * C + c) * H + h) * W + w];
+    }
+    tile[threadIdx.y][threadIdx.x] = v;
+  }
+  __syncthreads();
+  {
+    const size_t pp = p0 + threadIdx.y;
+    const int c = c0 + threadIdx.x;
+    if (pp < npix && c < c_pad)
+      y[(static_cast<size_t>(b) * npix + pp) * c_pad + c] = __float2bfloat16_rn(tile[threadIdx.x][threadIdx.y]);
+  }
+}
+
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C,
+                                             int H, int W) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.y * 32;
+  const size_t npix = static_cast<size_t>(H) * W;
+  const size_t p0 = static_cast<size_t>(blockIdx.x) * 32;
+  {
+    const size_t pp = p0 + threadIdx.y;
+    const int c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (pp < npix && c < C) v = __bfloat162float(x[(static_cast<size_t>(b) * npix + pp) * C + c]);
+    tile[threadIdx.y][threadIdx.x] = v;
+  }
+  __syncthreads();
+  {
+    const size_t pp = p0 + threadIdx.x;
+    const int c = c0 + threadIdx.y;
+    if (pp < npix && c < C) y[(static_cast<size_t>(b) * C + c) * npix + pp] = tile[threadIdx.x][threadIdx.y];
+  }
+}
+
+// ------------------------------------------------------------------------------------------ quantisers
+enum { kOpRound = 0, kOpSign = 1, kOpSoftSign = 2 };
+
+__device__ __forceinline__ float quant_op(int op, float x, float u) {
+  if (op == kOpRound) return rintf(x);  // round-half-to-even == torch.round
+  if (op == kOpSign) return static_cast<float>((x > 0.f) - (x < 0.f));  // torch.sign: NaN -> 0, -0 -> 0
+  // SoftSignFunction.forward: masks are evaluated on the input, x stays where both fail (NaN)
+  const float t = (1.f - x) / 2.f;
+  float y = x;
+  if (t <= u) y = 1.f;
+  if (t > u) y = -1.f;
+  return y;
+}
+
+template <int kOp>
+__global__ void __launch_bounds__(256)
+quant_elementwise_kernel(const float* __restrict__ x, const float* __restrict__ u, float* __restrict__ y, size_t n) {
+  const size_t n4 = n / 4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                         (kOp == kOpSoftSign ? reinterpret_cast<uintptr_t>(u) : 0)) & 15) == 0;
+  if (aligned) {
+    for (size_t i = tid; i < n4; i += stride) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(x) + i);
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kOp == kOpSoftSign) r = __ldg(reinterpret_cast<const float4*>(u) + i);
+      float4 o;
+      o.x = quant_op(kOp, a.x, r.x);
+      o.y = quant_op(kOp, a.y, r.y);
+      o.z = quant_op(kOp, a.z, r.z);
+      o.w = quant_op(kOp, a.w, r.w);
+      reinterpret_cast<float4*>(y)[i] = o;
+    }
+    for (size_t i = n4 * 4 + tid; i < n; i += stride) y[i] = quant_op(kOp, x[i], kOp == kOpSoftSign ? u[i] : 0.f);
+  } else {
+    for (size_t i = tid; i < n; i += stride) y[i] = quant_op(kOp, x[i], kOp == kOpSoftSign ? u[i] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+sign_to_bits_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, size_t n) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // ((x + 1) / 2).astype(uint8): float -> uint8 truncation of {0, 0.5, 1}
+    const float v = (x[i] + 1.f) / 2.f;
+    y[i] = static_cast<uint8_t>(static_cast<int>(v));
+  }
+}
+
+// S2HVQ encode: one thread per row of x; the code book lives in shared memory.
+__global__ void __launch_bounds__(128)
+s2hvq_encode_kernel(const float* __restrict__ x, const float* __restrict__ code_book, size_t rows, int d, int L,
+                    float sigma, float* __restrict__ scores, long long* __restrict__ index, float* __restrict__ one_hot,
+                    float* __restrict__ soft) {
+  extern __shared__ float s_cb[];  // [L][d]
+  for (int i = threadIdx.x; i < L * d; i += blockDim.x) s_cb[i] = code_book[i];
+  __syncthreads();
+  for (size_t row = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows;
+       row += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float* xr = x + row * d;
+    float best = 0.f;
+    int best_k = 0;
+    bool best_nan = false;
+    float smax = -INFINITY;  // max of -sigma*score for the soft path
+    for (int k = 0; k < L; ++k) {
+      float acc = 0.f;
+      for (int j = 0; j < d; ++j) {
+        const float df = xr[j] - s_cb[k * d + j];
+        acc += df * df;
+      }
+      if (scores) scores[row * L + k] = acc;
+      // torch.min: first minimal index; a NaN wins and the first NaN sticks
+      if (k == 0) {
+        best = acc;
+        best_nan = isnan(acc);
+      } else if (!best_nan && (isnan(acc) || acc < best)) {
+        best = acc;
+        best_k = k;
+        best_nan = isnan(acc);
+      }
+      smax = fmaxf(smax, -sigma * acc);
+    }
+    if (index) index[row] = best_k;
+    if (one_hot)
+      for (int k = 0; k < L; ++k) one_hot[row * L + k] = (k == best_k) ? 1.f : 0.f;
+    if (soft) {
+      float sum = 0.f;
+      for (int k = 0; k < L; ++k) {
+        float acc = 0.f;
+        for (int j = 0; j < d; ++j) {
+          const float df = xr[j] - s_cb[k * d + j];
+          acc += df * df;
+        }
+        const float e = expf(-sigma * acc - smax);
+        soft[row * L + k] = e;
+        sum += e;
+      }
+      const float inv = 1.f / sum;
+      for (int k = 0; k < L; ++k) soft[row * L + k] *= inv;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128)
+s2hvq_decode_kernel(const float* __restrict__ code_raw, const float* __restrict__ code_book, size_t rows, int d, int L,
+                    float* __restrict__ out, long long* __restrict__ index) {
+  for (size_t row = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows;
+       row += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float* cr = code_raw + row * L;
+    float best = cr[0];
+    int best_k = 0;
+    bool best_nan = isnan(best);
+    for (int k = 1; k < L; ++k) {
+      const float v = cr[k];
+      if (!best_nan && (isnan(v) || v > best)) {  // torch.max: first maximal index, NaN wins
+        best = v;
+        best_k = k;
+        best_nan = isnan(v);
+      }
+    }
+    if (index) index[row] = best_k;
+    for (int j = 0; j < d; ++j) out[row * d + j] = code_book[best_k * d + j];
+  }
+}
+
+static int grid_for(size_t work_items, int threads, int per_thread) {
+  size_t blocks = (work_items + static_cast<size_t>(threads) * per_thread - 1) / (static_cast<size_t>(threads) * per_thread);
+  const size_t cap = static_cast<size_t>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace jpdse
+
+using namespace jpdse;
+
+extern "C" int jpdse_build_input(const void* label, int label_dtype, const void* instance, int inst_dtype,
+                                 const float* image, int batch, int height, int width, int num_labels, void* out_nhwc,
+                                 int pad, int c_pad, float* out_nchw, int* bad_label_count, void* stream_v) {
+  if (label == nullptr || instance == nullptr || image == nullptr) return fail(JPDSE_ERR_INVALID, "build_input: NULL input");
+  if (batch <= 0 || height <= 1 || width <= 1 || num_labels <= 0) return fail(JPDSE_ERR_INVALID, "build_input: bad sizes");
+  if (label_dtype < 0 || label_dtype > 2 || inst_dtype < 0 || inst_dtype > 3) return fail(JPDSE_ERR_INVALID, "build_input: bad dtype code");
+  if (out_nhwc == nullptr && out_nchw == nullptr) return fail(JPDSE_ERR_INVALID, "build_input: no output requested");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (out_nhwc != nullptr) {
+    if (c_pad % 8 || c_pad < num_labels + 4) return fail(JPDSE_ERR_INVALID, "build_input: c_pad must be a multiple of 8 and >= num_labels+4");
+    if (pad < 0 || pad >= height || pad >= width) return fail(JPDSE_ERR_INVALID, "build_input: bad pad");
+    if (reinterpret_cast<uintptr_t>(out_nhwc) & 15) return fail(JPDSE_ERR_INVALID, "build_input: out_nhwc must be 16-byte aligned");
+    const size_t total = static_cast<size_t>(batch) * (height + 2 * pad) * (width + 2 * pad);
+    const size_t smem = static_cast<size_t>(kBuildThreads) * c_pad * 2;
+    if (smem > 48 * 1024) return fail(JPDSE_ERR_UNSUPPORTED, "build_input: c_pad too large");
+    const int grid = grid_for(total, kBuildThreads, 1);
+    build_input_nhwc_kernel<<<grid, kBuildThreads, smem, stream>>>(label, label_dtype, instance, inst_dtype, image, batch,
+                                                                   height, width, num_labels, pad, c_pad,
+                                                                   static_cast<__nv_bfloat16*>(out_nhwc), bad_label_count);
+    int rc = check_launch("build_input_nhwc_kernel");
+    if (rc != JPDSE_OK) return rc;
+  }
+  if (out_nchw != nullptr) {
+    const size_t total = static_cast<size_t>(batch) * height * width;
+    const int grid = grid_for(total, 256, 1);
+    build_input_nchw_kernel<<<grid, 256, 0, stream>>>(label, label_dtype, instance, inst_dtype, image, batch, height, width,
+                                                      num_labels, out_nchw, bad_label_count, out_nhwc == nullptr ? 1 : 0);
+    int rc = check_launch("build_input_nchw_kernel");
+    if (rc != JPDSE_OK) return rc;
+  }
+  return JPDSE_OK;
+}
+
+extern "C" int jpdse_instnorm_apply(const void* raw, const double* stats, const void* residual, void* out, int batch,
+                                    int height, int width, int channels, int pad, int relu, float eps, void* stream_v) {
+  if (raw == nullptr || stats == nullptr || out == nullptr) return fail(JPDSE_ERR_INVALID, "instnorm_apply: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0) return fail(JPDSE_ERR_INVALID, "instnorm_apply: bad sizes");
+  if (channels % 8 || channels > 8 * kNormThreads || (kNormThreads % (channels / 8)))
+    return fail(JPDSE_ERR_UNSUPPORTED, "instnorm_apply: channels must be 8*2^k <= %d (got %d)", 8 * kNormThreads, channels);
+  if (pad < 0 || pad >= height || pad >= width) return fail(JPDSE_ERR_INVALID, "instnorm_apply: bad pad");
+  if ((reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(residual)) & 15)
+    return fail(JPDSE_ERR_INVALID, "instnorm_apply: pointers must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int vpp = channels / 8;
+  const int ppi = kNormThreads / vpp;
+  const int npix = (height + 2 * pad) * (width + 2 * pad);
+  const int per_block = ppi * kNormIters;
+  dim3 grid((npix + per_block - 1) / per_block, batch);
+  const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(raw);
+  const __nv_bfloat16* rs = static_cast<const __nv_bfloat16*>(residual);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (relu && residual)
+    instnorm_apply_kernel<true, true><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
+  else if (relu)
+    instnorm_apply_kernel<true, false><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
+  else if (residual)
+    instnorm_apply_kernel<false, true><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
+  else
+    instnorm_apply_kernel<false, false><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
+  return check_launch("instnorm_apply_kernel");
+}
+
+extern "C" int jpdse_nchw_f32_to_nhwc_bf16(const float* x, void* y, int batch, int channels, int height, int width,
+                                           int pad_reflect, int c_pad, void* stream) {
+  if (x == nullptr || y == nullptr) return fail(JPDSE_ERR_INVALID, "nchw_to_nhwc: NULL pointer");
+  if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || pad_reflect < 0 || pad_reflect >= height || pad_reflect >= width)
+    return fail(JPDSE_ERR_INVALID, "nchw_to_nhwc: bad sizes");
+  if (c_pad < channels) return fail(JPDSE_ERR_INVALID, "nchw_to_nhwc: c_pad < channels");
+  const size_t npix = static_cast<size_t>(height + 2 * pad_reflect) * (width + 2 * pad_reflect);
+  dim3 grid(static_cast<unsigned>((npix + 31) / 32), (c_pad + 31) / 32, batch), block(32, 32);
+  nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), batch, channels, height, width, pad_reflect, c_pad);
+  return check_launch("nchw_f32_to_nhwc_bf16_kernel");
+}
+
+extern "C" int jpdse_nhwc_bf16_to_nchw_f32(const void* x, float* y, int batch, int channels, int height, int width,
+                                           void* stream) {
+  if (x == nullptr || y == nullptr) return fail(JPDSE_ERR_INVALID, "nhwc_to_nchw: NULL pointer");
+  if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return fail(JPDSE_ERR_INVALID, "nhwc_to_nchw: bad sizes");
+  const size_t npix = static_cast<size_t>(height) * width;
+  dim3 grid(static_cast<unsigned>((npix + 31) / 32), (channels + 31) / 32, batch), block(32, 32);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), y, batch, channels, height, width);
+  return check_launch("nhwc_bf16_to_nchw_f32_kernel");
+}
+
+template <int kOp>
+static int launch_quant(const float* x, const float* u, float* y, size_t n, void* stream, const char* name) {
+  if (n == 0) return JPDSE_OK;
+  if (x == nullptr || y == nullptr || (kOp == kOpSoftSign && u == nullptr)) return fail(JPDSE_ERR_INVALID, "%s: NULL pointer", name);
+  const int grid = grid_for(n, 256, 16);
+  quant_elementwise_kernel<kOp><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, u, y, n);
+  return check_launch(name);
+}
+
+extern "C" int jpdse_round_f32(const float* x, float* y, size_t n, void* stream) {
+  return launch_quant<kOpRound>(x, nullptr, y, n, stream, "round_f32");
+}
+extern "C" int jpdse_sign_f32(const float* x, float* y, size_t n, void* stream) {
+  return launch_quant<kOpSign>(x, nullptr, y, n, stream, "sign_f32");
+}
+extern "C" int jpdse_softsign_f32(const float* x, const float* u, float* y, size_t n, void* stream) {
+  return launch_quant<kOpSoftSign>(x, u, y, n, stream, "softsign_f32");
+}
+extern "C" int jpdse_sign_to_bits_u8(const float* x, uint8_t* y, size_t n, void* stream) {
+  if (n == 0) return JPDSE_OK;
+  if (x == nullptr || y == nullptr) return fail(JPDSE_ERR_INVALID, "sign_to_bits: NULL pointer");
+  sign_to_bits_kernel<<<grid_for(n, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n);
+  return check_launch("sign_to_bits_kernel");
+}
+
+extern "C" int jpdse_s2hvq_encode(const float* x, const float* code_book, size_t rows, int center_size, int n_center,
+                                  float sigma, float* scores, int64_t* index, float* one_hot, float* soft, void* stream) {
+  if (rows == 0) return JPDSE_OK;
+  if (x == nullptr || code_book == nullptr) return fail(JPDSE_ERR_INVALID, "s2hvq_encode: NULL pointer");
+  if (center_size <= 0 || n_center <= 0) return fail(JPDSE_ERR_INVALID, "s2hvq_encode: bad sizes");
+  if (!(sigma > 0.f)) return fail(JPDSE_ERR_INVALID, "s2hvq_encode: sigma must be greater than 0");
+  const size_t smem = static_cast<size_t>(center_size) * n_center * sizeof(float);
+  if (smem > 200 * 1024) return fail(JPDSE_ERR_UNSUPPORTED, "s2hvq_encode: code book larger than shared memory");
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(s2hvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "s2hvq_encode: %s", cudaGetErrorString(e));
+  }
+  s2hvq_encode_kernel<<<grid_for(rows, 128, 1), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, code_book, rows, center_size, n_center, sigma, scores, reinterpret_cast<long long*>(index), one_hot, soft);
+  return check_launch("s2hvq_encode_kernel");
+}
+
+extern "C" int jpdse_s2hvq_decode(const float* code_raw, const float* code_book, size_t rows, int center_size,
+                                  int n_center, float* out, int64_t* index, void* stream) {
+  if (rows == 0) return JPDSE_OK;
+  if (code_raw == nullptr || code_book == nullptr || out == nullptr) return fail(JPDSE_ERR_INVALID, "s2hvq_decode: NULL pointer");
+  if (center_size <= 0 || n_center <= 0) return fail(JPDSE_ERR_INVALID, "s2hvq_decode: bad sizes");
+  s2hvq_decode_kernel<<<grid_for(rows, 128, 1), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      code_raw, code_book, rows, center_size, n_center, out, reinterpret_cast<long long*>(index));
+  return check_launch("s2hvq_decode_kernel");
+}

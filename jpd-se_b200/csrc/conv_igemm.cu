@@ -1,0 +1,716 @@
+// Implicit-GEMM convolutions for the JPD-SE generator on sm_100a.
+//
+//   D[pixel, cout] = sum_{tap, cin} A[pixel @ tap, cin] * W[cout, tap, cin]
+//
+// One persistent, warp-specialised kernel covers every conv of GlobalGenerator
+// (reference: ctu/models/pix2pixHD_networks/networks.py:210,215,244,246,283-299):
+//   * A tiles (128 output pixels x 64 input channels, bf16) are fetched by TMA straight out of the
+//     NHWC activation tensor: the tensor map is a 4-D/5-D *view* of the activations chosen per conv
+//     kind so that "the 128 pixels under filter tap t" is one box (no im2col buffer, zero padding
+//     comes from TMA out-of-bounds fill, reflect padding was materialised by the producer kernel).
+//   * B tiles (BN output channels x 64, bf16) come from a pre-packed K-major weight matrix.
+//   * tcgen05.mma (M=128, N=BN, K=16) accumulates in TMEM (fp32); two accumulator buffers let the
+//     epilogue of tile i overlap the main loop of tile i+1.
+//   * The epilogue reads TMEM with tcgen05.ld, writes bf16 NHWC and reduces the InstanceNorm
+//     statistics (sum, sum of squares per (image, channel)) with a warp-shuffle transpose-reduce,
+//     or applies bias+tanh / sign for the two terminal convs.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+#include <cuda_bf16.h>
+
+#include <cstring>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace jpdse {
+
+constexpr int kTileM = 128;         // output pixels per tile (UMMA M)
+constexpr int kBlockK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kUmmaK = 16;          // K of one tcgen05.mma for 16-bit inputs
+constexpr int kABytes = kTileM * kBlockK * 2;
+constexpr int kMaxTaps = 9;
+constexpr int kThreads = 192;
+
+struct IgemmParams {
+  // tile grid
+  int batch, tiles_h, tiles_w, n_tiles;
+  int tile_h, tile_w;  // tile_h * tile_w == 128
+  // K loop
+  int ntaps, chunks_per_tap;
+  // A tensor-map addressing
+  int a_rank, dim_w, dim_h, dim_b;
+  int tap_off[kMaxTaps][5];
+  int b_k_offset;  // first k element of this launch inside the packed weight matrix (ConvT phases)
+  // output addressing
+  int out_h, out_w, os_h, os_w, op_h, op_w;
+  int ldc;      // channels of the output tensor
+  int n_valid;  // valid output channels (<= n_tiles * BN)
+  int epilogue;
+  void* out;
+  double* stats;
+  const float* bias;
+};
+
+template <int BN>
+struct IgemmCfg {
+  static constexpr int kBBytes = BN * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int kRedFloats = 4 * BN * 2;  // per-warp column partials (sum, sumsq)
+  // 1024 B alignment slack + stages + reduction scratch + barriers
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kRedFloats * 4 + 256;
+};
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// Column sums over the 32 lanes of a warp for 32 per-lane values: after the butterfly lane l holds
+// sum over lanes of v[l]. 31 shuffles instead of 32*5.
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      const float send = upper ? v[j] : v[j + s];
+      const float keep = upper ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+             const __grid_constant__ IgemmParams p) {
+  using Cfg = IgemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* s_red = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kRedFloats * 4);
+  uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc<1>(tmem_slot, Cfg::kTmemCols);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kblocks = p.ntaps * p.chunks_per_tap;
+  const int m_tiles = p.batch * p.tiles_h * p.tiles_w;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int tw = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int b = mt / p.tiles_h;
+        int base[5] = {0, 0, 0, 0, 0};
+        base[p.dim_w] += tw * p.tile_w;
+        base[p.dim_h] += th * p.tile_h;
+        base[p.dim_b] += b;
+        int kb = 0;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int c1 = base[1] + p.tap_off[t][1];
+          const int c2 = base[2] + p.tap_off[t][2];
+          const int c3 = base[3] + p.tap_off[t][3];
+          const int c4 = base[4] + p.tap_off[t][4];
+          for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + kABytes;
+            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            const int c0 = base[0] + p.tap_off[t][0] + ch * kBlockK;
+            if (p.a_rank == 4)
+              tma_load_4d(&tm_a, &full_bar[stage], sa, c0, c1, c2, c3);
+            else
+              tma_load_5d(&tm_a, &full_bar[stage], sa, c0, c1, c2, c3, c4);
+            tma_load_2d(&tm_b, &full_bar[stage], sb, p.b_k_offset + kb * kBlockK, nt * BN);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = umma_smem_desc_sw128(sa);
+          const uint64_t bdesc = umma_smem_desc_sw128(sa + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (>>4) address field
+            umma_bf16<1>(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;        // TMEM lanes [32*quarter, 32*quarter+32)
+    const int m = quarter * 32 + lane;   // tile row = output pixel within the tile
+    const int et = threadIdx.x - 64;     // 0..127
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int tw = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int b = mt / p.tiles_h;
+      const int r = m / p.tile_w;
+      const int c = m - r * p.tile_w;
+      const int oh = (th * p.tile_h + r) * p.os_h + p.op_h;
+      const int ow = (tw * p.tile_w + c) * p.os_w + p.op_w;
+      const int n0 = nt * BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
+      if (p.epilogue == JPDSE_EPI_RAW_STATS) {
+        __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
+                              ((static_cast<size_t>(b) * p.out_h + oh) * p.out_w + ow) * p.ldc + n0;
+        if constexpr (BN >= 32) {
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + ch * 32, v);
+            tmem_ld_wait();
+            float f[32], q[32];
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              f[2 * j] = __low2float(h);
+              f[2 * j + 1] = __high2float(h);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) q[j] = f[j] * f[j];
+            const float s1 = warp_transpose_reduce(f, lane);
+            const float s2 = warp_transpose_reduce(q, lane);
+            s_red[((warp - 2) * BN + ch * 32 + lane) * 2 + 0] = s1;
+            s_red[((warp - 2) * BN + ch * 32 + lane) * 2 + 1] = s2;
+          }
+        }
+        // accumulator drained: hand the TMEM buffer back before the cross-warp reduction
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int col = et; col < BN; col += 128) {
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            s1 += s_red[(w * BN + col) * 2 + 0];
+            s2 += s_red[(w * BN + col) * 2 + 1];
+          }
+          double* st = p.stats + (static_cast<size_t>(b) * p.ldc + n0 + col) * 2;
+          atomicAdd(st, static_cast<double>(s1));
+          atomicAdd(st + 1, static_cast<double>(s2));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else {
+        // terminal convs: few output channels, fp32 NCHW output
+        if constexpr (BN <= 128) {
+          float* obase = reinterpret_cast<float*>(p.out);
+          const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
+          const size_t pix = static_cast<size_t>(oh) * p.out_w + ow;
+#pragma unroll 1
+          for (int ch = 0; ch < BN / 16; ++ch) {
+            if (n0 + ch * 16 >= p.n_valid) break;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + ch * 16, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = n0 + ch * 16 + j;
+              if (n < p.n_valid) {
+                float x = __uint_as_float(v[j]);
+                float y;
+                if (p.epilogue == JPDSE_EPI_BIAS_TANH_NCHW) {
+                  y = tanhf(x + p.bias[n]);
+                } else {
+                  // torch.sign(torch.tanh(x)) == (x > 0) - (x < 0): tanh keeps the sign of every
+                  // non-zero float (denormals included) and torch.sign maps NaN and -0 to 0
+                  y = static_cast<float>((x > 0.f) - (x < 0.f));
+                }
+                obase[(static_cast<size_t>(b) * p.n_valid + n) * plane + pix] = y;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// bf16 tensor map, 128-byte swizzle, zero OOB fill. dims/box innermost first; strides (bytes) for dims 1..rank-1.
+static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(JPDSE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim,
+                  gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(JPDSE_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+                static_cast<int>(r), rank, (unsigned long long)gdim[0], (unsigned long long)(rank > 1 ? gdim[1] : 0),
+                (unsigned long long)(rank > 2 ? gdim[2] : 0), (unsigned long long)(rank > 3 ? gdim[3] : 0),
+                (unsigned long long)(rank > 4 ? gdim[4] : 0), bdim[0], rank > 1 ? bdim[1] : 0, rank > 2 ? bdim[2] : 0,
+                rank > 3 ? bdim[3] : 0, rank > 4 ? bdim[4] : 0);
+  }
+  return JPDSE_OK;
+}
+
+static int pick_bn(int cout) {
+  if (cout >= 256) return 256;
+  if (cout > 64) return 128;
+  if (cout > 32) return 64;
+  if (cout > 16) return 32;
+  return 16;
+}
+
+// ConvTranspose2d(k=3,s=2,p=1,op=1): out[2i-1+kh, 2j-1+kw] += in[i,j] * W[kh,kw].
+// Output phase 0 (even coordinate 2a) takes tap kh=1 at i=a; phase 1 (odd, 2a+1) takes kh=0 at i=a+1
+// and kh=2 at i=a.
+static int convt_taps(int phase, int kk[2], int dd[2]) {
+  if (phase == 0) {
+    kk[0] = 1;
+    dd[0] = 0;
+    return 1;
+  }
+  kk[0] = 0;
+  dd[0] = 1;
+  kk[1] = 2;
+  dd[1] = 0;
+  return 2;
+}
+
+struct ConvGeom {
+  int out_h, out_w;      // output spatial dims
+  int gemm_h, gemm_w;    // pixel grid the GEMM M dimension runs over (== out dims except ConvT: input dims)
+  int ktot;              // packed K per output channel (sum over phases for ConvT)
+  int rows;              // packed rows (cout rounded up to BN)
+  int bn;
+  int cpt;               // chunks per tap
+};
+
+static int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
+  if (d == nullptr) return fail(JPDSE_ERR_INVALID, "conv desc is NULL");
+  if (d->batch <= 0 || d->in_h <= 0 || d->in_w <= 0 || d->cin <= 0 || d->cout <= 0 || d->cin_real <= 0 ||
+      d->cin_real > d->cin || d->in_pad < 0)
+    return fail(JPDSE_ERR_INVALID, "conv desc: bad sizes");
+  if (d->kind == JPDSE_CONV3X3_PAD1 && d->in_pad != 1) return fail(JPDSE_ERR_INVALID, "CONV3X3_PAD1 needs in_pad == 1");
+  if (d->kind == JPDSE_CONV7X7_PAD3 && d->in_pad != 3) return fail(JPDSE_ERR_INVALID, "CONV7X7_PAD3 needs in_pad == 3");
+  g->bn = pick_bn(d->cout);
+  g->rows = ((d->cout + g->bn - 1) / g->bn) * g->bn;
+  switch (d->kind) {
+    case JPDSE_CONV3X3_PAD1:
+    case JPDSE_CONV1X1:
+      if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv: cin must be a multiple of 64 (got %d)", d->cin);
+      g->out_h = g->gemm_h = d->in_h;
+      g->out_w = g->gemm_w = d->in_w;
+      g->cpt = d->cin / 64;
+      g->ktot = (d->kind == JPDSE_CONV1X1 ? 1 : 9) * d->cin;
+      break;
+    case JPDSE_CONV3X3_S2:
+      if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv s2: cin must be a multiple of 64 (got %d)", d->cin);
+      if ((d->in_h & 1) || (d->in_w & 1)) return fail(JPDSE_ERR_UNSUPPORTED, "conv s2: odd input size");
+      g->out_h = g->gemm_h = d->in_h / 2;
+      g->out_w = g->gemm_w = d->in_w / 2;
+      g->cpt = d->cin / 64;
+      g->ktot = 9 * d->cin;
+      break;
+    case JPDSE_CONVT3X3_S2:
+      if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "convT: cin must be a multiple of 64 (got %d)", d->cin);
+      g->out_h = 2 * d->in_h;
+      g->out_w = 2 * d->in_w;
+      g->gemm_h = d->in_h;
+      g->gemm_w = d->in_w;
+      g->cpt = d->cin / 64;
+      g->ktot = 9 * d->cin;
+      break;
+    case JPDSE_CONV7X7_PAD3:
+      if ((d->cin * 2) % 16) return fail(JPDSE_ERR_UNSUPPORTED, "conv7x7: cin*2 bytes must be a multiple of 16");
+      g->out_h = g->gemm_h = d->in_h;
+      g->out_w = g->gemm_w = d->in_w;
+      g->cpt = (7 * d->cin + 63) / 64;
+      g->ktot = 7 * g->cpt * 64;
+      break;
+    default:
+      return fail(JPDSE_ERR_INVALID, "conv desc: unknown kind %d", d->kind);
+  }
+  if (d->epilogue == JPDSE_EPI_RAW_STATS) {
+    if (d->cout % g->bn || g->bn < 32)
+      return fail(JPDSE_ERR_UNSUPPORTED, "raw+stats epilogue needs cout %% %d == 0 (got %d)", g->bn, d->cout);
+  } else if (d->epilogue == JPDSE_EPI_BIAS_TANH_NCHW || d->epilogue == JPDSE_EPI_SIGN_NCHW) {
+    if (g->bn > 128) return fail(JPDSE_ERR_UNSUPPORTED, "NCHW epilogues support cout <= 128 (got %d)", d->cout);
+  } else {
+    return fail(JPDSE_ERR_INVALID, "conv desc: unknown epilogue %d", d->epilogue);
+  }
+  return JPDSE_OK;
+}
+
+// M tiling: 128 pixels = tile_h rows x tile_w columns of the GEMM pixel grid.
+static int pick_tile(int gh, int gw, int* th, int* tw) {
+  int w = gw < 128 ? gw : 128;
+  if (w <= 0 || (128 % w) != 0 || (gw % w) != 0)
+    return fail(JPDSE_ERR_UNSUPPORTED, "conv: width %d cannot be tiled into 128-pixel tiles", gw);
+  int h = 128 / w;
+  if (gh % h) return fail(JPDSE_ERR_UNSUPPORTED, "conv: %dx%d pixel grid is not a multiple of the %dx%d tile", gh, gw, h, w);
+  *th = h;
+  *tw = w;
+  return JPDSE_OK;
+}
+
+template <int BN>
+static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+    configured = true;
+  }
+  const int total = p.batch * p.tiles_h * p.tiles_w * p.n_tiles;
+  int grid = num_sms();
+  if (grid > total) grid = total;
+  igemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  return check_launch("igemm_kernel");
+}
+
+static int launch_igemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p,
+                           cudaStream_t stream) {
+  switch (bn) {
+    case 256: return launch_igemm<256>(ta, tb, p, stream);
+    case 128: return launch_igemm<128>(ta, tb, p, stream);
+    case 64: return launch_igemm<64>(ta, tb, p, stream);
+    case 32: return launch_igemm<32>(ta, tb, p, stream);
+    case 16: return launch_igemm<16>(ta, tb, p, stream);
+  }
+  return fail(JPDSE_ERR_INVALID, "no igemm instantiation for BN=%d", bn);
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+struct PackParams {
+  int kind, cin, cin_real, cout, rows, ktot, cpt;
+};
+
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, PackParams q) {
+  const size_t total = static_cast<size_t>(q.rows) * q.ktot;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float val = 0.f;
+    if (q.kind == JPDSE_CONVT3X3_S2) {
+      // layout: phase blocks [(ph,pw) = 00,01,10,11], each (rows x ntaps*cin) row-major
+      size_t rem = i;
+      int ph = 0, pw = 0, nt = 1;
+      for (int pidx = 0; pidx < 4; ++pidx) {
+        ph = pidx >> 1;
+        pw = pidx & 1;
+        nt = (ph ? 2 : 1) * (pw ? 2 : 1);
+        const size_t blk = static_cast<size_t>(q.rows) * nt * q.cin;
+        if (rem < blk) break;
+        rem -= blk;
+      }
+      const int kp = nt * q.cin;
+      const int n = static_cast<int>(rem / kp);
+      const int k = static_cast<int>(rem % kp);
+      const int t = k / q.cin, c = k % q.cin;
+      const int ntw = pw ? 2 : 1;
+      const int ti = t / ntw, tj = t % ntw;
+      const int kh = ph ? (ti == 0 ? 0 : 2) : 1;
+      const int kw = pw ? (tj == 0 ? 0 : 2) : 1;
+      if (n < q.cout && c < q.cin_real) val = w[((static_cast<size_t>(c) * q.cout + n) * 3 + kh) * 3 + kw];
+    } else {
+      const int n = static_cast<int>(i / q.ktot);
+      const int k = static_cast<int>(i % q.ktot);
+      if (q.kind == JPDSE_CONV7X7_PAD3) {
+        const int kh = k / (q.cpt * 64);
+        const int e = k % (q.cpt * 64);
+        const int kw = e / q.cin, c = e % q.cin;
+        if (n < q.cout && kw < 7 && c < q.cin_real)
+          val = w[((static_cast<size_t>(n) * q.cin_real + c) * 7 + kh) * 7 + kw];
+      } else if (q.kind == JPDSE_CONV1X1) {
+        if (n < q.cout && k < q.cin_real) val = w[static_cast<size_t>(n) * q.cin_real + k];
+      } else {
+        const int t = k / q.cin, c = k % q.cin;
+        if (n < q.cout && c < q.cin_real) val = w[(static_cast<size_t>(n) * q.cin_real + c) * 9 + t];
+      }
+    }
+    out[i] = __float2bfloat16_rn(val);
+  }
+}
+
+}  // namespace jpdse
+
+using namespace jpdse;
+
+extern "C" size_t jpdse_conv_packed_weight_bytes(const jpdse_conv_desc* d) {
+  ConvGeom g;
+  if (conv_geom(d, &g) != JPDSE_OK) return 0;
+  return static_cast<size_t>(g.rows) * g.ktot * 2;
+}
+
+extern "C" double jpdse_conv_flops(const jpdse_conv_desc* d) {
+  ConvGeom g;
+  if (conv_geom(d, &g) != JPDSE_OK) return 0.0;
+  const int taps = d->kind == JPDSE_CONV7X7_PAD3 ? 49 : (d->kind == JPDSE_CONV1X1 ? 1 : 9);
+  // ConvT counted as 9 taps per *input* pixel
+  return 2.0 * d->batch * static_cast<double>(g.gemm_h) * g.gemm_w * taps * d->cin_real * d->cout;
+}
+
+extern "C" int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w, void* w_packed, void* stream) {
+  ConvGeom g;
+  int rc = conv_geom(d, &g);
+  if (rc != JPDSE_OK) return rc;
+  if (w == nullptr || w_packed == nullptr) return fail(JPDSE_ERR_INVALID, "pack_weights: NULL pointer");
+  PackParams q{d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt};
+  const size_t total = static_cast<size_t>(g.rows) * g.ktot;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > num_sms() * 16) blocks = num_sms() * 16;
+  pack_weights_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, static_cast<__nv_bfloat16*>(w_packed), q);
+  return check_launch("pack_weights_kernel");
+}
+
+extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                                  void* y, double* stats, void* stream_v) {
+  ConvGeom g;
+  int rc = conv_geom(d, &g);
+  if (rc != JPDSE_OK) return rc;
+  if (x == nullptr || w_packed == nullptr || y == nullptr) return fail(JPDSE_ERR_INVALID, "conv_forward: NULL pointer");
+  if (d->epilogue == JPDSE_EPI_RAW_STATS && stats == nullptr) return fail(JPDSE_ERR_INVALID, "conv_forward: stats is NULL");
+  if (d->epilogue == JPDSE_EPI_BIAS_TANH_NCHW && bias == nullptr) return fail(JPDSE_ERR_INVALID, "conv_forward: bias is NULL");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w_packed) & 15) ||
+      (reinterpret_cast<uintptr_t>(y) & 15))
+    return fail(JPDSE_ERR_INVALID, "conv_forward: pointers must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  rc = pick_tile(g.gemm_h, g.gemm_w, &p.tile_h, &p.tile_w);
+  if (rc != JPDSE_OK) return rc;
+  p.batch = d->batch;
+  p.tiles_h = g.gemm_h / p.tile_h;
+  p.tiles_w = g.gemm_w / p.tile_w;
+  p.n_tiles = g.rows / g.bn;
+  p.chunks_per_tap = g.cpt;
+  p.out_h = g.out_h;
+  p.out_w = g.out_w;
+  p.os_h = p.os_w = 1;
+  p.ldc = d->cout;
+  p.n_valid = d->cout;
+  p.epilogue = d->epilogue;
+  p.out = y;
+  p.stats = stats;
+  p.bias = bias;
+
+  const uint64_t C = static_cast<uint64_t>(d->cin);
+  const uint64_t H = static_cast<uint64_t>(d->in_h), W = static_cast<uint64_t>(d->in_w), B = static_cast<uint64_t>(d->batch);
+  // physical (stored) extent of x and the address of its logical pixel (0,0)
+  const uint64_t Hp = H + 2 * static_cast<uint64_t>(d->in_pad), Wp = W + 2 * static_cast<uint64_t>(d->in_pad);
+  const uint8_t* xin = static_cast<const uint8_t*>(x) + (static_cast<uint64_t>(d->in_pad) * Wp + d->in_pad) * C * 2;
+  CUtensorMap ta, tb;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5];
+
+  if (d->kind == JPDSE_CONVT3X3_S2) {
+    // A: (B,H,W,C) as {C, W, H, B}; +1 neighbours past the bottom/right edge are TMA zero fill
+    dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = B;
+    strides[0] = C * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
+    box[0] = 64; box[1] = p.tile_w; box[2] = p.tile_h; box[3] = 1;
+    rc = make_tmap(&ta, xin, 4, dims, strides, box);
+    if (rc != JPDSE_OK) return rc;
+    p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
+    p.os_h = p.os_w = 2;
+    size_t k_elems_before = 0;  // rows * K of the previous phase blocks
+    for (int pidx = 0; pidx < 4; ++pidx) {
+      const int ph = pidx >> 1, pw = pidx & 1;
+      int kh[2], dh[2], kw[2], dw[2];
+      const int nth = convt_taps(ph, kh, dh), ntw = convt_taps(pw, kw, dw);
+      p.ntaps = nth * ntw;
+      memset(p.tap_off, 0, sizeof(p.tap_off));
+      for (int i = 0; i < nth; ++i)
+        for (int j = 0; j < ntw; ++j) {
+          p.tap_off[i * ntw + j][1] = dw[j];
+          p.tap_off[i * ntw + j][2] = dh[i];
+        }
+      p.op_h = ph; p.op_w = pw;
+      const uint64_t kp = static_cast<uint64_t>(p.ntaps) * C;
+      uint64_t bd[2] = {kp, static_cast<uint64_t>(g.rows)};
+      uint64_t bs[1] = {kp * 2};
+      uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
+      rc = make_tmap(&tb, static_cast<const uint8_t*>(w_packed) + k_elems_before * 2, 2, bd, bs, bb);
+      if (rc != JPDSE_OK) return rc;
+      p.b_k_offset = 0;
+      rc = launch_igemm_bn(g.bn, ta, tb, p, stream);
+      if (rc != JPDSE_OK) return rc;
+      k_elems_before += static_cast<size_t>(g.rows) * kp;
+    }
+    return JPDSE_OK;
+  }
+
+  switch (d->kind) {
+    case JPDSE_CONV3X3_PAD1: {
+      xin = static_cast<const uint8_t*>(x);  // taps address the stored border directly
+      dims[0] = C; dims[1] = Wp; dims[2] = Hp; dims[3] = B;
+      strides[0] = C * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
+      box[0] = 64; box[1] = p.tile_w; box[2] = p.tile_h; box[3] = 1;
+      p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
+      p.ntaps = 9;
+      for (int t = 0; t < 9; ++t) {
+        p.tap_off[t][1] = t % 3;
+        p.tap_off[t][2] = t / 3;
+      }
+      break;
+    }
+    case JPDSE_CONV1X1: {
+      dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = B;
+      strides[0] = C * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
+      box[0] = 64; box[1] = p.tile_w; box[2] = p.tile_h; box[3] = 1;
+      p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
+      p.ntaps = 1;
+      break;
+    }
+    case JPDSE_CONV3X3_S2: {
+      // (B,H,W,C) viewed as {2C, W/2, 2, H/2, B}: a column pair is one 2C-wide "pixel", rows split
+      // into (pair, parity). Tap kh -> input row 2*oh+kh-1 = pair oh-1 parity 1 | pair oh parity 0 | 1.
+      dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+      strides[0] = 2 * C * 2; strides[1] = Wp * C * 2; strides[2] = 2 * Wp * C * 2; strides[3] = Hp * Wp * C * 2;
+      box[0] = 64; box[1] = p.tile_w; box[2] = 1; box[3] = p.tile_h; box[4] = 1;
+      p.a_rank = 5; p.dim_w = 1; p.dim_h = 3; p.dim_b = 4;
+      p.ntaps = 9;
+      for (int t = 0; t < 9; ++t) {
+        const int kh = t / 3, kw = t % 3;
+        p.tap_off[t][0] = (kw == 1) ? 0 : static_cast<int>(C);
+        p.tap_off[t][1] = (kw == 0) ? -1 : 0;
+        p.tap_off[t][2] = (kh == 1) ? 0 : 1;
+        p.tap_off[t][3] = (kh == 0) ? -1 : 0;
+      }
+      break;
+    }
+    case JPDSE_CONV7X7_PAD3: {
+      // one "tap" per filter row: the 7*C elements under a filter row are contiguous in NHWC, so
+      // the A operand is an overlapping-window view {7C (padded to cpt*64), W, H+6, B} with a
+      // pixel stride of C elements. Elements past 7*C meet zero weights.
+      xin = static_cast<const uint8_t*>(x);
+      dims[0] = static_cast<uint64_t>(g.cpt) * 64; dims[1] = W; dims[2] = Hp; dims[3] = B;
+      strides[0] = C * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
+      box[0] = 64; box[1] = p.tile_w; box[2] = p.tile_h; box[3] = 1;
+      p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
+      p.ntaps = 7;
+      for (int t = 0; t < 7; ++t) p.tap_off[t][2] = t;
+      break;
+    }
+  }
+  rc = make_tmap(&ta, xin, p.a_rank, dims, strides, box);
+  if (rc != JPDSE_OK) return rc;
+  uint64_t bd[2] = {static_cast<uint64_t>(g.ktot), static_cast<uint64_t>(g.rows)};
+  uint64_t bs[1] = {static_cast<uint64_t>(g.ktot) * 2};
+  uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
+  rc = make_tmap(&tb, w_packed, 2, bd, bs, bb);
+  if (rc != JPDSE_OK) return rc;
+  return launch_igemm_bn(g.bn, ta, tb, p, stream);
+}

@@ -1,0 +1,230 @@
+"""Torch-tensor front end of the C ABI (include/jpdse_b200.h).
+
+PyTorch only supplies device memory and the current stream; every computation is a kernel of
+libjpdse_b200.so. Each wrapper validates device / dtype / contiguity and raises on any error --
+there is no fallback path.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (CONV1X1, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_PAD3, CONVT3X3_S2, EPI_BIAS_TANH_NCHW,
+                   EPI_RAW_STATS, EPI_SIGN_NCHW, ConvDesc, JpdseError, check)
+
+_LABEL_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.int64: 2}
+_INST_DTYPES = {torch.int32: 0, torch.int16: 1, torch.int64: 2, torch.float32: 3}
+
+# counts kernels launched through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise JpdseError("%s must be a CUDA tensor (jpdse_b200 has no CPU path)" % name)
+    if not t.is_contiguous():
+        raise JpdseError("%s must be contiguous" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise JpdseError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    return t
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# ------------------------------------------------------------------------------------------------ input build
+def build_input(label, instance, image, num_labels, pad=3, c_pad=None, nhwc=True, nchw=False, out_nhwc=None,
+                bad_count=None):
+    """One-hot + edge + concat (+reflect pad). See jpdse_build_input.
+
+    Returns (nhwc_or_None, nchw_or_None). `nhwc` is bf16 (B, H+2pad, W+2pad, c_pad) carved from a flat
+    buffer with 4 KiB of zeroed slack behind it (the 7x7 stem's window view over-reads by < 128 B).
+    """
+    lib = _lib.load()
+    _need(label, "label")
+    _need(instance, "instance")
+    _need(image, "image", torch.float32)
+    if label.dtype not in _LABEL_DTYPES:
+        raise JpdseError("label dtype %s not supported (float32, uint8, int64)" % label.dtype)
+    if instance.dtype not in _INST_DTYPES:
+        raise JpdseError("instance dtype %s not supported (int32, int16, int64, float32)" % instance.dtype)
+    B, _, H, W = image.shape
+    if tuple(label.shape) != (B, 1, H, W) or tuple(instance.shape) != (B, 1, H, W) or image.shape[1] != 3:
+        raise JpdseError("build_input: label/instance must be (B,1,H,W) and image (B,3,H,W)")
+    if c_pad is None:
+        c_pad = (num_labels + 4 + 7) // 8 * 8
+    o_nhwc = None
+    if nhwc:
+        o_nhwc = out_nhwc if out_nhwc is not None else alloc_nhwc(B, H + 2 * pad, W + 2 * pad, c_pad, image.device)
+    o_nchw = torch.empty((B, num_labels + 4, H, W), dtype=torch.float32, device=image.device) if nchw else None
+    check(lib.jpdse_build_input(_ptr(label), _LABEL_DTYPES[label.dtype], _ptr(instance), _INST_DTYPES[instance.dtype],
+                                _ptr(image), B, H, W, num_labels, _ptr(o_nhwc), pad, c_pad, _ptr(o_nchw),
+                                _ptr(bad_count), _stream()))
+    _count(int(nhwc) + int(nchw))
+    return o_nhwc, o_nchw
+
+
+def alloc_nhwc(B, H, W, C, device, slack_bytes=4096):
+    """bf16 (B,H,W,C) view over a zero-initialised flat buffer with trailing slack."""
+    n = B * H * W * C
+    flat = torch.zeros(n + slack_bytes // 2, dtype=torch.bfloat16, device=device)
+    return flat[:n].view(B, H, W, C)
+
+
+# ------------------------------------------------------------------------------------------------ convolutions
+class Conv:
+    """One convolution of the generator: descriptor + packed bf16 weights (+ bias for the head)."""
+
+    def __init__(self, kind, epilogue, batch, in_h, in_w, in_pad, cin, cin_real, cout, device):
+        self.lib = _lib.load()
+        self.desc = ConvDesc(kind, epilogue, batch, in_h, in_w, in_pad, cin, cin_real, cout)
+        nbytes = self.lib.jpdse_conv_packed_weight_bytes(ctypes.byref(self.desc))
+        if nbytes == 0:
+            raise JpdseError("conv descriptor rejected: %s" % self.lib.jpdse_last_error().decode())
+        self.w_packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=device)
+        self.bias = None
+        self.flops = self.lib.jpdse_conv_flops(ctypes.byref(self.desc))
+        self.kind, self.epilogue = kind, epilogue
+        self.out_hw = {CONV3X3_S2: (in_h // 2, in_w // 2), CONVT3X3_S2: (in_h * 2, in_w * 2)}.get(kind, (in_h, in_w))
+        self.cout = cout
+        self.batch = batch
+
+    def pack(self, weight, bias=None):
+        """weight: float32 torch layout (Conv2d (Cout,Cin,k,k) / ConvTranspose2d (Cin,Cout,k,k))."""
+        w = _need(weight.detach(), "weight", torch.float32)
+        check(self.lib.jpdse_conv_pack_weights(ctypes.byref(self.desc), _ptr(w), _ptr(self.w_packed), _stream()))
+        _count()
+        if bias is not None:
+            self.bias = _need(bias.detach(), "bias", torch.float32)
+
+    def forward(self, x, y, stats=None):
+        _need(x, "x", torch.bfloat16)
+        _need(y, "y")
+        check(self.lib.jpdse_conv_forward(ctypes.byref(self.desc), _ptr(x), _ptr(self.w_packed), _ptr(self.bias), _ptr(y),
+                                          _ptr(stats), _stream()))
+        _count(4 if self.kind == CONVT3X3_S2 else 1)
+        return y
+
+
+def instnorm_apply(raw, stats, out, batch, height, width, channels, pad, relu, residual=None, eps=1e-5):
+    lib = _lib.load()
+    _need(raw, "raw", torch.bfloat16)
+    _need(stats, "stats", torch.float64)
+    _need(out, "out", torch.bfloat16)
+    if residual is not None:
+        _need(residual, "residual", torch.bfloat16)
+    check(lib.jpdse_instnorm_apply(_ptr(raw), _ptr(stats), _ptr(residual), _ptr(out), batch, height, width, channels,
+                                   pad, int(bool(relu)), eps, _stream()))
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ layout
+def nchw_to_nhwc_bf16(x, pad_reflect=0, c_pad=None, out=None):
+    lib = _lib.load()
+    _need(x, "x", torch.float32)
+    B, C, H, W = x.shape
+    c_pad = C if c_pad is None else c_pad
+    if out is None:
+        out = alloc_nhwc(B, H + 2 * pad_reflect, W + 2 * pad_reflect, c_pad, x.device)
+    check(lib.jpdse_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), B, C, H, W, pad_reflect, c_pad, _stream()))
+    _count()
+    return out
+
+
+def nhwc_bf16_to_nchw(x, out=None):
+    lib = _lib.load()
+    _need(x, "x", torch.bfloat16)
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    check(lib.jpdse_nhwc_bf16_to_nchw_f32(_ptr(x), _ptr(out), B, C, H, W, _stream()))
+    _count()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ quantisers
+def round_f32(x):
+    lib = _lib.load()
+    _need(x, "x", torch.float32)
+    y = torch.empty_like(x)
+    check(lib.jpdse_round_f32(_ptr(x), _ptr(y), x.numel(), _stream()))
+    _count()
+    return y
+
+
+def sign_f32(x):
+    lib = _lib.load()
+    _need(x, "x", torch.float32)
+    y = torch.empty_like(x)
+    check(lib.jpdse_sign_f32(_ptr(x), _ptr(y), x.numel(), _stream()))
+    _count()
+    return y
+
+
+def softsign_f32(x, u):
+    lib = _lib.load()
+    _need(x, "x", torch.float32)
+    _need(u, "u", torch.float32)
+    if u.shape != x.shape:
+        raise JpdseError("softsign: noise must have the input's shape")
+    y = torch.empty_like(x)
+    check(lib.jpdse_softsign_f32(_ptr(x), _ptr(u), _ptr(y), x.numel(), _stream()))
+    _count()
+    return y
+
+
+def sign_to_bits(x):
+    lib = _lib.load()
+    _need(x, "x", torch.float32)
+    y = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    check(lib.jpdse_sign_to_bits_u8(_ptr(x), _ptr(y), x.numel(), _stream()))
+    _count()
+    return y
+
+
+def s2hvq_encode(x_rows, code_book, sigma, want_scores=False, want_index=False, want_one_hot=False, want_soft=False):
+    """x_rows: (rows, center_size) float32; returns dict of the requested outputs."""
+    lib = _lib.load()
+    _need(x_rows, "x", torch.float32)
+    _need(code_book, "code_book", torch.float32)
+    rows, d = x_rows.shape
+    L = code_book.shape[0]
+    if code_book.shape[1] != d:
+        raise JpdseError("s2hvq: x rows and code book centers differ in size")
+    dev = x_rows.device
+    out = {
+        "scores": torch.empty((rows, L), dtype=torch.float32, device=dev) if want_scores else None,
+        "index": torch.empty((rows,), dtype=torch.int64, device=dev) if want_index else None,
+        "one_hot": torch.empty((rows, L), dtype=torch.float32, device=dev) if want_one_hot else None,
+        "soft": torch.empty((rows, L), dtype=torch.float32, device=dev) if want_soft else None,
+    }
+    check(lib.jpdse_s2hvq_encode(_ptr(x_rows), _ptr(code_book), rows, d, L, float(sigma), _ptr(out["scores"]),
+                                 _ptr(out["index"]), _ptr(out["one_hot"]), _ptr(out["soft"]), _stream()))
+    _count()
+    return out
+
+
+def s2hvq_decode(code_raw_rows, code_book, want_index=False):
+    lib = _lib.load()
+    _need(code_raw_rows, "code_raw", torch.float32)
+    _need(code_book, "code_book", torch.float32)
+    rows, L = code_raw_rows.shape
+    d = code_book.shape[1]
+    if code_book.shape[0] != L:
+        raise JpdseError("s2hvq decode: code_raw last dim must equal the number of centers")
+    out = torch.empty((rows, d), dtype=torch.float32, device=code_raw_rows.device)
+    idx = torch.empty((rows,), dtype=torch.int64, device=out.device) if want_index else None
+    check(lib.jpdse_s2hvq_decode(_ptr(code_raw_rows), _ptr(code_book), rows, d, L, _ptr(out), _ptr(idx), _stream()))
+    _count()
+    return (out, idx) if want_index else out
