@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""Benchmark of the JPD-SE generator hot path on B200 (metric and config from BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--height H --width W] [--impl reference]
+
+A step = one forward of the semantic-aware pix2pixHD generator (fused one-hot/edge/concat input build +
+182.6 M-parameter GlobalGenerator) over one batch of synthetic Cityscapes-shaped inputs
+(BASELINE.json configs[1]: batch 16 at 1024x512, bf16 kernels, random-init weights).
+
+One JSON line on stdout (rank 0):
+  value    images/s, whole job, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e      images/s through the ctu-API call (trainer.get_img) with pinned HOST inputs and a device->host
+           read of the output image inside the timed region
+  roofline the residual-block 3x3 conv kernel (70 % of the FLOPs): algorithmic FLOPs / CUDA-event time
+  cpu_baseline  the CPU restatement of the reference path (oracle/) on this box's host cores
+`--impl reference` times that CPU path alone, with the same metric/config keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (1024x512 codec fwd)"
+RES_CONV_FLOPS_PER_IMAGE = 38654705664.0   # 2*2048*1024*9216
+FWD_FLOPS_PER_IMAGE = 988513566720.0
+
+
+def synth_inputs(batch, height, width, seed=1234, qf=36):
+    """tiled label/instance maps, uniform image, quantise+noise stand-in for BPG."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    th, tw = height // 32, width // 32
+    label = torch.randint(0, 34, (batch, 1, th, tw), generator=g).repeat_interleave(32, 2).repeat_interleave(32, 3)
+    inst = torch.randint(0, 50, (batch, 1, th, tw), generator=g).repeat_interleave(32, 2).repeat_interleave(32, 3)
+    image = torch.rand(batch, 3, height, width, generator=g) - 0.5
+    q, sigma = {33: (4, 0.01), 36: (6, 0.015), 39: (8, 0.02), 42: (12, 0.03)}[qf]
+    deg = torch.round((image + 0.5) * 255.0 / q) * q / 255.0 - 0.5 + torch.randn(image.shape, generator=g) * sigma
+    return label.float(), inst.int(), deg.clamp_(-0.5, 0.5)
+
+
+def make_opt():
+    return argparse.Namespace(model="pix2pixHD", gpu_ids=[0], is_train=False, num_labels=35,
+                              contain_dontcare_label=False, no_label=False, no_instance=False, no_feat=False,
+                              no_label_encoding=True, no_feat_encoding=True, no_generator_binarization=True,
+                              sem_masking=False, input_nc=3, num_out_channels=3, ngf=64, netG="global",
+                              n_downsample_global=4, n_blocks_global=9, n_local_enhancers=1, n_blocks_local=3,
+                              norm="instance", use_compressed=False)
+
+
+class ClockSampler:
+    """SM clocks / throttle reasons sampled by one long-lived `nvidia-smi -lms 100` while the timed region runs."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.t0 = self.t1 = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
+    def summary(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            out = ""
+        import datetime
+        rows = []
+        for ln in out.splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), f[3:7]))
+            except ValueError:
+                continue
+        inside = [r for r in rows if self.t0 is not None and self.t0 - 0.05 <= r[0] <= self.t1 + 0.05]
+        window = "timed region"
+        if not inside:  # region shorter than the sampling period: use the samples taken under load (warm-up included)
+            inside, window = [r for r in rows if r[1] > 0], "warm-up + timed region"
+        mhz = sorted(r[1] for r in inside)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3][i].lower().startswith("active") for r in inside)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": max([r[2] for r in inside] or [0]) or None,
+                "reasons": reasons, "samples": len(inside), "window": window}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", d.get("bf16_tflops")), d.get("bf16_tflops"), "measured"
+    return 1400.0, 1590.0, "fallback"
+
+
+def cpu_reference_time(batch, height, width, steps, warmup, weights=None):
+    """Times the CPU restatement of the reference forward (oracle/) on all host threads. Returns s/step."""
+    import torch
+    from oracle import generator_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    if weights is None:
+        import jpdse_b200  # noqa: F401
+        import importlib
+        nw = importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
+        torch.manual_seed(1234)
+        weights = nw.define_G(39, 3, 64, "global", 4, 9, 1, 3, "instance", gpu_ids=[]).state_dict()
+    label, inst, image = synth_inputs(batch, height, width)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            x = torch.from_numpy(orc.build_input(label.numpy(), inst.numpy(), image.numpy(), 35))
+            orc.generator_forward(weights, x, 4, 9)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel to the box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_b = 1  # bounded sample: one image per step
+    sec = cpu_reference_time(sample_b, args.height, args.width, args.steps, args.warmup)
+    v = sample_b / sec
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "batch 1 of the %dx%d workload per step, fp32, torch CPU (oneDNN), %d threads"
+                                       % (args.width, args.height, cores)},
+            "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "pix2pixHD-BPG QF36 semantic-aware generator inference, batch %d at %dx%d, 35-class label map "
+                        "+ instance edges + RGB, random-init weights" % (args.batch, args.width, args.height),
+            "batch_per_gpu": args.batch, "height": args.height, "width": args.width,
+            "l2": "inputs+activations per step are GBs >> 126 MB L2 (no flush needed)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--height", type=int, default=512)
+    ap.add_argument("--width", type=int, default=1024)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", action="store_true", help="print a per-kernel-type time breakdown to stderr")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import jpdse_b200  # noqa: F401  (raises if libjpdse_b200.so is missing)
+    import importlib
+    from jpdse_b200 import ops
+    trainers = importlib.import_module("jpd-se_b200.ctu.trainers")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    opt = make_opt()
+    opt.gpu_ids = [local]
+    torch.manual_seed(1234)
+    trainer = trainers.get_trainer(opt)(opt, "test")
+    netG = trainer.model.netG
+    B, H, W = args.batch, args.height, args.width
+    label, inst, image = synth_inputs(B, H, W, seed=1234 + rank)
+    d_label, d_inst, d_image = label.to(dev), inst.to(dev), image.to(dev)
+    plan = netG.plan_for(B, H, W, dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- device-resident throughput
+    with torch.no_grad():
+        sampler = ClockSampler(local) if rank == 0 else None
+        for _ in range(args.warmup):
+            plan.forward_from_maps(d_label, d_inst, d_image, 35)
+        barrier()
+        ops.launch_count = 0
+        # events around the residual-block convs (the roofline kernel), on the launching stream
+        res_events = []
+        res_convs = [cv for pair in plan.res for cv in pair]
+        orig_forward = {id(cv): cv.forward for cv in res_convs}
+
+        def timed(cv):
+            f = orig_forward[id(cv)]
+
+            def wrapped(x, y, stats=None):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = f(x, y, stats)
+                e1.record()
+                res_events.append((e0, e1))
+                return r
+            return wrapped
+        for cv in res_convs:
+            cv.forward = timed(cv)
+        barrier()
+        if sampler:
+            sampler.begin()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(args.steps):
+            plan.forward_from_maps(d_label, d_inst, d_image, 35)
+        end.record()
+        barrier()
+        if sampler:
+            sampler.end()
+        for cv in res_convs:
+            cv.forward = orig_forward[id(cv)]
+        launches = ops.launch_count
+        clocks = sampler.summary() if sampler else None
+    elapsed_ms = start.elapsed_time(end)
+    res_ms = sum(a.elapsed_time(b) for a, b in res_events) / max(len(res_events), 1)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---------------------------------------------------------------- end to end through the ctu API
+    pin = {k: v.pin_memory() for k, v in (("label", label), ("instance", inst), ("image", image))}
+    host_out = torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory()
+    with torch.no_grad():
+        for _ in range(2):
+            host_out.copy_(trainer.get_img(dict(pin)), non_blocking=True)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for _ in range(args.steps):
+            host_out.copy_(trainer.get_img(dict(pin)), non_blocking=True)
+        e2.record()
+        barrier()
+    e2e_ms = s2.elapsed_time(e2)
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in pin.values())
+    d2h = host_out.numel() * host_out.element_size()
+
+    if rank != 0:
+        return
+    sustained, burst, peak_kind = load_peaks()
+    scale = (H * W) / (512.0 * 1024.0)
+    res_flops = RES_CONV_FLOPS_PER_IMAGE * scale * B
+    achieved = res_flops / (res_ms * 1e-3) / 1e12 if res_ms > 0 else 0.0
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"kernel": "igemm_kernel<256> (ResnetBlock 3x3 conv 1024->1024)", "bound": "tensor",
+                         "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
+                         "frac_of_burst_peak": achieved / burst, "peak_source": peak_kind + " (bf16_tflops_sustained)",
+                         "launch_ms": res_ms, "flops_per_launch": res_flops, "traffic": None,
+                         "whole_forward_tflops": FWD_FLOPS_PER_IMAGE * scale * B / (ms_per_step * 1e-3) / 1e12}}
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sec = cpu_reference_time(1, H, W, steps=3, warmup=1, weights={k: v.cpu() for k, v in netG.state_dict().items()})
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": "3 timed forwards of batch 1 at %dx%d (same generator, fp32, torch CPU)" % (W, H)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

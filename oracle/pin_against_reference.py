@@ -1,0 +1,144 @@
+"""Pins the oracle to the reference and (re)generates tests/golden/*.npz.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/pin_against_reference.py
+
+It imports the UNMODIFIED reference modules, feeds both the reference and the oracle restatement the same
+seeded inputs, asserts bit-identical results on CPU, and stores small input/output vectors that the CPU
+test-suite (tests/test_oracle_golden.py) re-checks anywhere. Nothing here is product code.
+"""
+import functools
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("JPDSE_REFERENCE", "/root/reference")
+GOLDEN = os.environ.get("JPDSE_GOLDEN_DIR", os.path.join(ROOT, "tests", "golden"))
+
+
+def import_reference():
+    sys.path.insert(0, REF)
+    sys.path.insert(0, ROOT)
+    for m in ("skimage", "skimage.io"):  # imported but unused by ctu/data/ctu_dataset.py:14
+        sys.modules.setdefault(m, types.ModuleType(m))
+    from ctu.models.pix2pixHD_networks import networks
+    from ctu.models import pix2pixHD_model
+    from ctu.quantizers import binarize, round as round_mod, s2h_vq
+    return networks, pix2pixHD_model, binarize, round_mod, s2h_vq
+
+
+def main():
+    networks, p2p, binarize, round_mod, s2h_vq = import_reference()
+    from oracle import generator_oracle as orc
+    from oracle import quantizer_oracle as qorc
+    import importlib
+    ours = importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
+    os.makedirs(GOLDEN, exist_ok=True)
+    g = torch.Generator().manual_seed(20201234)
+
+    # ---------------------------------------------------------------- preprocess: one-hot / edges / concat
+    B, H, W, L = 2, 24, 40, 35
+    label = torch.randint(0, L, (B, 1, H // 4, W // 4), generator=g).repeat_interleave(4, 2).repeat_interleave(4, 3).float()
+    label[0, 0, 0, :5] = torch.tensor([0.0, 34.0, 33.999, 1.5, 0.99])  # .long() truncation cases
+    inst = torch.randint(0, 6, (B, 1, H // 8, W // 8), generator=g).repeat_interleave(8, 2).repeat_interleave(8, 3).int()
+    inst[1, 0, 5, 7] = 1000  # isolated pixel: 4-neighbour cross
+    image = torch.rand(B, 3, H, W, generator=g) - 0.5
+    opt = types.SimpleNamespace(use_compressed=False, no_label=False, num_labels=L, contain_dontcare_label=False,
+                                data_type=32, no_instance=False, sem_masking=False)
+    stub = types.SimpleNamespace(opt=opt, use_gpu=lambda: False, FloatTensor=torch.FloatTensor,
+                                 ByteTensor=torch.ByteTensor)
+    stub.get_edges = functools.partial(p2p.Pix2PixHDModel.get_edges, stub)
+    ref_pre = p2p.Pix2PixHDModel.preprocess(stub, {"label": label.clone(), "instance": inst.clone(), "image": image.clone()})
+    ref_concat = torch.cat((ref_pre["input_label"], ref_pre["real_image"]), dim=1)  # pix2pixHD_model.py:595
+    got = orc.build_input(label.numpy(), inst.numpy(), image.numpy(), L)
+    assert np.array_equal(got, ref_concat.numpy()), "oracle build_input != reference preprocess+concat"
+    np.savez_compressed(os.path.join(GOLDEN, "preprocess.npz"), label=label.numpy(), instance=inst.numpy(),
+                        image=image.numpy(), input_concat=ref_concat.numpy().astype(np.float32), num_labels=L)
+    print("preprocess: oracle == reference (bit-exact); golden written")
+
+    # ---------------------------------------------------------------- generator forward
+    cfg = dict(input_nc=39, output_nc=3, ngf=64, n_down=4, n_blocks=2, seed=1234)
+    torch.manual_seed(cfg["seed"])
+    G = networks.define_G(cfg["input_nc"], cfg["output_nc"], cfg["ngf"], "global", cfg["n_down"], cfg["n_blocks"], 1, 3,
+                          "instance", gpu_ids=[]).eval()
+    torch.manual_seed(cfg["seed"])
+    G2 = ours.define_G(cfg["input_nc"], cfg["output_nc"], cfg["ngf"], "global", cfg["n_down"], cfg["n_blocks"], 1, 3,
+                       "instance", gpu_ids=[])
+    sd, sd2 = G.state_dict(), G2.state_dict()
+    assert list(sd.keys()) == list(sd2.keys()), "state-dict keys differ from the reference"
+    assert all(torch.equal(sd[k], sd2[k]) for k in sd), "same seed must give the reference's weights"
+    x = torch.randn(1, 39, 32, 64, generator=g)
+    with torch.no_grad():
+        y_ref = G(x)
+        y_orc = orc.generator_forward(sd, x, cfg["n_down"], cfg["n_blocks"])
+    assert torch.equal(y_ref, y_orc), "oracle generator != reference generator"
+    wsum = float(sum(v.double().sum() for v in sd.values()))
+    np.savez_compressed(os.path.join(GOLDEN, "generator_small.npz"), x=x.numpy(), y=y_ref.numpy(),
+                        weight_sum=wsum, **{k: np.int64(v) for k, v in cfg.items()})
+    print("generator: oracle == reference (bit-exact), our define_G reproduces the reference init; golden written")
+
+    # full-size architecture, tiny image: checks the 9-block / 1024-channel wiring
+    torch.manual_seed(1234)
+    Gf = networks.define_G(39, 3, 64, "global", 4, 9, 1, 3, "instance", gpu_ids=[]).eval()
+    xf = torch.randn(1, 39, 32, 64, generator=g)
+    with torch.no_grad():
+        assert torch.equal(Gf(xf), orc.generator_forward(Gf.state_dict(), xf, 4, 9))
+    print("generator (full 182.6M-param architecture): oracle == reference (bit-exact)")
+
+    # ---------------------------------------------------------------- quantisers
+    q = (torch.randn(4099, generator=g) * 3).float()
+    q[:10] = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, 1.4, 1.6, 0.0, -0.0, float("nan")])
+    r_ref = round_mod.RoundedIdentity.apply(q)
+    assert np.array_equal(qorc.rounded_identity(q.numpy()), r_ref.numpy(), equal_nan=True)
+    ds = binarize.DifferentiableSign().eval()
+    s_ref = ds(q)
+    assert np.array_equal(qorc.sign(q.numpy()), s_ref.numpy())
+    # stochastic sign: same RNG stream -> same uniform draw
+    xs = torch.tanh(torch.randn(4099, generator=g))
+    torch.manual_seed(99)
+    ss_ref = binarize.SoftSignFunction.apply(xs)
+    torch.manual_seed(99)
+    u = xs.new(xs.size()).uniform_()
+    assert np.array_equal(qorc.soft_sign(xs.numpy(), u.numpy()), ss_ref.numpy())
+    # binarizer
+    torch.manual_seed(5)
+    bz = binarize.Binarizer(64, 16).eval()
+    xb = torch.randn(1, 64, 8, 16, generator=g)
+    with torch.no_grad():
+        b_ref = bz(xb)
+    assert torch.equal(qorc.binarizer_eval(xb, bz.conv.weight.detach()), b_ref)
+    # S2HVQ: dyadic inputs -> every fp32 operation is exact, so indices/scores are summation-order independent
+    n, code_len, csz, ncen = 6, 5, 8, 16
+    cb = torch.randint(-8, 9, (ncen, csz), generator=g).float() / 4
+    cb[3] = cb[1]  # duplicated center: argmin/argmax ties must resolve to the first index
+    xv = torch.randint(-8, 9, (n, code_len * csz), generator=g).float() / 4
+    vq = s2h_vq.S2HVQ(cb.clone(), sigma=1.5)
+    with torch.no_grad():
+        xm = vq._vec2mtrx(xv, code_len)
+        sc_ref = vq._get_score_mtrx(xm)
+        hard_ref = vq.encode(xv, code_len, train=False, raw=True)
+        idx_ref = vq.encode(xv, code_len, train=False, raw=False)
+        soft_ref = vq.encode(xv, code_len, train=True, raw=True)
+        dec_ref = vq.decode(hard_ref)
+    assert torch.equal(qorc.s2hvq_scores(xm, cb), sc_ref)
+    o_idx, o_hard = qorc.s2hvq_hard(xm, cb)
+    assert torch.equal(o_idx, idx_ref) and torch.equal(o_hard, hard_ref)
+    assert torch.equal(qorc.s2hvq_soft(xm, cb, 1.5), soft_ref)
+    assert torch.equal(qorc.s2hvq_decode(hard_ref, cb)[0], dec_ref)
+    np.savez_compressed(os.path.join(GOLDEN, "quantizers.npz"), q=q.numpy(), round=r_ref.numpy(), sign=s_ref.numpy(),
+                        ss_x=xs.numpy(), ss_u=u.numpy(), ss_y=ss_ref.numpy(), bin_x=xb.numpy(),
+                        bin_w=bz.conv.weight.detach().numpy(), bin_y=b_ref.numpy(), vq_x=xv.numpy(), vq_cb=cb.numpy(),
+                        vq_code_len=code_len, vq_sigma=1.5, vq_scores=sc_ref.numpy(), vq_hard=hard_ref.numpy(),
+                        vq_index=idx_ref.numpy(), vq_soft=soft_ref.numpy(), vq_decoded=dec_ref.numpy())
+    # the reference's own smoke values (round.py:17-32): 1.5 -> 2, 1.4 -> 1, 1.6 -> 2
+    assert qorc.rounded_identity(np.array([1.5, 1.4, 1.6], dtype=np.float32)).tolist() == [2.0, 1.0, 2.0]
+    print("quantisers: oracle == reference (bit-exact); golden written")
+
+
+if __name__ == "__main__":
+    main()

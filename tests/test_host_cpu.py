@@ -1,0 +1,127 @@
+"""CPU: the C-ABI library loads and exports every symbol of include/jpdse_b200.h; the ctu-API mirror keeps the
+reference's names / keys / error behaviour; nothing computes without a GPU."""
+import argparse
+import ctypes
+import importlib
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "jpdse_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(jpdse_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+    import jpdse_b200
+    lib = jpdse_b200._lib.load()
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "libjpdse_b200.so does not export %s" % n
+    # every declared function has a ctypes signature and vice versa
+    assert sorted(jpdse_b200._lib.SIGNATURES) == names
+    assert lib.jpdse_abi_version() == 1
+    assert lib.jpdse_last_error() is not None
+
+
+def test_conv_desc_validation_without_gpu():
+    import jpdse_b200
+    from jpdse_b200._lib import CONV3X3_PAD1, CONV7X7_PAD3, EPI_RAW_STATS, ConvDesc
+    lib = jpdse_b200._lib.load()
+    assert ctypes.sizeof(ConvDesc) == 9 * 4
+    good = ConvDesc(CONV3X3_PAD1, EPI_RAW_STATS, 16, 32, 64, 1, 1024, 1024, 1024)
+    assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(good)) == 1024 * 9 * 1024 * 2
+    assert lib.jpdse_conv_flops(ctypes.byref(good)) == 16 * 38654705664.0
+    stem = ConvDesc(CONV7X7_PAD3, EPI_RAW_STATS, 1, 512, 1024, 3, 40, 39, 64)
+    assert lib.jpdse_conv_flops(ctypes.byref(stem)) == 128245039104.0
+    bad = ConvDesc(CONV3X3_PAD1, EPI_RAW_STATS, 1, 32, 64, 1, 100, 100, 64)  # cin not a multiple of 64
+    assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(bad)) == 0
+    assert b"multiple of 64" in lib.jpdse_last_error()
+    bad2 = ConvDesc(CONV3X3_PAD1, EPI_RAW_STATS, 1, 32, 64, 0, 64, 64, 64)  # PAD1 kind needs the border
+    assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(bad2)) == 0
+
+
+def _networks():
+    return importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
+
+
+def test_define_g_matches_reference_layout():
+    nw = _networks()
+    torch.manual_seed(0)
+    net = nw.define_G(39, 3, 64, "global", 4, 9, 1, 3, "instance", gpu_ids=[])
+    sd = net.state_dict()
+    assert sum(p.numel() for p in net.parameters()) == 182556163
+    assert len(sd) == 56
+    want = ["model.%d" % i for i in (1, 4, 7, 10, 13)] + \
+           ["model.%d.conv_block.%d" % (i, j) for i in range(16, 25) for j in (1, 5)] + \
+           ["model.%d" % i for i in (25, 28, 31, 34, 38)]
+    assert sorted(sd) == sorted(k + s for k in want for s in (".weight", ".bias"))
+    assert tuple(sd["model.25.weight"].shape) == (1024, 512, 3, 3)  # ConvTranspose2d layout (Cin,Cout,3,3)
+    assert tuple(sd["model.1.weight"].shape) == (64, 39, 7, 7)
+    assert abs(float(sd["model.16.conv_block.1.weight"].std()) - 0.02) < 1e-3  # weights_init N(0, 0.02)
+
+
+def test_reference_error_behaviour():
+    nw = _networks()
+    with pytest.raises(TypeError):  # the reference's bare raise('generator not implemented!')
+        nw.define_G(39, 3, 64, "nope")
+    with pytest.raises(NotImplementedError):
+        nw.get_norm_layer("foo")
+    net = nw.define_G(39, 3, 64, "global", 1, 0)
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 39, 8, 8), mode="bogus")
+    with pytest.raises(AttributeError):
+        net(torch.zeros(1, 39, 8, 8), mode="get_binary_code")
+
+
+def test_no_cpu_fallback():
+    import jpdse_b200
+    nw = _networks()
+    net = nw.define_G(39, 3, 64, "global", 1, 0).eval()
+    with torch.no_grad(), pytest.raises(jpdse_b200.JpdseError):
+        net(torch.zeros(1, 39, 128, 128))
+    from jpdse_b200 import ops
+    with pytest.raises(jpdse_b200.JpdseError):
+        ops.round_f32(torch.zeros(4))
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "jpd-se_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|import_module\([\"']oracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(text), "%s imports the oracle" % os.path.join(dirpath, f)
+
+
+def test_trainer_lookup_and_modes():
+    trainers = importlib.import_module("jpd-se_b200.ctu.trainers")
+    opt = argparse.Namespace(model="pix2pixHD")
+    cls = trainers.get_trainer(opt)
+    assert cls.__name__ == "Pix2PixHDTrainer"
+    with pytest.raises(ValueError):
+        trainers.get_trainer(argparse.Namespace(model="pix2pixHD")).__init__(cls.__new__(cls), opt, "bogus")
+    with pytest.raises(ModuleNotFoundError):
+        trainers.get_trainer(argparse.Namespace(model="toderici2017"))
+
+
+def test_s2hvq_mirror_argument_errors():
+    s2h = importlib.import_module("jpd-se_b200.ctu.quantizers.s2h_vq")
+    vq = s2h.S2HVQ(torch.zeros(4, 2), sigma=2.0)
+    assert vq.center_size == 2 and vq.sigma == 2.0
+    with pytest.raises(ValueError):
+        vq.encode(torch.zeros(3, 4), code_len=8)
+    with pytest.raises(ValueError):
+        vq.encode(torch.zeros(3, 5), code_len=2)
+    with pytest.raises(ValueError):
+        vq.encode(torch.zeros(3, 8), code_len=2)  # center size 4 != code book's 2
+    with pytest.raises(AssertionError):
+        s2h.S2HVQ(torch.zeros(4, 2), sigma=0.0)

@@ -1,0 +1,22 @@
+"""CPU, only where /root/reference exists (the build container): re-runs the pin of the oracle against the
+imported, unmodified reference. On the GPU box the reference is absent and these tests skip; the golden
+vectors it produced are checked by test_oracle_golden.py everywhere."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "ctu")), reason="reference tree not mounted here")
+def test_oracle_is_bit_identical_to_reference(tmp_path):
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1", JPDSE_GOLDEN_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "pin_against_reference.py")], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "preprocess: oracle == reference" in r.stdout
+    assert "generator: oracle == reference" in r.stdout
+    assert "quantisers: oracle == reference" in r.stdout
