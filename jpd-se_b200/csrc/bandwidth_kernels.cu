@@ -171,7 +171,7 @@ instnorm_apply_kernel(const __nv_bfloat16* __restrict__ raw, const double* __res
       double var = st[2 * j + 1] * inv_n - m * m;  // biased variance, fp64 so E[x^2]-E[x]^2 does not cancel
       if (var < 0.0) var = 0.0;
       mean[j] = static_cast<float>(m);
-      rstd[j] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      rstd[j] = rsqrtf(static_cast<float>(var) + eps);  // fp32 like the reference's invstd
     }
   }
   const int pix0 = blockIdx.x * (ppi * kNormIters);

@@ -22,6 +22,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "conv_shared.cuh"
 #include "ptx.cuh"
 
 namespace jpdse {
@@ -65,22 +66,6 @@ struct IgemmCfg {
 };
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
-// Column sums over the 32 lanes of a warp for 32 per-lane values: after the butterfly lane l holds
-// sum over lanes of v[l]. 31 shuffles instead of 32*5.
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool upper = (lane & s) != 0;
-#pragma unroll
-    for (int j = 0; j < s; ++j) {
-      const float send = upper ? v[j] : v[j + s];
-      const float keep = upper ? v[j + s] : v[j];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -337,9 +322,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor map, 128-byte swizzle, zero OOB fill. dims/box innermost first; strides (bytes) for dims 1..rank-1.
-static int make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box) {
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                   const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (fn == nullptr) return fail(JPDSE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[5], gstr[4];
@@ -388,16 +372,7 @@ static int convt_taps(int phase, int kk[2], int dd[2]) {
   return 2;
 }
 
-struct ConvGeom {
-  int out_h, out_w;      // output spatial dims
-  int gemm_h, gemm_w;    // pixel grid the GEMM M dimension runs over (== out dims except ConvT: input dims)
-  int ktot;              // packed K per output channel (sum over phases for ConvT)
-  int rows;              // packed rows (cout rounded up to BN)
-  int bn;
-  int cpt;               // chunks per tap
-};
-
-static int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
+int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
   if (d == nullptr) return fail(JPDSE_ERR_INVALID, "conv desc is NULL");
   if (d->batch <= 0 || d->in_h <= 0 || d->in_w <= 0 || d->cin <= 0 || d->cout <= 0 || d->cin_real <= 0 ||
       d->cin_real > d->cin || d->in_pad < 0)
@@ -406,6 +381,7 @@ static int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
   if (d->kind == JPDSE_CONV7X7_PAD3 && d->in_pad != 3) return fail(JPDSE_ERR_INVALID, "CONV7X7_PAD3 needs in_pad == 3");
   g->bn = pick_bn(d->cout);
   g->rows = ((d->cout + g->bn - 1) / g->bn) * g->bn;
+  g->path = kPathIgemm;
   switch (d->kind) {
     case JPDSE_CONV3X3_PAD1:
     case JPDSE_CONV1X1:
@@ -438,6 +414,17 @@ static int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
       g->out_w = g->gemm_w = d->in_w;
       g->cpt = (7 * d->cin + 63) / 64;
       g->ktot = 7 * g->cpt * 64;
+      // full-resolution stem / head: row-stationary kernels (conv_rowstat.cu) when the shape allows
+      if (d->epilogue == JPDSE_EPI_BIAS_TANH_NCHW && d->cin == 64 && d->cout <= 4 && d->in_w >= 128) {
+        g->path = kPathRowHead;
+        g->rows = 7 * 32;  // [q = 6-kh][kw*cout+co padded to 32]
+        g->ktot = 64;
+      } else if (d->epilogue == JPDSE_EPI_RAW_STATS && d->cin == 40 && d->cout % 32 == 0 && d->cout <= 128 &&
+                 d->in_w % 128 == 0) {
+        g->path = kPathRowStem;
+        g->rows = (d->cout / 32) * 7 * 5 * 32;  // [split][kb][q = 6-kh][32 channels]
+        g->ktot = 64;
+      }
       break;
     default:
       return fail(JPDSE_ERR_INVALID, "conv desc: unknown kind %d", d->kind);
@@ -495,7 +482,7 @@ static int launch_igemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb,
 
 // ------------------------------------------------------------------------------------------ weight packing
 struct PackParams {
-  int kind, cin, cin_real, cout, rows, ktot, cpt;
+  int kind, cin, cin_real, cout, rows, ktot, cpt, path;
 };
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, PackParams q) {
@@ -503,7 +490,28 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     float val = 0.f;
-    if (q.kind == JPDSE_CONVT3X3_S2) {
+    if (q.path == kPathRowHead) {
+      // [q = 6 - kh][n = kw*cout + co (zero padded to 32)][c]
+      const int c = static_cast<int>(i % 64);
+      const int n = static_cast<int>((i / 64) % 32);
+      const int kh = 6 - static_cast<int>(i / (64 * 32));
+      const int kw = n / q.cout, co = n % q.cout;
+      if (kw < 7 && c < q.cin_real) val = w[((static_cast<size_t>(co) * q.cin_real + c) * 7 + kh) * 7 + kw];
+    } else if (q.path == kPathRowStem) {
+      // [split][kb][q = 6 - kh][n (32)][k (64)], element e = kb*64+k of the 7*cin window under filter row kh
+      const int k = static_cast<int>(i % 64);
+      size_t r = i / 64;
+      const int n = static_cast<int>(r % 32);
+      r /= 32;
+      const int kh = 6 - static_cast<int>(r % 7);
+      r /= 7;
+      const int kb = static_cast<int>(r % 5);
+      const int split = static_cast<int>(r / 5);
+      const int e = kb * 64 + k;
+      const int kw = e / q.cin, c = e % q.cin;
+      if (kw < 7 && c < q.cin_real)
+        val = w[((static_cast<size_t>(split * 32 + n) * q.cin_real + c) * 7 + kh) * 7 + kw];
+    } else if (q.kind == JPDSE_CONVT3X3_S2) {
       // layout: phase blocks [(ph,pw) = 00,01,10,11], each (rows x ntaps*cin) row-major
       size_t rem = i;
       int ph = 0, pw = 0, nt = 1;
@@ -567,7 +575,7 @@ extern "C" int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w,
   int rc = conv_geom(d, &g);
   if (rc != JPDSE_OK) return rc;
   if (w == nullptr || w_packed == nullptr) return fail(JPDSE_ERR_INVALID, "pack_weights: NULL pointer");
-  PackParams q{d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt};
+  PackParams q{d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt, g.path};
   const size_t total = static_cast<size_t>(g.rows) * g.ktot;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
@@ -587,6 +595,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       (reinterpret_cast<uintptr_t>(y) & 15))
     return fail(JPDSE_ERR_INVALID, "conv_forward: pointers must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (g.path != kPathIgemm) return rowconv_forward(d, g.path == kPathRowHead, x, w_packed, bias, y, stats, stream);
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -621,7 +630,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     dims[0] = C; dims[1] = W; dims[2] = H; dims[3] = B;
     strides[0] = C * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
     box[0] = 64; box[1] = p.tile_w; box[2] = p.tile_h; box[3] = 1;
-    rc = make_tmap(&ta, xin, 4, dims, strides, box);
+    rc = make_tmap_bf16(&ta, xin, 4, dims, strides, box);
     if (rc != JPDSE_OK) return rc;
     p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
     p.os_h = p.os_w = 2;
@@ -642,7 +651,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       uint64_t bd[2] = {kp, static_cast<uint64_t>(g.rows)};
       uint64_t bs[1] = {kp * 2};
       uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
-      rc = make_tmap(&tb, static_cast<const uint8_t*>(w_packed) + k_elems_before * 2, 2, bd, bs, bb);
+      rc = make_tmap_bf16(&tb, static_cast<const uint8_t*>(w_packed) + k_elems_before * 2, 2, bd, bs, bb);
       if (rc != JPDSE_OK) return rc;
       p.b_k_offset = 0;
       rc = launch_igemm_bn(g.bn, ta, tb, p, stream);
@@ -705,12 +714,12 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       break;
     }
   }
-  rc = make_tmap(&ta, xin, p.a_rank, dims, strides, box);
+  rc = make_tmap_bf16(&ta, xin, p.a_rank, dims, strides, box);
   if (rc != JPDSE_OK) return rc;
   uint64_t bd[2] = {static_cast<uint64_t>(g.ktot), static_cast<uint64_t>(g.rows)};
   uint64_t bs[1] = {static_cast<uint64_t>(g.ktot) * 2};
   uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
-  rc = make_tmap(&tb, w_packed, 2, bd, bs, bb);
+  rc = make_tmap_bf16(&tb, w_packed, 2, bd, bs, bb);
   if (rc != JPDSE_OK) return rc;
   return launch_igemm_bn(g.bn, ta, tb, p, stream);
 }

@@ -141,16 +141,18 @@ def _conv_case(ops, cuda, kind_name, B, H, W, cin, cout, cin_real=None, seed=0):
     ("convs2", 2, 16, 32, 64, 128), ("convs2", 1, 32, 64, 128, 256),
     ("convt", 2, 8, 16, 128, 64), ("convt", 1, 16, 32, 256, 128),
     ("conv7x7", 2, 8, 16, 40, 64, 39), ("conv7x7", 1, 16, 128, 40, 64, 39),
+    ("conv7x7", 2, 140, 256, 40, 64, 39),  # row-stationary stem path: 2 strips, a full and a ragged row chunk
 ])
 def test_conv_kinds(cuda, case):
     _conv_case(_ops(), cuda, *case, seed=len(case) + case[2])
 
 
-def test_head_conv_bias_tanh(cuda):
+@pytest.mark.parametrize("shape", [(2, 16, 64), (2, 16, 128), (2, 140, 256)])  # generic path / row path / ragged chunks
+def test_head_conv_bias_tanh(cuda, shape):
     ops = _ops()
     from jpdse_b200._lib import CONV7X7_PAD3, EPI_BIAS_TANH_NCHW
     g = torch.Generator().manual_seed(11)
-    B, H, W = 2, 16, 128
+    B, H, W = shape
     x = _bf(torch.randn(B, 64, H, W, generator=g))
     w = _bf(torch.randn(3, 64, 7, 7, generator=g) * 0.02)
     bias = torch.randn(3, generator=g) * 0.1

@@ -141,11 +141,13 @@ def stage_convt():
 
 
 def stage_stem():
-    return _run_conv("stem", 2, 8, 16, 40, 64, cin_real=39) and _run_conv("stem", 1, 16, 128, 40, 64, cin_real=39, seed=6)
+    return (_run_conv("stem", 2, 8, 16, 40, 64, cin_real=39) and _run_conv("stem", 1, 16, 128, 40, 64, cin_real=39, seed=6)
+            and _run_conv("stem", 2, 140, 256, 40, 64, cin_real=39, seed=8))
 
 
 def stage_head():
-    return _run_conv("head", 2, 8, 16, 64, 3) and _run_conv("head", 1, 16, 128, 64, 3, seed=7)
+    return (_run_conv("head", 2, 8, 16, 64, 3) and _run_conv("head", 1, 16, 128, 64, 3, seed=7)
+            and _run_conv("head", 2, 140, 256, 64, 3, seed=9))
 
 
 def _gen_case(B, H, W, n_down, n_blocks, seed=1234):
