@@ -15,10 +15,12 @@
 //     statistics (sum, sum of squares per (image, channel)) with a warp-shuffle transpose-reduce,
 //     or applies bias+tanh / sign for the two terminal convs.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
-// warps 2..5 = epilogue (TMEM lane quarter = warp_idx % 4).
+// Warp roles (320 threads): warps 0..3 and 4..7 = two epilogue warpgroups, one per TMEM accumulator buffer (TMEM
+// lane quarter = warp_idx % 4); warp 8 = TMA producer, warp 9 = TMEM owner + MMA issuer. For the low-K convs
+// (full-resolution ConvT / stride-2 layers) the epilogue, not the MMA, is the critical path.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -32,7 +34,11 @@ constexpr int kBlockK = 64;         // bf16 elements per k-block = one 128-byte 
 constexpr int kUmmaK = 16;          // K of one tcgen05.mma for 16-bit inputs
 constexpr int kABytes = kTileM * kBlockK * 2;
 constexpr int kMaxTaps = 9;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;       // two epilogue warpgroups (one per TMEM accumulator) + 2 control warps
+// The control warps get the HIGHEST warp ids: the sub-partition arbiter favours high ids, and the single TMA /
+// MMA threads are the critical path of the low-K convs.
+constexpr int kProducerWarp = 8;
+constexpr int kMmaWarp = 9;
 
 struct IgemmParams {
   // tile grid
@@ -52,6 +58,8 @@ struct IgemmParams {
   void* out;
   double* stats;
   const float* bias;
+  long long* dbg;  // optional per-CTA role wait counters (tools only), else nullptr
+  int dbg_flags;   // developer experiments: bit0 skip statistics, bit1 skip output stores
 };
 
 template <int BN>
@@ -60,8 +68,8 @@ struct IgemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int kRedFloats = 4 * BN * 2;  // per-warp column partials (sum, sumsq)
-  // 1024 B alignment slack + stages + reduction scratch + barriers
+  static constexpr int kRedFloats = 8 * 32 * 17;  // per-epilogue-warp transpose scratch: 32 rows x 16 bf16x2 (+1 pad)
+  // 1024 B alignment slack + stages + transpose scratch + barriers
   static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kRedFloats * 4 + 256;
 };
 
@@ -73,8 +81,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
              const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* s_red = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  // 1024 B alignment as an OFFSET from the shared window (keeps the pointer in the shared address space -> LDS/STS)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint32_t* s_red = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kRedFloats * 4);
   uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
@@ -85,7 +94,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -98,7 +107,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tmem_alloc<1>(tmem_slot, Cfg::kTmemCols);
     tmem_relinquish<1>();
   }
@@ -111,11 +120,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   const int m_tiles = p.batch * p.tiles_h * p.tiles_w;
   const int total_tiles = m_tiles * p.n_tiles;
 
-  if (warp == 0) {
+  if (warp == kProducerWarp) {
     // ================================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      long long dbg_prod = 0;
+      const long long dbg_t0 = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         int mt = tile / p.n_tiles;
@@ -134,7 +145,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           const int c3 = base[3] + p.tap_off[t][3];
           const int c4 = base[4] + p.tap_off[t][4];
           for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb) {
+            const long long tw0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (p.dbg) dbg_prod += clock64() - tw0;
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -151,22 +164,32 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           }
         }
       }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = dbg_prod;
+        p.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0;
+      }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(kTileM, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      long long dbg_full = 0, dbg_tempty = 0;
+      const long long dbg_t0 = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const long long tw0 = p.dbg ? clock64() : 0;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        if (p.dbg) dbg_tempty += clock64() - tw0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
         for (int kb = 0; kb < kblocks; ++kb) {
+          const long long tw1 = p.dbg ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (p.dbg) dbg_full += clock64() - tw1;
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_smem_desc_sw128(sa);
@@ -187,16 +210,46 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 2] = dbg_full;
+        p.dbg[blockIdx.x * 8 + 3] = dbg_tempty;
+        p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0;
+      }
     }
     __syncwarp();
   } else {
-    // ================================================================== epilogue (warps 2..5)
+    // ================================================================== epilogue (warps 0..3 / 4..7)
+    const int group = warp >> 2;         // epilogue warpgroup == TMEM accumulator buffer it drains
     const int quarter = warp & 3;        // TMEM lanes [32*quarter, 32*quarter+32)
     const int m = quarter * 32 + lane;   // tile row = output pixel within the tile
-    const int et = threadIdx.x - 64;     // 0..127
-    int acc = 0;
+    uint32_t* s_t = s_red + warp * (32 * 17);  // this warp's transpose scratch
+    const int acc = group;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // InstanceNorm statistics: running column sums in registers, flushed with one atomic per column when the
+    // (image, channel tile) changes -- at full resolution a CTA stays on one image for ~100 tiles.
+    constexpr int kChunks = BN >= 32 ? BN / 32 : 1;
+    float run_s1a[kChunks], run_s1b[kChunks], run_s2a[kChunks], run_s2b[kChunks];
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) run_s1a[ch] = run_s1b[ch] = run_s2a[ch] = run_s2b[ch] = 0.f;
+    int cur_b = -1, cur_n0 = 0;
+    auto flush = [&]() {
+      if (cur_b >= 0 && lane < 16) {
+#pragma unroll
+        for (int ch = 0; ch < kChunks; ++ch) {
+          double* st = p.stats + (static_cast<size_t>(cur_b) * p.ldc + cur_n0 + ch * 32 + lane * 2) * 2;
+          atomicAdd(st + 0, static_cast<double>(run_s1a[ch]));
+          atomicAdd(st + 1, static_cast<double>(run_s2a[ch]));
+          atomicAdd(st + 2, static_cast<double>(run_s1b[ch]));
+          atomicAdd(st + 3, static_cast<double>(run_s2b[ch]));
+          run_s1a[ch] = run_s1b[ch] = run_s2a[ch] = run_s2b[ch] = 0.f;
+        }
+      }
+    };
+    int tile_i = 0;
+    long long dbg_epi = 0;
+    const long long dbg_t0 = p.dbg ? clock64() : 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
+      if ((tile_i & 1) != group) continue;
       const int nt = tile % p.n_tiles;
       int mt = tile / p.n_tiles;
       const int tw = mt % p.tiles_w;
@@ -209,56 +262,68 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       const int ow = (tw * p.tile_w + c) * p.os_w + p.op_w;
       const int n0 = nt * BN;
 
-      mbar_wait(&tfull_bar[acc], acc_phase);
+      const long long tw2 = p.dbg ? clock64() : 0;
+      mbar_wait_parked(&tfull_bar[acc], acc_phase);
+      if (p.dbg) dbg_epi += clock64() - tw2;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
       if (p.epilogue == JPDSE_EPI_RAW_STATS) {
+        if (b != cur_b || n0 != cur_n0) {
+          flush();
+          cur_b = b;
+          cur_n0 = n0;
+        }
         __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
                               ((static_cast<size_t>(b) * p.out_h + oh) * p.out_w + ow) * p.ldc + n0;
         if constexpr (BN >= 32) {
-#pragma unroll 1
-          for (int ch = 0; ch < BN / 32; ++ch) {
+#pragma unroll
+          for (int ch = 0; ch < kChunks; ++ch) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr + ch * 32, v);
             tmem_ld_wait();
-            float f[32], q[32];
             uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
               pk[j] = *reinterpret_cast<uint32_t*>(&h);
-              f[2 * j] = __low2float(h);
-              f[2 * j + 1] = __high2float(h);
             }
             uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
+            if (!(p.dbg_flags & 2)) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            }
+            if (p.dbg_flags & 1) continue;
+            // column sums of the bf16-rounded tile through a 32x16-word shared transpose (bank-conflict free):
+            // lane l then owns column pair (l & 15) over rows 16*(l >> 4) .. +15
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) q[j] = f[j] * f[j];
-            const float s1 = warp_transpose_reduce(f, lane);
-            const float s2 = warp_transpose_reduce(q, lane);
-            s_red[((warp - 2) * BN + ch * 32 + lane) * 2 + 0] = s1;
-            s_red[((warp - 2) * BN + ch * 32 + lane) * 2 + 1] = s2;
+            for (int j = 0; j < 16; ++j) s_t[lane * 17 + j] = pk[j];
+            __syncwarp();
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+            const uint32_t* col = s_t + (lane >> 4) * (16 * 17) + (lane & 15);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const uint32_t w2 = col[t * 17];
+              const float lo = __uint_as_float(w2 << 16), hi = __uint_as_float(w2 & 0xffff0000u);
+              s1a += lo;
+              s1b += hi;
+              s2a = fmaf(lo, lo, s2a);
+              s2b = fmaf(hi, hi, s2b);
+            }
+            s1a += __shfl_xor_sync(0xffffffffu, s1a, 16);
+            s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
+            s2a += __shfl_xor_sync(0xffffffffu, s2a, 16);
+            s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
+            run_s1a[ch] += s1a;
+            run_s1b[ch] += s1b;
+            run_s2a[ch] += s2a;
+            run_s2b[ch] += s2b;
           }
         }
-        // accumulator drained: hand the TMEM buffer back before the cross-warp reduction
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int col = et; col < BN; col += 128) {
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            s1 += s_red[(w * BN + col) * 2 + 0];
-            s2 += s_red[(w * BN + col) * 2 + 1];
-          }
-          double* st = p.stats + (static_cast<size_t>(b) * p.ldc + n0 + col) * 2;
-          atomicAdd(st, static_cast<double>(s1));
-          atomicAdd(st + 1, static_cast<double>(s2));
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       } else {
         // terminal convs: few output channels, fp32 NCHW output
         if constexpr (BN <= 128) {
@@ -293,14 +358,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      acc_phase ^= 1;
+    }
+    if (p.epilogue == JPDSE_EPI_RAW_STATS) flush();
+    if (p.dbg && lane == 0 && (warp == 0 || warp == 4)) {
+      p.dbg[blockIdx.x * 8 + 5 + group] = dbg_epi;
+      if (group == 0) p.dbg[blockIdx.x * 8 + 7] = clock64() - dbg_t0;
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, Cfg::kTmemCols);
   }
@@ -452,6 +521,9 @@ static int pick_tile(int gh, int gw, int* th, int* tw) {
   return JPDSE_OK;
 }
 
+static long long* g_dbg = nullptr;  // role counters of the LAST igemm launch when enabled (tools/role_times.py)
+static bool g_dbg_enabled = false;
+
 template <int BN>
 static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN>;
@@ -556,6 +628,22 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 
 using namespace jpdse;
 
+// Developer instrumentation (not part of the documented ABI): per-CTA role wait cycles of the last
+// implicit-GEMM launch: [producer wait-empty, producer total, mma wait-full, mma wait-tmem-empty, mma total,
+// epilogue0 wait-tmem-full, epilogue1 wait-tmem-full, epilogue total] x 148 CTAs.
+extern "C" int jpdse_debug_role_counters(int enable, long long* host_out, int max_values) {
+  if (g_dbg == nullptr) {
+    if (cudaMalloc(&g_dbg, sizeof(long long) * 8 * 256) != cudaSuccess) return fail(JPDSE_ERR_CUDA, "debug buffer alloc failed");
+    cudaMemset(g_dbg, 0, sizeof(long long) * 8 * 256);
+  }
+  if (host_out != nullptr && max_values > 0) {
+    cudaDeviceSynchronize();
+    cudaMemcpy(host_out, g_dbg, sizeof(long long) * (max_values < 8 * 256 ? max_values : 8 * 256), cudaMemcpyDeviceToHost);
+  }
+  g_dbg_enabled = enable != 0;
+  return JPDSE_OK;
+}
+
 extern "C" size_t jpdse_conv_packed_weight_bytes(const jpdse_conv_desc* d) {
   ConvGeom g;
   if (conv_geom(d, &g) != JPDSE_OK) return 0;
@@ -615,6 +703,15 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   p.out = y;
   p.stats = stats;
   p.bias = bias;
+  p.dbg = g_dbg_enabled ? g_dbg : nullptr;
+  {
+    static int flags = -1;
+    if (flags < 0) {
+      const char* e = getenv("JPDSE_DEBUG_FLAGS");
+      flags = e ? atoi(e) : 0;
+    }
+    p.dbg_flags = flags;
+  }
 
   const uint64_t C = static_cast<uint64_t>(d->cin);
   const uint64_t H = static_cast<uint64_t>(d->in_h), W = static_cast<uint64_t>(d->in_w), B = static_cast<uint64_t>(d->batch);

@@ -16,7 +16,8 @@
 //          read through an overlapping-window tensor map (pixel stride 40 elements, 5 k-blocks of 64);
 //          N = 32 of the 64 output channels per CTA so that 7 x 5 x 4 KiB of weights fit in shared memory.
 //
-// Warp roles as in conv_igemm.cu: warp 0 TMA producer, warp 1 TMEM owner + MMA issuer, warps 2..5 epilogue.
+// Warp roles as in conv_igemm.cu: warps 0..3 / 4..7 two epilogue warpgroups that drain alternate output rows,
+// warp 8 TMA producer, warp 9 TMEM owner + MMA issuer.
 #include <cuda_bf16.h>
 
 #include <cstring>
@@ -31,7 +32,9 @@ constexpr int kRowN = 32;                          // accumulator columns per sl
 constexpr int kRowSlots = 16;                      // accumulator ring (7 live output rows + 9 draining / free)
 constexpr int kRowBTile = kRowN * 64 * 2;          // one (kb, q) weight tile, bytes; q = 6 - kh
 constexpr int kRowATile = 128 * 64 * 2;            // one A k-block, bytes
-constexpr int kRowThreads = 192;
+constexpr int kRowThreads = 320;                   // two epilogue warpgroups (alternate rows) + 2 control warps
+constexpr int kRowProducerWarp = 8;                // control warps take the highest ids (arbiter priority)
+constexpr int kRowMmaWarp = 9;
 
 struct RowConvParams {
   int batch, height, width;   // output = logical input size
@@ -49,7 +52,7 @@ template <int KB, bool kHead>
 struct RowCfg {
   static constexpr int kStages = kHead ? 8 : 4;
   static constexpr int kBBytes = 7 * KB * kRowBTile;
-  static constexpr int kScratchFloats = kHead ? 2 * 28 * 136 : 4 * kRowN * 2;
+  static constexpr int kScratchFloats = kHead ? 2 * 2 * 28 * 136 : 8 * 32 * 17;
   static constexpr int kSmemBytes = 1024 + kBBytes + kStages * kRowATile + kScratchFloats * 4 + 512;
 };
 
@@ -59,7 +62,8 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                const __grid_constant__ RowConvParams p) {
   using Cfg = RowCfg<KB, kHead>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024 B alignment as an OFFSET from the shared window (keeps the pointers in the shared address space)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_b = smem;                                   // resident weights
   uint8_t* s_a = smem + Cfg::kBBytes;                    // A ring
   float* s_scr = reinterpret_cast<float*>(s_a + Cfg::kStages * kRowATile);
@@ -74,7 +78,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kRowProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -88,7 +92,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     mbar_init(bfull_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == kRowMmaWarp) {
     tmem_alloc<1>(tmem_slot, kRowSlots * kRowN);
     tmem_relinquish<1>();
   }
@@ -103,9 +107,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int ctas = kHead ? static_cast<int>(gridDim.x) : static_cast<int>(gridDim.x) / p.n_splits;
   const int items = p.batch * p.strips * p.chunks;
 
-  if (warp == 0) {
+  if (warp == kRowProducerWarp) {
     // ================================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_arrive_expect_tx(bfull_bar, Cfg::kBBytes);
       for (int kb = 0; kb < KB; ++kb)
         tma_load_2d(&tm_b, bfull_bar, s_b + kb * 7 * kRowBTile, 0, (split * KB + kb) * 7 * kRowN);
@@ -139,9 +143,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == kRowMmaWarp) {
     // ================================================================== MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(bfull_bar, 0);
       tc_fence_after();
       const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(s_b));
@@ -214,10 +218,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
     __syncwarp();
   } else {
-    // ================================================================== epilogue (warps 2..5)
+    // ================================================================== epilogue (warps 0..3 / 4..7)
+    const int group = warp >> 2;          // warpgroup g drains the output rows whose running number is == g (mod 2)
     const int quarter = warp & 3;
     const int pos = quarter * 32 + lane;  // position inside the strip = TMEM lane
     uint32_t n0 = 0;
+    uint32_t grp_rows = 0;                // rows this group has drained (selects the head's double buffer)
     for (int item = cta; item < items; item += ctas) {
       const int chunk = item % p.chunks;
       const int strip = (item / p.chunks) % p.strips;
@@ -225,11 +231,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int r0 = chunk * p.chunk_rows;
       const int rows = min(p.chunk_rows, p.height - r0);
       const int ow = strip * p.strip_step + pos;
-      float acc1 = 0.f, acc2 = 0.f;  // stem: this lane's column statistics over the rows of the item
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;  // stem: column-pair statistics over this item's rows
       for (int j = 0; j < rows; ++j) {
         const uint32_t n = n0 + j;
+        if (static_cast<int>(n & 1) != group) continue;
         const int slot = n & (kRowSlots - 1);
-        mbar_wait(&tfull_bar[slot], (n / kRowSlots) & 1);
+        mbar_wait_parked(&tfull_bar[slot], (n / kRowSlots) & 1);
         tc_fence_after();
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * kRowN, v);
@@ -241,11 +248,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if constexpr (kHead) {
           // P[kw*cout+co][pos] -> shared (double buffered), then out[ow] = tanh(bias + sum_kw P[kw, co][pos + kw])
           const int np = 7 * p.cout;
-          float* sp = s_scr + (j & 1) * (28 * 136);
+          float* sp = s_scr + (group * 2 + static_cast<int>(grp_rows & 1)) * (28 * 136);
 #pragma unroll
           for (int q = 0; q < 28; ++q)
             if (q < np) sp[q * 136 + pos] = __uint_as_float(v[q]);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (group == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
           if (pos < p.strip_valid && ow < p.width) {
             const size_t plane = static_cast<size_t>(p.height) * p.width;
             float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(b) * p.cout * plane +
@@ -259,46 +267,52 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
               o[co * plane] = 1.f - __fdividef(2.f, e + 1.f);
             }
           }
-          // the next row writes the other buffer; the row after that is ordered behind the next barrier
+          // this group's next row writes the other buffer; the one after that is ordered behind the next barrier
         } else {
           __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
                                 ((static_cast<size_t>(b) * p.height + oh) * p.width + ow) * p.cout + split * kRowN;
-          float f[32], q2[32];
           uint32_t pk[16];
 #pragma unroll
           for (int t = 0; t < 16; ++t) {
             __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * t]), __uint_as_float(v[2 * t + 1]));
             pk[t] = *reinterpret_cast<uint32_t*>(&h);
-            f[2 * t] = __low2float(h);
-            f[2 * t + 1] = __high2float(h);
           }
           uint4* dst = reinterpret_cast<uint4*>(orow);
 #pragma unroll
           for (int t = 0; t < 4; ++t) dst[t] = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          // column sums through a per-warp 32x16-word shared transpose: lane l owns column pair (l & 15) over
+          // rows 16*(l >> 4) .. +15 (see conv_igemm.cu)
+          uint32_t* s_t = reinterpret_cast<uint32_t*>(s_scr) + warp * (32 * 17);
+          __syncwarp();
 #pragma unroll
-          for (int t = 0; t < 32; ++t) q2[t] = f[t] * f[t];
-          acc1 += warp_transpose_reduce(f, lane);
-          acc2 += warp_transpose_reduce(q2, lane);
+          for (int t = 0; t < 16; ++t) s_t[lane * 17 + t] = pk[t];
+          __syncwarp();
+          const uint32_t* col = s_t + (lane >> 4) * (16 * 17) + (lane & 15);
+#pragma unroll
+          for (int t = 0; t < 16; ++t) {
+            const uint32_t w2 = col[t * 17];
+            const float lo = __uint_as_float(w2 << 16), hi = __uint_as_float(w2 & 0xffff0000u);
+            s1a += lo;
+            s1b += hi;
+            s2a = fmaf(lo, lo, s2a);
+            s2b = fmaf(hi, hi, s2b);
+          }
         }
+        ++grp_rows;
       }
       if constexpr (!kHead) {
-        // one (sum, sumsq) atomic pair per column per item
-        s_scr[((warp - 2) * kRowN + lane) * 2 + 0] = acc1;
-        s_scr[((warp - 2) * kRowN + lane) * 2 + 1] = acc2;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        const int et = threadIdx.x - 64;
-        if (et < kRowN) {
-          float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            s1 += s_scr[(w * kRowN + et) * 2 + 0];
-            s2 += s_scr[(w * kRowN + et) * 2 + 1];
-          }
-          double* st = p.stats + (static_cast<size_t>(b) * p.cout + split * kRowN + et) * 2;
-          atomicAdd(st, static_cast<double>(s1));
-          atomicAdd(st + 1, static_cast<double>(s2));
+        // one atomic per column per warp per item
+        s1a += __shfl_xor_sync(0xffffffffu, s1a, 16);
+        s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
+        s2a += __shfl_xor_sync(0xffffffffu, s2a, 16);
+        s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
+        if (lane < 16) {
+          double* st = p.stats + (static_cast<size_t>(b) * p.cout + split * kRowN + lane * 2) * 2;
+          atomicAdd(st + 0, static_cast<double>(s1a));
+          atomicAdd(st + 1, static_cast<double>(s2a));
+          atomicAdd(st + 2, static_cast<double>(s1b));
+          atomicAdd(st + 3, static_cast<double>(s2b));
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
       n0 += rows;
     }
@@ -306,7 +320,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kRowMmaWarp) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, kRowSlots * kRowN);
   }
