@@ -68,12 +68,19 @@ enum jpdse_conv_kind {
   JPDSE_CONVT3X3_S2 = 2,    /* ConvTranspose 3x3 s2 p1 op1: x is (B,H,W,Cin), out (B,2H,2W,Cout)     */
   JPDSE_CONV7X7_PAD3 = 3,   /* 7x7 stride 1 on an input already padded by 3: x is (B,H+6,W+6,Cin);   */
                             /* Cin*2 bytes must be a multiple of 16 (Cin = 40 for the stem, 64 head) */
-  JPDSE_CONV1X1 = 4         /* 1x1: x is (B,H,W,Cin)                                                 */
+  JPDSE_CONV1X1 = 4,        /* 1x1: x is (B,H,W,Cin)                                                 */
+  /* data-gradient kinds (backward of the two "PAD" kinds): full correlation with the flipped,       */
+  /* channel-transposed filter. x is the output gradient stored with a ZERO border of 2 (6):         */
+  /* (B,H+4,W+4,Cin) -> y (B,H+2,W+2,Cout) = gradient w.r.t. the PADDED forward input. The weight    */
+  /* handed to jpdse_conv_pack_weights is the FORWARD conv's (Cin_this = Cout_fwd, Cout_this = Cin_fwd) */
+  JPDSE_CONV3X3_FULL = 5,
+  JPDSE_CONV7X7_FULL = 6    /* x (B,H+12,W+12,Cin) with Cin*2 bytes a multiple of 16 and 7*Cin <= 64 */
 };
 enum jpdse_conv_epilogue {
   JPDSE_EPI_RAW_STATS = 0,      /* y = bf16 NHWC raw conv output, stats += (sum, sumsq) per (b,c)    */
   JPDSE_EPI_BIAS_TANH_NCHW = 1, /* y = float32 NCHW tanh(conv + bias)            (networks.py:246)   */
-  JPDSE_EPI_SIGN_NCHW = 2       /* y = float32 NCHW sign(tanh(conv))             (binarize.py:51-54) */
+  JPDSE_EPI_SIGN_NCHW = 2,      /* y = float32 NCHW sign(tanh(conv))             (binarize.py:51-54) */
+  JPDSE_EPI_RAW = 3             /* y = bf16 NHWC, no statistics (gradients)                           */
 };
 typedef struct jpdse_conv_desc {
   int kind;      /* enum jpdse_conv_kind */

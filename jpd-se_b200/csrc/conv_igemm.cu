@@ -50,6 +50,8 @@ struct IgemmParams {
   int a_rank, dim_w, dim_h, dim_b;
   int tap_off[kMaxTaps][5];
   int b_k_offset;  // first k element of this launch inside the packed weight matrix (ConvT phases)
+  int flat_pitch;  // > 0: "flat" mode -- M runs over flat positions y*pitch+x of a padded image (any H, W);
+                   // rows with y >= out_h or x >= out_w are computed but neither stored nor counted
   // output addressing
   int out_h, out_w, os_h, os_w, op_h, op_w;
   int ldc;      // channels of the output tensor
@@ -152,7 +154,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             uint8_t* sb = sa + kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             const int c0 = base[0] + p.tap_off[t][0] + ch * kBlockK;
-            if (p.a_rank == 4)
+            if (p.a_rank == 3)
+              tma_load_3d(&tm_a, &full_bar[stage], sa, c0, c1, c2);
+            else if (p.a_rank == 4)
               tma_load_4d(&tm_a, &full_bar[stage], sa, c0, c1, c2, c3);
             else
               tma_load_5d(&tm_a, &full_bar[stage], sa, c0, c1, c2, c3, c4);
@@ -258,8 +262,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       const int b = mt / p.tiles_h;
       const int r = m / p.tile_w;
       const int c = m - r * p.tile_w;
-      const int oh = (th * p.tile_h + r) * p.os_h + p.op_h;
-      const int ow = (tw * p.tile_w + c) * p.os_w + p.op_w;
+      int oh = (th * p.tile_h + r) * p.os_h + p.op_h;
+      int ow = (tw * p.tile_w + c) * p.os_w + p.op_w;
+      bool valid = true;
+      if (p.flat_pitch > 0) {  // flat mode: ow is the flat position
+        oh = ow / p.flat_pitch;
+        ow -= oh * p.flat_pitch;
+        valid = oh < p.out_h && ow < p.out_w;
+      }
       const int n0 = nt * BN;
 
       const long long tw2 = p.dbg ? clock64() : 0;
@@ -268,8 +278,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
-      if (p.epilogue == JPDSE_EPI_RAW_STATS) {
-        if (b != cur_b || n0 != cur_n0) {
+      if (p.epilogue == JPDSE_EPI_RAW_STATS || p.epilogue == JPDSE_EPI_RAW) {
+        const bool want_stats = p.epilogue == JPDSE_EPI_RAW_STATS;
+        if (want_stats && (b != cur_b || n0 != cur_n0)) {
           flush();
           cur_b = b;
           cur_n0 = n0;
@@ -289,11 +300,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
               pk[j] = *reinterpret_cast<uint32_t*>(&h);
             }
             uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
-            if (!(p.dbg_flags & 2)) {
+            if (valid && !(p.dbg_flags & 2)) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
             }
-            if (p.dbg_flags & 1) continue;
+            if (!want_stats || (p.dbg_flags & 1)) continue;
+            if (!valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) pk[j] = 0u;
+            }
             // column sums of the bf16-rounded tile through a 32x16-word shared transpose (bank-conflict free):
             // lane l then owns column pair (l & 15) over rows 16*(l >> 4) .. +15
             __syncwarp();
@@ -452,6 +467,22 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
   g->rows = ((d->cout + g->bn - 1) / g->bn) * g->bn;
   g->path = kPathIgemm;
   switch (d->kind) {
+    case JPDSE_CONV3X3_FULL:
+      if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv full: cin must be a multiple of 64 (got %d)", d->cin);
+      if (d->in_pad != 2) return fail(JPDSE_ERR_INVALID, "CONV3X3_FULL needs in_pad == 2");
+      g->out_h = g->gemm_h = d->in_h + 2;
+      g->out_w = g->gemm_w = d->in_w + 2;
+      g->cpt = d->cin / 64;
+      g->ktot = 9 * d->cin;
+      break;
+    case JPDSE_CONV7X7_FULL:
+      if ((d->cin * 2) % 16 || 7 * d->cin > 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv7x7 full: need cin*2 %% 16 == 0 and 7*cin <= 64");
+      if (d->in_pad != 6) return fail(JPDSE_ERR_INVALID, "CONV7X7_FULL needs in_pad == 6");
+      g->out_h = g->gemm_h = d->in_h + 6;
+      g->out_w = g->gemm_w = d->in_w + 6;
+      g->cpt = 1;
+      g->ktot = 7 * 64;
+      break;
     case JPDSE_CONV3X3_PAD1:
     case JPDSE_CONV1X1:
       if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv: cin must be a multiple of 64 (got %d)", d->cin);
@@ -498,7 +529,7 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
     default:
       return fail(JPDSE_ERR_INVALID, "conv desc: unknown kind %d", d->kind);
   }
-  if (d->epilogue == JPDSE_EPI_RAW_STATS) {
+  if (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW) {
     if (d->cout % g->bn || g->bn < 32)
       return fail(JPDSE_ERR_UNSUPPORTED, "raw+stats epilogue needs cout %% %d == 0 (got %d)", g->bn, d->cout);
   } else if (d->epilogue == JPDSE_EPI_BIAS_TANH_NCHW || d->epilogue == JPDSE_EPI_SIGN_NCHW) {
@@ -607,7 +638,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
     } else {
       const int n = static_cast<int>(i / q.ktot);
       const int k = static_cast<int>(i % q.ktot);
-      if (q.kind == JPDSE_CONV7X7_PAD3) {
+      if (q.kind == JPDSE_CONV3X3_FULL) {
+        // W'[n = ci_fwd][t' = kh'*3+kw'][c = co_fwd] = W_fwd[co_fwd][ci_fwd][2-kh'][2-kw']
+        const int t = k / q.cin, c = k % q.cin;
+        const int kh = 2 - t / 3, kw = 2 - t % 3;
+        if (n < q.cout && c < q.cin_real) val = w[((static_cast<size_t>(c) * q.cout + n) * 3 + kh) * 3 + kw];
+      } else if (q.kind == JPDSE_CONV7X7_FULL) {
+        // per filter row kh': window element e = kw'*cin + c ; W'[n][kh'][e] = W_fwd[c][n][6-kh'][6-kw']
+        const int khp = k / 64, e = k % 64;
+        const int kwp = e / q.cin, c = e % q.cin;
+        if (n < q.cout && kwp < 7 && c < q.cin_real)
+          val = w[((static_cast<size_t>(c) * q.cout + n) * 7 + (6 - khp)) * 7 + (6 - kwp)];
+      } else if (q.kind == JPDSE_CONV7X7_PAD3) {
         const int kh = k / (q.cpt * 64);
         const int e = k % (q.cpt * 64);
         const int kw = e / q.cin, c = e % q.cin;
@@ -687,11 +729,22 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  rc = pick_tile(g.gemm_h, g.gemm_w, &p.tile_h, &p.tile_w);
-  if (rc != JPDSE_OK) return rc;
+  const bool flat = d->kind == JPDSE_CONV3X3_FULL || d->kind == JPDSE_CONV7X7_FULL;
   p.batch = d->batch;
-  p.tiles_h = g.gemm_h / p.tile_h;
-  p.tiles_w = g.gemm_w / p.tile_w;
+  if (flat) {
+    // M runs over flat positions y*pitch + x of the zero-bordered input; pitch = stored width
+    p.flat_pitch = d->in_w + 2 * d->in_pad;
+    const long long last = static_cast<long long>(g.out_h - 1) * p.flat_pitch + g.out_w;  // positions needed
+    p.tile_h = 1;
+    p.tile_w = 128;
+    p.tiles_h = 1;
+    p.tiles_w = static_cast<int>((last + 127) / 128);
+  } else {
+    rc = pick_tile(g.gemm_h, g.gemm_w, &p.tile_h, &p.tile_w);
+    if (rc != JPDSE_OK) return rc;
+    p.tiles_h = g.gemm_h / p.tile_h;
+    p.tiles_w = g.gemm_w / p.tile_w;
+  }
   p.n_tiles = g.rows / g.bn;
   p.chunks_per_tap = g.cpt;
   p.out_h = g.out_h;
@@ -758,7 +811,26 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     return JPDSE_OK;
   }
 
-  switch (d->kind) {
+  if (flat) {
+    // {K-inner, flat position, image}; reads past the last position of an image meet the next image's zero
+    // border (or TMA zero fill behind the last image) and only feed rows that are never stored
+    const uint64_t L = Hp * Wp;
+    xin = static_cast<const uint8_t*>(x);
+    dims[1] = L; dims[2] = B;
+    strides[0] = C * 2; strides[1] = L * C * 2;
+    box[0] = 64; box[1] = 128; box[2] = 1;
+    p.a_rank = 3; p.dim_w = 1; p.dim_h = 1; p.dim_b = 2;
+    if (d->kind == JPDSE_CONV3X3_FULL) {
+      dims[0] = C;
+      p.ntaps = 9;
+      for (int t = 0; t < 9; ++t) p.tap_off[t][1] = (t / 3) * static_cast<int>(Wp) + (t % 3);
+    } else {
+      dims[0] = 64;  // 7*C window elements (+ zero-weight tail) under a filter row
+      p.ntaps = 7;
+      for (int t = 0; t < 7; ++t) p.tap_off[t][1] = t * static_cast<int>(Wp);
+    }
+  }
+  switch (flat ? -1 : d->kind) {
     case JPDSE_CONV3X3_PAD1: {
       xin = static_cast<const uint8_t*>(x);  // taps address the stored border directly
       dims[0] = C; dims[1] = Wp; dims[2] = Hp; dims[3] = B;
