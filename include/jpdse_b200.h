@@ -106,6 +106,50 @@ int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const void* w_pa
 double jpdse_conv_flops(const jpdse_conv_desc* d);
 
 /* ---------------------------------------------------------------------------------------------
+ * Weight gradient of one convolution (the wgrad part of what autograd runs for `loss_G.backward()`,
+ * ctu/trainers/pix2pixHD_trainer.py:69, through networks.py:210,215,244,246,283-299).
+ *
+ *   d        : the FORWARD conv descriptor
+ *   x        : the forward input exactly as jpdse_conv_forward saw it (bf16 NHWC incl. its border)
+ *   dy       : bf16 NHWC gradient w.r.t. the raw conv output, (B, out_h + 2*dy_pad, out_w + 2*dy_pad, cout)
+ *              with a border of dy_pad pixels that is skipped (the data-gradient kinds want it zero).
+ *              7x7 head (JPDSE_EPI_BIAS_TANH_NCHW): dy is the 8-channel tensor written by
+ *              jpdse_tanh_backward_nchw, dy_pad must be 6.
+ *   dw       : float32 gradient in the torch weight layout -- Conv2d (cout, cin_real, k, k),
+ *              ConvTranspose2d (cin, cout, k, k); overwritten, or accumulated into if `accumulate`
+ *   workspace: jpdse_conv_wgrad_workspace_bytes(d, dy_pad) bytes of scratch (split-K partial sums)
+ */
+size_t jpdse_conv_wgrad_workspace_bytes(const jpdse_conv_desc* d, int dy_pad);
+int jpdse_conv_wgrad(const jpdse_conv_desc* d, const void* x, const void* dy, int dy_pad, float* dw,
+                     int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * InstanceNorm2d(affine=False) backward (networks.py:27-36), fused with the backward of what the
+ * forward apply kernel fused: ReLU (networks.py:204), the ResnetBlock skip (:303-305) and
+ * ReflectionPad2d (:210,246,275-276,291-292).
+ *
+ * reduce: dy = [xhat > 0] * (fold(g) + skip), xhat = (raw - mean) * rstd
+ *   g     : bf16 (B, H+2*g_pad, W+2*g_pad, C) gradient w.r.t. the reflect-padded layer output; the
+ *           border is folded back onto the interior pixels it mirrored
+ *   skip  : optional bf16 (B,H,W,C) second gradient of the same tensor (the skip connection)
+ *   raw, stats : what the forward conv wrote (raw output + (sum, sumsq))
+ *   dy    : bf16 (B,H,W,C) out
+ *   sums  : double (B,C,2) += (sum dy, sum dy*xhat); zeroed by the caller
+ * apply : dx = rstd * (dy - sum1/n - xhat * sum2/n) -> bf16 (B, H+2*dx_pad, W+2*dx_pad, C), border = 0
+ */
+int jpdse_instnorm_backward_reduce(const void* g, int g_pad, const void* skip, const void* raw,
+                                   const double* stats, void* dy, double* sums, int batch, int height,
+                                   int width, int channels, int relu, float eps, void* stream);
+int jpdse_instnorm_backward_apply(const void* dy, const void* raw, const double* stats,
+                                  const double* sums, void* dx, int dx_pad, int batch, int height,
+                                  int width, int channels, float eps, void* stream);
+/* Head: nn.Tanh backward (networks.py:246). grad_out / out: float32 NCHW (B,channels<=8,H,W);
+ * d_pre: bf16 (B,H+12,W+12,8) = grad_out * (1 - out^2), zero border 6, channels >= `channels` zero;
+ * dbias: float32 (channels) += sum over (B,H,W) of d_pre (zeroed by the caller). */
+int jpdse_tanh_backward_nchw(const float* grad_out, const float* out, void* d_pre, float* dbias,
+                             int batch, int channels, int height, int width, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * InstanceNorm apply (+ReLU) (+residual) (+reflect pad) -- the second half of
  * nn.InstanceNorm2d(affine=False, eps=1e-5) (networks.py:27-36) whose statistics were reduced by
  * the producing conv's epilogue; ReLU (networks.py:204), ResnetBlock skip add (:303-305) and the

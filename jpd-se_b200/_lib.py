@@ -19,8 +19,8 @@ class ConvDesc(ctypes.Structure):
 
 
 # enum jpdse_conv_kind / jpdse_conv_epilogue
-CONV3X3_PAD1, CONV3X3_S2, CONVT3X3_S2, CONV7X7_PAD3, CONV1X1 = range(5)
-EPI_RAW_STATS, EPI_BIAS_TANH_NCHW, EPI_SIGN_NCHW = range(3)
+CONV3X3_PAD1, CONV3X3_S2, CONVT3X3_S2, CONV7X7_PAD3, CONV1X1, CONV3X3_FULL, CONV7X7_FULL = range(7)
+EPI_RAW_STATS, EPI_BIAS_TANH_NCHW, EPI_SIGN_NCHW, EPI_RAW = range(4)
 
 # symbol -> (restype, argtypes); also the list the CPU test checks against the header
 SIGNATURES = {
@@ -33,6 +33,15 @@ SIGNATURES = {
     "jpdse_conv_forward": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
     "jpdse_conv_flops": (c_double, [ctypes.POINTER(ConvDesc)]),
+    "jpdse_conv_wgrad_workspace_bytes": (c_size_t, [ctypes.POINTER(ConvDesc), c_int]),
+    "jpdse_conv_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
+                                 c_size_t, c_void_p]),
+    "jpdse_instnorm_backward_reduce": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               c_int, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "jpdse_instnorm_backward_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                              c_int, c_int, c_float, c_void_p]),
+    "jpdse_tanh_backward_nchw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                         c_void_p]),
     "jpdse_instnorm_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_float, c_void_p]),
     "jpdse_nchw_f32_to_nhwc_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

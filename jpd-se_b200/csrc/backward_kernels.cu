@@ -1,0 +1,326 @@
+// HBM-bound kernels of the generator BACKWARD pass (what `loss_G.backward()` runs through autograd in the
+// reference: ctu/trainers/pix2pixHD_trainer.py:69 over ctu/models/pix2pixHD_networks/networks.py:198-305):
+//
+//   instnorm_backward_reduce  reflect-pad fold-back (+ skip-connection gradient) + ReLU mask -> dy (bf16), and the
+//                             two per-(image, channel) sums  S1 = sum dy,  S2 = sum dy * xhat  of the
+//                             InstanceNorm2d(affine=False) backward (networks.py:27-36)
+//   instnorm_backward_apply   dx = rstd * (dy - S1/n - xhat * S2/n), written with the ZERO border the data-gradient
+//                             conv (JPDSE_CONV3X3_FULL / CONV7X7_FULL) reads
+//   tanh_backward_nchw        head: d_pre = dout * (1 - out^2) (nn.Tanh, networks.py:246) -> 8-channel NHWC bf16
+//                             with a zero border of 6, plus the bias gradient
+// Same conventions as bandwidth_kernels.cu: 16-byte vectors over the channel dimension, thread = (pixel, 8 channels).
+#include <cuda_bf16.h>
+
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace jpdse {
+
+constexpr int kBwdThreads = 256;
+constexpr int kBwdIters = 32;
+
+__device__ __forceinline__ uint32_t bwd_pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    f[2 * j] = __uint_as_float(w[j] << 16);
+    f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
+__device__ __forceinline__ void load_mean_rstd(const double* stats, int b, int C, int vec, double inv_n, float eps,
+                                               float (&mean)[8], float (&rstd)[8]) {
+  const double* st = stats + (static_cast<size_t>(b) * C + vec * 8) * 2;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const double m = st[2 * j] * inv_n;
+    double var = st[2 * j + 1] * inv_n - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[j] = static_cast<float>(m);
+    rstd[j] = rsqrtf(static_cast<float>(var) + eps);  // same expression as the forward apply kernel
+  }
+}
+
+// sources of the reflect-pad fold for interior index i: padded indices q with reflect(q - pad) == i
+__device__ __forceinline__ int fold_sources(int i, int n, int pad, int (&q)[3]) {
+  int c = 0;
+  q[c++] = i + pad;
+  if (pad > 0) {
+    if (i >= 1 && i <= pad) q[c++] = pad - i;
+    if (i <= n - 2 && i >= n - 1 - pad) q[c++] = pad + 2 * (n - 1) - i;
+  }
+  return c;
+}
+
+template <bool kRelu, bool kSkip>
+__global__ void __launch_bounds__(kBwdThreads)
+instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, const __nv_bfloat16* __restrict__ skip,
+                                const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
+                                __nv_bfloat16* __restrict__ dy, double* __restrict__ sums, int H, int W, int C, float eps) {
+  __shared__ float s_red[kBwdThreads][17];
+  const int vpp = C >> 3;
+  const int ppi = kBwdThreads / vpp;
+  const int vec = threadIdx.x % vpp;
+  const int psub = threadIdx.x / vpp;
+  const int b = blockIdx.y;
+  const int npix = H * W;
+  const int Wg = W + 2 * gpad, Hg = H + 2 * gpad;
+  float mean[8], rstd[8];
+  load_mean_rstd(stats, b, C, vec, 1.0 / (static_cast<double>(H) * W), eps, mean, rstd);
+  const uint4* g4 = reinterpret_cast<const uint4*>(g) + static_cast<size_t>(b) * Hg * Wg * vpp;
+  const uint4* skip4 = reinterpret_cast<const uint4*>(skip) + static_cast<size_t>(b) * npix * vpp;
+  const uint4* raw4 = reinterpret_cast<const uint4*>(raw) + static_cast<size_t>(b) * npix * vpp;
+  uint4* dy4 = reinterpret_cast<uint4*>(dy) + static_cast<size_t>(b) * npix * vpp;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const int pix0 = blockIdx.x * (ppi * kBwdIters);
+  for (int it = 0; it < kBwdIters; ++it) {
+    const int pp = pix0 + it * ppi + psub;
+    if (pp >= npix) break;
+    const int h = pp / W, w = pp - h * W;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int qh[3], qw[3];
+    const int nh = fold_sources(h, H, gpad, qh), nw = fold_sources(w, W, gpad, qw);
+    for (int a = 0; a < nh; ++a)
+      for (int c = 0; c < nw; ++c) {
+        float f[8];
+        unpack8(__ldg(g4 + (static_cast<size_t>(qh[a]) * Wg + qw[c]) * vpp + vec), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    if (kSkip) {
+      float f[8];
+      unpack8(__ldg(skip4 + static_cast<size_t>(pp) * vpp + vec), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    float x[8];
+    unpack8(__ldg(raw4 + static_cast<size_t>(pp) * vpp + vec), x);
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float xh0 = (x[j] - mean[j]) * rstd[j], xh1 = (x[j + 1] - mean[j + 1]) * rstd[j + 1];
+      float d0 = acc[j], d1 = acc[j + 1];
+      if (kRelu) {
+        d0 = xh0 > 0.f ? d0 : 0.f;
+        d1 = xh1 > 0.f ? d1 : 0.f;
+      }
+      const uint32_t pk = bwd_pack_bf16x2(d0, d1);
+      ow[j >> 1] = pk;
+      d0 = __uint_as_float(pk << 16);  // sums over the stored (bf16-rounded) gradient: the apply pass re-reads it
+      d1 = __uint_as_float(pk & 0xffff0000u);
+      s1[j] += d0;
+      s1[j + 1] += d1;
+      s2[j] = fmaf(d0, xh0, s2[j]);
+      s2[j + 1] = fmaf(d1, xh1, s2[j + 1]);
+    }
+    dy4[static_cast<size_t>(pp) * vpp + vec] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  // block reduction over the pixel sub-lanes of each channel vector
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_red[threadIdx.x][j] = s1[j];
+    s_red[threadIdx.x][8 + j] = s2[j];
+  }
+  __syncthreads();
+  for (int stride = ppi >> 1; stride >= 1; stride >>= 1) {
+    if (psub < stride) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s_red[threadIdx.x][j] += s_red[threadIdx.x + stride * vpp][j];
+    }
+    __syncthreads();
+  }
+  if (psub == 0) {
+    double* out = sums + (static_cast<size_t>(b) * C + vec * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(out + 2 * j, static_cast<double>(s_red[threadIdx.x][j]));
+      atomicAdd(out + 2 * j + 1, static_cast<double>(s_red[threadIdx.x][8 + j]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads)
+instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ raw,
+                               const double* __restrict__ stats, const double* __restrict__ sums,
+                               __nv_bfloat16* __restrict__ dx, int zpad, int H, int W, int C, float eps) {
+  const int vpp = C >> 3;
+  const int ppi = kBwdThreads / vpp;
+  const int vec = threadIdx.x % vpp;
+  const int psub = threadIdx.x / vpp;
+  const int b = blockIdx.y;
+  const int Wz = W + 2 * zpad, Hz = H + 2 * zpad;
+  const int npix = Hz * Wz;
+  const double inv_n = 1.0 / (static_cast<double>(H) * W);
+  float mean[8], rstd[8], m1[8], m2[8];
+  load_mean_rstd(stats, b, C, vec, inv_n, eps, mean, rstd);
+  {
+    const double* sm = sums + (static_cast<size_t>(b) * C + vec * 8) * 2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      m1[j] = static_cast<float>(sm[2 * j] * inv_n);
+      m2[j] = static_cast<float>(sm[2 * j + 1] * inv_n);
+    }
+  }
+  const uint4* dy4 = reinterpret_cast<const uint4*>(dy) + static_cast<size_t>(b) * H * W * vpp;
+  const uint4* raw4 = reinterpret_cast<const uint4*>(raw) + static_cast<size_t>(b) * H * W * vpp;
+  uint4* dx4 = reinterpret_cast<uint4*>(dx) + static_cast<size_t>(b) * npix * vpp;
+  const int pix0 = blockIdx.x * (ppi * kBwdIters);
+#pragma unroll 4
+  for (int it = 0; it < kBwdIters; ++it) {
+    const int pp = pix0 + it * ppi + psub;
+    if (pp >= npix) break;
+    const int ph = pp / Wz, pw = pp - ph * Wz;
+    const int h = ph - zpad, w = pw - zpad;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const size_t src = (static_cast<size_t>(h) * W + w) * vpp + vec;
+      float d[8], x[8];
+      unpack8(__ldg(dy4 + src), d);
+      unpack8(__ldg(raw4 + src), x);
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float xh0 = (x[j] - mean[j]) * rstd[j], xh1 = (x[j + 1] - mean[j + 1]) * rstd[j + 1];
+        ow[j >> 1] = bwd_pack_bf16x2(rstd[j] * (d[j] - m1[j] - xh0 * m2[j]), rstd[j + 1] * (d[j + 1] - m1[j + 1] - xh1 * m2[j + 1]));
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    dx4[static_cast<size_t>(pp) * vpp + vec] = o;
+  }
+}
+
+// one thread per STORED pixel of d_pre (B, H+12, W+12, 8)
+__global__ void __launch_bounds__(256)
+tanh_backward_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ out, __nv_bfloat16* __restrict__ dpre,
+                          float* __restrict__ dbias, int B, int Cout, int H, int W) {
+  __shared__ float s_b[8][8];
+  const int Ws = W + 12, Hs = H + 12;
+  const size_t total = static_cast<size_t>(B) * Hs * Ws;
+  const size_t plane = static_cast<size_t>(H) * W;
+  float bsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bsum[j] = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int pw = static_cast<int>(i % Ws);
+    const size_t r = i / Ws;
+    const int ph = static_cast<int>(r % Hs);
+    const int b = static_cast<int>(r / Hs);
+    const int h = ph - 6, w = pw - 6;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const size_t src = static_cast<size_t>(b) * Cout * plane + static_cast<size_t>(h) * W + w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < Cout) {
+          const float y = __ldg(out + src + j * plane);
+          v[j] = __ldg(gout + src + j * plane) * (1.f - y * y);
+          bsum[j] += v[j];
+        }
+    }
+    reinterpret_cast<uint4*>(dpre)[i] =
+        make_uint4(bwd_pack_bf16x2(v[0], v[1]), bwd_pack_bf16x2(v[2], v[3]), bwd_pack_bf16x2(v[4], v[5]), bwd_pack_bf16x2(v[6], v[7]));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float s = bsum[j];
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_b[warp][j] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < Cout) {
+    float s = 0.f;
+    for (int wv = 0; wv < 8; ++wv) s += s_b[wv][threadIdx.x];
+    atomicAdd(dbias + threadIdx.x, s);
+  }
+}
+
+static int check_channels(int channels, const char* what) {
+  if (channels % 8 || channels > 8 * kBwdThreads || (kBwdThreads % (channels / 8)))
+    return fail(JPDSE_ERR_UNSUPPORTED, "%s: channels must be 8*2^k <= %d (got %d)", what, 8 * kBwdThreads, channels);
+  return JPDSE_OK;
+}
+
+}  // namespace jpdse
+
+using namespace jpdse;
+
+extern "C" int jpdse_instnorm_backward_reduce(const void* g, int g_pad, const void* skip, const void* raw, const double* stats,
+                                              void* dy, double* sums, int batch, int height, int width, int channels, int relu,
+                                              float eps, void* stream_v) {
+  if (g == nullptr || raw == nullptr || stats == nullptr || dy == nullptr || sums == nullptr)
+    return fail(JPDSE_ERR_INVALID, "instnorm_backward_reduce: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0) return fail(JPDSE_ERR_INVALID, "instnorm_backward_reduce: bad sizes");
+  int rc = check_channels(channels, "instnorm_backward_reduce");
+  if (rc != JPDSE_OK) return rc;
+  if (g_pad < 0 || 2 * g_pad >= height || 2 * g_pad >= width) return fail(JPDSE_ERR_INVALID, "instnorm_backward_reduce: bad pad");
+  if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(raw) |
+       reinterpret_cast<uintptr_t>(dy)) & 15)
+    return fail(JPDSE_ERR_INVALID, "instnorm_backward_reduce: pointers must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int vpp = channels / 8, ppi = kBwdThreads / vpp;
+  const int per_block = ppi * kBwdIters;
+  dim3 grid((height * width + per_block - 1) / per_block, batch);
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(g);
+  const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(skip);
+  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(raw);
+  __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dy);
+  if (relu && skip)
+    instnorm_backward_reduce_kernel<true, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps);
+  else if (relu)
+    instnorm_backward_reduce_kernel<true, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps);
+  else if (skip)
+    instnorm_backward_reduce_kernel<false, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps);
+  else
+    instnorm_backward_reduce_kernel<false, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps);
+  return check_launch("instnorm_backward_reduce_kernel");
+}
+
+extern "C" int jpdse_instnorm_backward_apply(const void* dy, const void* raw, const double* stats, const double* sums, void* dx,
+                                             int dx_pad, int batch, int height, int width, int channels, float eps,
+                                             void* stream_v) {
+  if (dy == nullptr || raw == nullptr || stats == nullptr || sums == nullptr || dx == nullptr)
+    return fail(JPDSE_ERR_INVALID, "instnorm_backward_apply: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0 || dx_pad < 0) return fail(JPDSE_ERR_INVALID, "instnorm_backward_apply: bad sizes");
+  int rc = check_channels(channels, "instnorm_backward_apply");
+  if (rc != JPDSE_OK) return rc;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(dx)) & 15)
+    return fail(JPDSE_ERR_INVALID, "instnorm_backward_apply: pointers must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  const int vpp = channels / 8, ppi = kBwdThreads / vpp;
+  const int per_block = ppi * kBwdIters;
+  const int npix = (height + 2 * dx_pad) * (width + 2 * dx_pad);
+  dim3 grid((npix + per_block - 1) / per_block, batch);
+  instnorm_backward_apply_kernel<<<grid, kBwdThreads, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(raw), stats, sums, static_cast<__nv_bfloat16*>(dx),
+      dx_pad, height, width, channels, eps);
+  return check_launch("instnorm_backward_apply_kernel");
+}
+
+extern "C" int jpdse_tanh_backward_nchw(const float* grad_out, const float* out, void* d_pre, float* dbias, int batch,
+                                        int channels, int height, int width, void* stream_v) {
+  if (grad_out == nullptr || out == nullptr || d_pre == nullptr || dbias == nullptr)
+    return fail(JPDSE_ERR_INVALID, "tanh_backward_nchw: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0 || channels <= 0 || channels > 8)
+    return fail(JPDSE_ERR_INVALID, "tanh_backward_nchw: bad sizes (channels must be 1..8)");
+  if (reinterpret_cast<uintptr_t>(d_pre) & 15) return fail(JPDSE_ERR_INVALID, "tanh_backward_nchw: d_pre must be 16-byte aligned");
+  const size_t total = static_cast<size_t>(batch) * (height + 12) * (width + 12);
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = static_cast<size_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  tanh_backward_nchw_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      grad_out, out, static_cast<__nv_bfloat16*>(d_pre), dbias, batch, channels, height, width);
+  return check_launch("tanh_backward_nchw_kernel");
+}

@@ -9,8 +9,8 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (CONV1X1, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_PAD3, CONVT3X3_S2, EPI_BIAS_TANH_NCHW,
-                   EPI_RAW_STATS, EPI_SIGN_NCHW, ConvDesc, JpdseError, check)
+from ._lib import (CONV1X1, CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_FULL, CONV7X7_PAD3, CONVT3X3_S2,
+                   EPI_BIAS_TANH_NCHW, EPI_RAW, EPI_RAW_STATS, EPI_SIGN_NCHW, ConvDesc, JpdseError, check)
 
 _LABEL_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.int64: 2}
 _INST_DTYPES = {torch.int32: 0, torch.int16: 1, torch.int64: 2, torch.float32: 3}
@@ -95,7 +95,8 @@ class Conv:
         self.bias = None
         self.flops = self.lib.jpdse_conv_flops(ctypes.byref(self.desc))
         self.kind, self.epilogue = kind, epilogue
-        self.out_hw = {CONV3X3_S2: (in_h // 2, in_w // 2), CONVT3X3_S2: (in_h * 2, in_w * 2)}.get(kind, (in_h, in_w))
+        self.out_hw = {CONV3X3_S2: (in_h // 2, in_w // 2), CONVT3X3_S2: (in_h * 2, in_w * 2),
+                       CONV3X3_FULL: (in_h + 2, in_w + 2), CONV7X7_FULL: (in_h + 6, in_w + 6)}.get(kind, (in_h, in_w))
         self.cout = cout
         self.batch = batch
 
@@ -115,6 +116,33 @@ class Conv:
         _count(4 if self.kind == CONVT3X3_S2 else 1)
         return y
 
+    def wgrad(self, x, dy, dy_pad, dw, accumulate=False):
+        """dw (float32, torch weight layout) = / += weight gradient of THIS (forward) conv. See jpdse_conv_wgrad."""
+        _need(x, "x", torch.bfloat16)
+        _need(dy, "dy", torch.bfloat16)
+        _need(dw, "dw", torch.float32)
+        nbytes = self.lib.jpdse_conv_wgrad_workspace_bytes(ctypes.byref(self.desc), dy_pad)
+        if nbytes == 0:
+            raise JpdseError("conv_wgrad rejected: %s" % self.lib.jpdse_last_error().decode())
+        ws = _workspace(nbytes, x.device)
+        check(self.lib.jpdse_conv_wgrad(ctypes.byref(self.desc), _ptr(x), _ptr(dy), dy_pad, _ptr(dw), int(bool(accumulate)),
+                                        _ptr(ws), ws.numel() * 4, _stream()))
+        _count(2)
+        return dw
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """One growing float32 scratch buffer per device (kernels on one stream use it one after the other)."""
+    key = str(device)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() * 4 < nbytes:
+        ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        _ws_cache[key] = ws
+    return ws
+
 
 def instnorm_apply(raw, stats, out, batch, height, width, channels, pad, relu, residual=None, eps=1e-5):
     lib = _lib.load()
@@ -127,6 +155,48 @@ def instnorm_apply(raw, stats, out, batch, height, width, channels, pad, relu, r
                                    pad, int(bool(relu)), eps, _stream()))
     _count()
     return out
+
+
+def instnorm_backward_reduce(g, g_pad, skip, raw, stats, dy, sums, batch, height, width, channels, relu, eps=1e-5):
+    lib = _lib.load()
+    _need(g, "g", torch.bfloat16)
+    _need(raw, "raw", torch.bfloat16)
+    _need(stats, "stats", torch.float64)
+    _need(dy, "dy", torch.bfloat16)
+    _need(sums, "sums", torch.float64)
+    if skip is not None:
+        _need(skip, "skip", torch.bfloat16)
+    check(lib.jpdse_instnorm_backward_reduce(_ptr(g), g_pad, _ptr(skip), _ptr(raw), _ptr(stats), _ptr(dy), _ptr(sums), batch,
+                                             height, width, channels, int(bool(relu)), eps, _stream()))
+    _count()
+    return dy
+
+
+def instnorm_backward_apply(dy, raw, stats, sums, dx, dx_pad, batch, height, width, channels, eps=1e-5):
+    lib = _lib.load()
+    _need(dy, "dy", torch.bfloat16)
+    _need(raw, "raw", torch.bfloat16)
+    _need(stats, "stats", torch.float64)
+    _need(sums, "sums", torch.float64)
+    _need(dx, "dx", torch.bfloat16)
+    check(lib.jpdse_instnorm_backward_apply(_ptr(dy), _ptr(raw), _ptr(stats), _ptr(sums), _ptr(dx), dx_pad, batch, height,
+                                            width, channels, eps, _stream()))
+    _count()
+    return dx
+
+
+def tanh_backward_nchw(grad_out, out, d_pre, dbias):
+    lib = _lib.load()
+    _need(grad_out, "grad_out", torch.float32)
+    _need(out, "out", torch.float32)
+    _need(d_pre, "d_pre", torch.bfloat16)
+    _need(dbias, "dbias", torch.float32)
+    B, C, H, W = out.shape
+    if tuple(grad_out.shape) != (B, C, H, W) or tuple(d_pre.shape) != (B, H + 12, W + 12, 8):
+        raise JpdseError("tanh_backward: shape mismatch")
+    check(lib.jpdse_tanh_backward_nchw(_ptr(grad_out), _ptr(out), _ptr(d_pre), _ptr(dbias), B, C, H, W, _stream()))
+    _count()
+    return d_pre
 
 
 # ------------------------------------------------------------------------------------------------ layout

@@ -1,0 +1,223 @@
+"""GPU parity tests of the generator BACKWARD kernels (run with -m gpu on a B200), through the C ABI.
+
+The checker is torch CPU fp32 autograd of the reference's own ops (nn.Conv2d / ConvTranspose2d / InstanceNorm2d /
+ReflectionPad2d / ReLU / Tanh: ctu/models/pix2pixHD_networks/networks.py:198-305) on the SAME bf16-rounded operands.
+
+Tolerances
+  weight gradient (bf16 operands, fp32 accumulate over up to 2^17 pixels): |err| <= 2e-3 * max|ref| (fp32 summation
+      order only -- the operands are identical)
+  data gradient: one bf16 rounding of the result (2^-7 relative to the output max)
+  InstanceNorm backward: bf16 rounding of dy and dx (2^-6 relative to the max)
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def _ops():
+    import jpdse_b200  # noqa: F401
+    from jpdse_b200 import ops
+    return ops
+
+
+def _nhwc(t, pad=0, c_pad=None, mode="constant"):
+    """fp32 NCHW cpu -> bf16 NHWC (optionally spatially padded / channel padded)"""
+    if pad:
+        t = F.pad(t, (pad, pad, pad, pad), mode=mode)
+    t = t.permute(0, 2, 3, 1).contiguous()
+    if c_pad is not None and c_pad > t.shape[-1]:
+        t = F.pad(t, (0, c_pad - t.shape[-1]))
+    return t.bfloat16().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------ weight gradients
+@pytest.mark.parametrize("case", [
+    ("conv3x3", 2, 8, 16, 64, 64), ("conv3x3", 2, 16, 16, 128, 256), ("conv3x3", 1, 32, 64, 256, 128),
+    ("conv3x3", 3, 32, 64, 512, 1024),
+    ("conv1x1", 2, 8, 16, 128, 128),
+    ("convs2", 2, 16, 32, 64, 128), ("convs2", 1, 64, 128, 128, 256), ("convs2", 2, 32, 32, 512, 1024),
+    ("convt", 2, 8, 16, 128, 64), ("convt", 1, 32, 64, 256, 128), ("convt", 2, 8, 16, 1024, 512),
+    ("stem", 2, 8, 16, 40, 64), ("stem", 1, 64, 128, 40, 64), ("stem", 2, 70, 96, 40, 64),
+    ("head", 2, 8, 16, 64, 3), ("head", 1, 64, 128, 64, 3), ("head", 2, 70, 100, 64, 3),
+])
+def test_conv_wgrad(cuda, case):
+    ops = _ops()
+    from jpdse_b200._lib import (CONV1X1, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_PAD3, CONVT3X3_S2, EPI_BIAS_TANH_NCHW,
+                                 EPI_RAW_STATS)
+    kind_name, B, H, W, cin, cout = case
+    g = torch.Generator().manual_seed(B * 1000 + H + cin)
+    cin_real = 39 if kind_name == "stem" else cin
+    x = _bf(torch.randn(B, cin_real, H, W, generator=g))
+    epi, dy_pad = EPI_RAW_STATS, 0
+    if kind_name == "conv3x3":
+        kind, pad, mode, dy_pad = CONV3X3_PAD1, 1, "reflect", 2
+        w = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+        y = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w)
+    elif kind_name == "conv1x1":
+        kind, pad, mode = CONV1X1, 0, "constant"
+        w = torch.zeros(cout, cin, 1, 1, requires_grad=True)
+        y = F.conv2d(x, w)
+    elif kind_name == "convs2":
+        kind, pad, mode = CONV3X3_S2, 0, "constant"
+        w = torch.zeros(cout, cin, 3, 3, requires_grad=True)
+        y = F.conv2d(x, w, stride=2, padding=1)
+    elif kind_name == "convt":
+        kind, pad, mode = CONVT3X3_S2, 0, "constant"
+        w = torch.zeros(cin, cout, 3, 3, requires_grad=True)
+        y = F.conv_transpose2d(x, w, stride=2, padding=1, output_padding=1)
+    elif kind_name == "stem":
+        kind, pad, mode = CONV7X7_PAD3, 3, "reflect"
+        w = torch.zeros(cout, cin_real, 7, 7, requires_grad=True)
+        y = F.conv2d(F.pad(x, (3, 3, 3, 3), mode="reflect"), w)
+    else:
+        kind, pad, mode, epi, dy_pad = CONV7X7_PAD3, 3, "reflect", EPI_BIAS_TANH_NCHW, 6
+        w = torch.zeros(cout, cin, 7, 7, requires_grad=True)
+        y = F.conv2d(F.pad(x, (3, 3, 3, 3), mode="reflect"), w)
+    dy = _bf(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    ref = w.grad
+    xd = _nhwc(x, pad, c_pad=cin, mode=mode).to(cuda)
+    if kind_name == "stem":  # the window view over-reads a few elements behind the tensor: keep zeroed slack
+        flat = torch.zeros(xd.numel() + 2048, dtype=torch.bfloat16, device=cuda)
+        flat[: xd.numel()] = xd.reshape(-1)
+        xd = flat[: xd.numel()].view(xd.shape)
+    dyd = _nhwc(dy, dy_pad, c_pad=8 if kind_name == "head" else None).to(cuda)
+    cv = ops.Conv(kind, epi, B, H, W, pad, cin, cin_real, cout, cuda)
+    dw = torch.full(ref.shape, float("nan"), device=cuda)
+    cv.wgrad(xd, dyd, dy_pad, dw)
+    torch.cuda.synchronize()
+    got = dw.cpu()
+    assert not torch.isnan(got).any()
+    scale = float(ref.abs().max())
+    assert float((got - ref).abs().max()) <= 2e-3 * scale, "weight gradient differs from torch autograd"
+    cv.wgrad(xd, dyd, dy_pad, dw, accumulate=True)
+    assert float((dw.cpu() - 2 * ref).abs().max()) <= 4e-3 * scale
+
+
+# ------------------------------------------------------------------------------------------------ data gradients
+@pytest.mark.parametrize("case", [("conv3x3", 2, 8, 16, 64, 64), ("conv3x3", 1, 32, 64, 256, 128), ("conv3x3", 2, 12, 20, 128, 128),
+                                  ("convs2", 2, 16, 32, 64, 128), ("convs2", 1, 32, 64, 256, 512),
+                                  ("convt", 2, 8, 16, 128, 64), ("convt", 1, 16, 32, 512, 256),
+                                  ("head", 2, 8, 16, 64, 3), ("head", 1, 40, 72, 64, 3)])
+def test_conv_dgrad(cuda, case):
+    """Gradient w.r.t. the conv input through the same implicit-GEMM kernel (role-swapped kinds)."""
+    ops = _ops()
+    from jpdse_b200._lib import CONV3X3_FULL, CONV3X3_S2, CONV7X7_FULL, CONVT3X3_S2, EPI_RAW
+    kind_name, B, H, W, cin, cout = case
+    g = torch.Generator().manual_seed(B * 77 + W + cout)
+    if kind_name == "conv3x3":
+        xp = torch.zeros(B, cin, H + 2, W + 2, requires_grad=True)  # gradient w.r.t. the PADDED input
+        w = _bf(torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+        y = F.conv2d(xp, w)
+        dy = _bf(torch.randn(y.shape, generator=g))
+        y.backward(dy)
+        cv = ops.Conv(CONV3X3_FULL, EPI_RAW, B, H, W, 2, cout, cout, cin, cuda)
+        dyd = _nhwc(dy, 2).to(cuda)
+    elif kind_name == "head":
+        xp = torch.zeros(B, cin, H + 6, W + 6, requires_grad=True)
+        w = _bf(torch.randn(cout, cin, 7, 7, generator=g) * 0.05)
+        y = F.conv2d(xp, w)
+        dy = _bf(torch.randn(y.shape, generator=g))
+        y.backward(dy)
+        cv = ops.Conv(CONV7X7_FULL, EPI_RAW, B, H, W, 6, 8, cout, cin, cuda)
+        dyd = _nhwc(dy, 6, c_pad=8).to(cuda)
+    elif kind_name == "convs2":
+        xp = torch.zeros(B, cin, H, W, requires_grad=True)
+        w = _bf(torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+        y = F.conv2d(xp, w, stride=2, padding=1)
+        dy = _bf(torch.randn(y.shape, generator=g))
+        y.backward(dy)
+        # dgrad of a stride-2 conv == ConvTranspose forward with the same weight memory (Cin_T = cout, Cout_T = cin)
+        cv = ops.Conv(CONVT3X3_S2, EPI_RAW, B, H // 2, W // 2, 0, cout, cout, cin, cuda)
+        dyd = _nhwc(dy).to(cuda)
+    else:
+        xp = torch.zeros(B, cin, H, W, requires_grad=True)
+        w = _bf(torch.randn(cin, cout, 3, 3, generator=g) * 0.05)
+        y = F.conv_transpose2d(xp, w, stride=2, padding=1, output_padding=1)
+        dy = _bf(torch.randn(y.shape, generator=g))
+        y.backward(dy)
+        # dgrad of a ConvTranspose == stride-2 conv with the same weight memory (Cout_c = cin, Cin_c = cout)
+        cv = ops.Conv(CONV3X3_S2, EPI_RAW, B, 2 * H, 2 * W, 0, cout, cout, cin, cuda)
+        dyd = _nhwc(dy).to(cuda)
+    ref = xp.grad
+    cv.pack(w.to(cuda))
+    flat = torch.zeros(dyd.numel() + 2048, dtype=torch.bfloat16, device=cuda)
+    flat[: dyd.numel()] = dyd.reshape(-1)
+    dyd = flat[: dyd.numel()].view(dyd.shape)
+    out = torch.full((B, ref.shape[2], ref.shape[3], cin), float("nan"), dtype=torch.bfloat16, device=cuda)
+    cv.forward(dyd, out)
+    torch.cuda.synchronize()
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    assert not torch.isnan(got).any()
+    assert float((got - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -7
+
+
+# ------------------------------------------------------------------------------------------------ InstanceNorm backward
+@pytest.mark.parametrize("C,H,W,gpad,relu,skip,zpad", [(64, 16, 24, 0, True, False, 0), (64, 12, 20, 3, True, False, 0),
+                                                       (1024, 8, 16, 1, True, False, 2), (1024, 8, 16, 1, False, True, 2),
+                                                       (128, 9, 7, 1, True, True, 0), (256, 6, 10, 0, False, False, 2)])
+def test_instnorm_backward(cuda, C, H, W, gpad, relu, skip, zpad):
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + H + gpad)
+    B = 2
+    raw = _bf(torch.randn(B, C, H, W, generator=g) * 2 + 0.3).requires_grad_(True)
+    y = F.instance_norm(raw, eps=1e-5)
+    if relu:
+        y = F.relu(y)
+    yp = F.pad(y, (gpad, gpad, gpad, gpad), mode="reflect") if gpad else y
+    gp = _bf(torch.randn(yp.shape, generator=g))
+    sk = _bf(torch.randn(y.shape, generator=g)) if skip else None
+    loss = (yp * gp).sum() + ((y * sk).sum() if skip else 0.0)
+    loss.backward()
+    ref_dx = raw.grad
+    # expected dy (before the norm backward): fold + skip + mask
+    y2 = y.detach().clone().requires_grad_(True)
+    yp2 = F.pad(y2, (gpad, gpad, gpad, gpad), mode="reflect") if gpad else y2
+    ((yp2 * gp).sum() + ((y2 * sk).sum() if skip else 0.0)).backward()
+    ref_dy = y2.grad * ((y.detach() > 0).float() if relu else 1.0)
+
+    rawd = _nhwc(raw.detach()).to(cuda)
+    stats = torch.stack([raw.detach().double().sum(dim=(2, 3)), (raw.detach().double() ** 2).sum(dim=(2, 3))], dim=-1).contiguous().to(cuda)
+    gd = _nhwc(gp).to(cuda)
+    skd = _nhwc(sk).to(cuda) if skip else None
+    dy = torch.full((B, H, W, C), float("nan"), dtype=torch.bfloat16, device=cuda)
+    sums = torch.zeros(B, C, 2, dtype=torch.float64, device=cuda)
+    ops.instnorm_backward_reduce(gd, gpad, skd, rawd, stats, dy, sums, B, H, W, C, relu)
+    dx = torch.full((B, H + 2 * zpad, W + 2 * zpad, C), float("nan"), dtype=torch.bfloat16, device=cuda)
+    ops.instnorm_backward_apply(dy, rawd, stats, sums, dx, zpad, B, H, W, C)
+    torch.cuda.synchronize()
+    got_dy = dy.float().cpu().permute(0, 3, 1, 2)
+    assert float((got_dy - ref_dy).abs().max()) <= 2.0 ** -7 * max(1.0, float(ref_dy.abs().max()))
+    assert torch.allclose(sums[:, :, 0].cpu(), got_dy.double().sum(dim=(2, 3)), rtol=1e-5, atol=1e-3)
+    got = dx.float().cpu().permute(0, 3, 1, 2)
+    assert not torch.isnan(got).any()
+    if zpad:
+        inner = got[:, :, zpad:-zpad, zpad:-zpad]
+        assert float(got.double().abs().sum() - inner.double().abs().sum()) == 0.0  # zero border
+        got = inner
+    assert float((got - ref_dx).abs().max()) <= 2.0 ** -6 * max(1.0, float(ref_dx.abs().max()))
+
+
+def test_tanh_backward(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(2)
+    B, C, H, W = 2, 3, 20, 36
+    pre = torch.randn(B, C, H, W, generator=g, requires_grad=True)
+    out = torch.tanh(pre)
+    go = torch.randn(B, C, H, W, generator=g)
+    out.backward(go)
+    d_pre = torch.full((B, H + 12, W + 12, 8), float("nan"), dtype=torch.bfloat16, device=cuda)
+    dbias = torch.zeros(C, device=cuda)
+    ops.tanh_backward_nchw(go.to(cuda), out.detach().to(cuda), d_pre, dbias)
+    got = d_pre.float().cpu()
+    assert not torch.isnan(got).any()
+    inner = got[:, 6:-6, 6:-6, :3].permute(0, 3, 1, 2)
+    assert float((inner - pre.grad).abs().max()) <= 2.0 ** -8 * float(pre.grad.abs().max())
+    assert float(got.double().abs().sum() - inner.double().abs().sum()) == 0.0  # zero border and zero pad channels
+    assert torch.allclose(dbias.cpu(), pre.grad.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
