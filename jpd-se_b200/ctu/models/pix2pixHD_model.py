@@ -1,4 +1,4 @@
-"""Hot-path mirror of ``ctu.models.pix2pixHD_model.Pix2PixHDModel`` (inference side).
+"""Hot-path mirror of ``ctu.models.pix2pixHD_model.Pix2PixHDModel``.
 
 Follows the reference for the configuration its scripts ship (scripts/pix2pixHD_bpg_test.sh:
 ``--no_label_encoding --no_feat_encoding --no_generator_binarization``, no ``--sem_masking``):
@@ -8,12 +8,19 @@ Follows the reference for the configuration its scripts ship (scripts/pix2pixHD_
   get_edges     :774-783
   _get_img      :508-618 -- the zero_vis / zero_sem / zero_ins switches (:583-595), concat, netG call
   get_img       :463-465
+  get_train_loss :709-771 -- fake/real discrimination, GAN + feature-matching + VGG + distortion losses; the
+                generator forward/backward inside it are the sm_100a kernels (one autograd node), netD / VGG /
+                the losses are stock PyTorch (SURVEY.md section 8f "next" rows)
+  get_eval_loss :636-641 -- distortion after de-normalisation and uint8 truncation (ctu/utils/misc.py:64-95)
+  create_optimizers :247-281, discriminate :451-460, save / load_network (base_model.py:54-97)
 
 The default ``get_img`` path never materialises the reference's (B,39,H,W) float tensors: label ids,
 instance ids and the image go straight into the fused input-build kernel (jpdse_build_input), which
 writes the reflect-padded NHWC bf16 operand of the stem conv. ``preprocess`` / ``get_edges`` remain
 available with the reference's outputs for callers (and tests) that want them.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -40,9 +47,9 @@ class Pix2PixHDModel(nn.Module):
             if _opt(opt, flag, want) != want:
                 raise NotImplementedError('jpdse_b200 Pix2PixHDModel: option %s=%r is outside the accelerated path '
                                           '(shipped scripts use %r)' % (flag, getattr(opt, flag), want))
-        if self.is_train:
-            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: training mode needs the generator backward '
-                                      '(not implemented yet)')
+        if self.is_train and (_opt(opt, 'fp16', False) or _opt(opt, 'niter_fix_global', 0) > 0):
+            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: --fp16 (apex) / --niter_fix_global are outside the '
+                                      'accelerated path')
         self.num_labels = opt.num_labels + 1 if _opt(opt, 'contain_dontcare_label', False) else opt.num_labels
         netG_input_nc = self.num_labels
         if not _opt(opt, 'no_instance', False):
@@ -54,6 +61,58 @@ class Pix2PixHDModel(nn.Module):
             _opt(opt, 'n_downsample_global', 4), _opt(opt, 'n_blocks_global', 9), _opt(opt, 'n_local_enhancers', 1),
             _opt(opt, 'n_blocks_local', 3), _opt(opt, 'norm', 'instance'), gpu_ids=self.gpu_ids,
             binarize_generator=False)
+        if self.is_train:
+            # pix2pixHD_model.py:151-162: D sees semantics (+edge) + image
+            netD_input_nc = self.num_labels + _opt(opt, 'num_out_channels', 3)
+            if not _opt(opt, 'no_instance', False):
+                netD_input_nc += 1
+            self.netD = networks.define_D(netD_input_nc, _opt(opt, 'ndf', 64), _opt(opt, 'n_layers_D', 3),
+                                          _opt(opt, 'norm', 'instance'), _opt(opt, 'no_lsgan', False),
+                                          _opt(opt, 'num_D', 2), True, gpu_ids=self.gpu_ids)
+        if not self.is_train or _opt(opt, 'load_model', False):
+            if _opt(opt, 'checkpoints_dir', None) is not None:
+                self.load_network(self.netG, 'G', opt)
+                if self.is_train:
+                    self.load_network(self.netD, 'D', opt)
+        if self.is_train:
+            if _opt(opt, 'pool_size', 0) > 0:
+                raise NotImplementedError('jpdse_b200: ImagePool (pool_size > 0) is outside the accelerated path')
+            self.criterionGAN = networks.GANLoss(use_lsgan=not _opt(opt, 'no_lsgan', False))
+            self.criterionFeat = torch.nn.L1Loss()
+            self.criterionVGG = networks.VGGLoss(self.gpu_ids)
+        else:
+            self.loss_names = ('G_Distortion')  # sic: a plain string in the reference (:215)
+        fn = _opt(opt, 'distortion_loss_fn', 'l1')
+        self.criterionDistortion = torch.nn.L1Loss() if fn == 'l1' else torch.nn.MSELoss()
+
+    # ------------------------------------------------------------------ checkpoints (base_model.py:54-97)
+    def load_network(self, network, network_label, opt):
+        load_path = os.path.join(opt.checkpoints_dir, 'net_%s.pth' % network_label)
+        if not os.path.isfile(load_path):
+            print('%s does not exist' % load_path)
+            if network_label == 'G':
+                raise TypeError('generator must exist')  # the reference's bare raise('...') is a TypeError
+            return
+        sd = torch.load(load_path, map_location='cpu')
+        try:
+            network.load_state_dict(sd)
+        except RuntimeError:
+            own = network.state_dict()
+            network.load_state_dict({k: v for k, v in sd.items() if k in own and v.size() == own[k].size()}, strict=False)
+            print('pretrained network %s does not match exactly; loaded the layers that do' % network_label)
+
+    def save_network(self, network, network_label, save_dir):
+        torch.save({k: v.cpu() for k, v in network.state_dict().items()}, os.path.join(save_dir, 'net_%s.pth' % network_label))
+
+    def save(self):
+        self.save_network(self.netG, 'G', self.opt.save_dir)
+        if self.is_train:
+            self.save_network(self.netD, 'D', self.opt.save_dir)
+
+    def create_optimizers(self, opt):
+        # pix2pixHD_model.py:247-281: two Adams, same lr / betas
+        kw = dict(lr=_opt(opt, 'lr', 0.0002), betas=(_opt(opt, 'beta1', 0.5), _opt(opt, 'beta2', 0.999)))
+        return torch.optim.Adam(list(self.netG.parameters()), **kw), torch.optim.Adam(list(self.netD.parameters()), **kw)
 
     def use_gpu(self):
         return len(self.gpu_ids) > 0
@@ -62,8 +121,13 @@ class Pix2PixHDModel(nn.Module):
     def forward(self, x_dict, opt, mode):
         if mode == 'get_img':
             return self.get_img(x_dict)
-        if mode in ('get_code', 'get_train_loss', 'get_eval_loss', 'get_eval_rate'):
-            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: mode %r is not on the accelerated path yet' % mode)
+        if mode == 'get_train_loss':
+            return self.get_train_loss(x_dict)
+        if mode == 'get_eval_loss':
+            return self.get_eval_loss(x_dict)
+        if mode in ('get_code', 'get_eval_rate'):
+            # only meaningful with encoders / binarizers, which the shipped scripts disable
+            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: mode %r needs the encoder/binarizer path' % mode)
         raise ValueError('Invalid forward mode: {}'.format(mode))
 
     # ------------------------------------------------------------------ preprocessing with reference outputs
@@ -128,3 +192,54 @@ class Pix2PixHDModel(nn.Module):
                              "path, supply the decoded image tensor")
         image = x_dict[key].cuda(non_blocking=True).float().contiguous()
         return self.netG.forward_from_maps(label, inst, image, self.num_labels)
+
+    # ------------------------------------------------------------------ training (pix2pixHD_model.py:451-460, 709-771)
+    def _fast_inputs(self, x_dict):
+        label = x_dict['label'].cuda(non_blocking=True).contiguous()
+        inst = x_dict['instance'].cuda(non_blocking=True).contiguous()
+        image = x_dict['image'].cuda(non_blocking=True).float().contiguous()
+        return label, inst, image
+
+    def discriminate(self, input_label, test_image, use_pool=False, keep_input=False):
+        # cuts the graph of both inputs: this is the discriminator's own loss
+        input_concat = torch.cat((input_label.detach(), test_image.detach()), dim=1)
+        return self.netD.forward(input_concat, keep_input)
+
+    def get_train_loss(self, x_dict):
+        opt = self.opt
+        if _opt(opt, 'use_compressed', False) or _opt(opt, 'zero_vis', False) or _opt(opt, 'zero_sem', False) \
+                or _opt(opt, 'zero_ins', False) or _opt(opt, 'no_instance', False):
+            raise NotImplementedError('jpdse_b200: get_train_loss supports the shipped training configuration only')
+        label, inst, real_image = self._fast_inputs(x_dict)
+        # one input-build launch gives the reference's input_label (for netD) AND the stem operand
+        bad = torch.zeros(1, dtype=torch.int32, device=real_image.device)
+        _, nchw = ops.build_input(label, inst, real_image, self.num_labels, nhwc=False, nchw=True, bad_count=bad)
+        input_label = nchw[:, :self.num_labels + 1]
+        fake_image = self.netG.forward_from_maps(label, inst, real_image, self.num_labels)
+        keep_input = bool(_opt(opt, 'match_raw_feat', False))
+        pred_fake_pool = self.discriminate(input_label, fake_image, use_pool=True)
+        loss_D_fake = self.criterionGAN(pred_fake_pool, False)
+        pred_real = self.discriminate(input_label, real_image, keep_input=keep_input)
+        loss_D_real = self.criterionGAN(pred_real, True)
+        pred_fake = self.netD.forward(torch.cat((input_label, fake_image), dim=1), keep_input=keep_input)
+        loss_G_GAN = self.criterionGAN(pred_fake, True)
+        loss_G_GAN_Feat = 0.
+        D_weights = 1.0 / _opt(opt, 'num_D', 2)
+        for i in range(_opt(opt, 'num_D', 2)):
+            for j in range(len(pred_fake[i]) - 1):
+                loss_G_GAN_Feat = loss_G_GAN_Feat + D_weights * self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
+        loss_G_VGG = self.criterionVGG(fake_image, real_image)
+        loss_G_distortion = self.criterionDistortion(fake_image, real_image)
+        return loss_G_GAN, loss_G_GAN_Feat, loss_G_VGG, loss_G_distortion, loss_D_real, loss_D_fake
+
+    def _to_uint8_float(self, t):
+        """tensor2im (ctu/utils/misc.py:64-95) on-device: (x*std+mean)*255 in float64, clip, TRUNCATE to uint8."""
+        mean = torch.tensor(_opt(self.opt, 'normalize_mean', (0.5, 0.5, 0.5)), dtype=torch.float64, device=t.device)
+        std = torch.tensor(_opt(self.opt, 'normalize_std', (1.0, 1.0, 1.0)), dtype=torch.float64, device=t.device)
+        x = (t.detach().float().double() * std.view(1, -1, 1, 1) + mean.view(1, -1, 1, 1)) * 255.0
+        return x.clamp_(0, 255).to(torch.uint8).to(torch.float)
+
+    def get_eval_loss(self, x_dict):
+        recon = self.get_img(x_dict)
+        real = x_dict['image'].cuda(non_blocking=True).float()
+        return self.criterionDistortion(self._to_uint8_float(recon), self._to_uint8_float(real))

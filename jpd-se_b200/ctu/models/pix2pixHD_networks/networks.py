@@ -1,13 +1,19 @@
-"""Drop-in for the generator half of ``ctu.models.pix2pixHD_networks.networks``.
+"""Drop-in for ``ctu.models.pix2pixHD_networks.networks``.
 
 Same names, signatures, state-dict keys and error behaviour as the reference
 (ctu/models/pix2pixHD_networks/networks.py:19-56 ``weights_init`` / ``get_norm_layer`` / ``define_G``,
-:198-263 ``GlobalGenerator``, :266-305 ``ResnetBlock``), but ``GlobalGenerator.forward`` runs the
-hand-written sm_100a kernels of libjpdse_b200.so instead of ATen/cuDNN. The ``nn`` modules below only
-hold the parameters (so ``net_G.pth`` loads unchanged and ``print(netG)`` looks the same); none of their
-``forward`` methods is on the path.
+:198-263 ``GlobalGenerator``, :266-305 ``ResnetBlock``), but ``GlobalGenerator.forward`` -- and, when gradients
+are enabled, its backward -- run the hand-written sm_100a kernels of libjpdse_b200.so instead of ATen/cuDNN.
+The generator's ``nn`` modules only hold the parameters (so ``net_G.pth`` loads unchanged and ``print(netG)``
+looks the same); none of their ``forward`` methods is on the path.
+
+The training step's other networks (SURVEY.md section 8f "next" rows, not the accelerated path) are plain
+PyTorch modules with the reference's parameter names so ``net_D.pth`` loads unchanged:
+``define_D`` / ``MultiscaleDiscriminator`` / ``NLayerDiscriminator`` (:58-66, :371-471), ``GANLoss`` (:80-122),
+``VGGLoss`` / ``Vgg19`` (:124-139, :474-504).
 """
 import functools
+import os
 
 import torch
 import torch.nn as nn
@@ -54,6 +60,43 @@ def define_G(input_nc, output_nc, ngf, netG, n_downsample_global=3, n_blocks_glo
         netG.cuda(gpu_ids[0])
     netG.apply(weights_init)
     return netG
+
+
+class _GeneratorFunction(torch.autograd.Function):
+    """Autograd node of the whole generator: forward and backward are GeneratorPlan kernel sequences."""
+
+    @staticmethod
+    def forward(ctx, module, plan, run, *params):
+        out = run(plan)
+        ctx.module, ctx.plan, ctx.generation = module, plan, plan.generation
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        module, plan = ctx.module, ctx.plan
+        if plan.generation != ctx.generation:
+            raise JpdseError('jpdse_b200: the generator ran another forward before this backward; its saved '
+                             'activations are gone (run one forward per backward)')
+        named = list(module.named_parameters())
+        shapes = {n[:-len('.weight')]: tuple(p.shape) for n, p in named if n.endswith('.weight')}
+        reducer = module.grad_reducer
+        if reducer is not None:
+            reducer.begin([(n, p) for n, p in named])
+        grads = plan.backward(grad_out.contiguous().float(), shapes,
+                              on_grad=None if reducer is None else reducer.ready,
+                              alloc=None if reducer is None else reducer.alloc)
+        out = []
+        for n, p in named:
+            g = grads.get(n)
+            if g is None and p.requires_grad:
+                # a conv bias in front of an affine-free InstanceNorm: its gradient is exactly zero
+                g = reducer.alloc(n, tuple(p.shape)).zero_() if reducer is not None else torch.zeros_like(p)
+                if reducer is not None:
+                    reducer.ready(n, g)
+            out.append(g if p.requires_grad else None)
+        if reducer is not None:
+            reducer.finish()
+        return (None, None, None) + tuple(out)
 
 
 class ResnetBlock(nn.Module):
@@ -106,20 +149,25 @@ class GlobalGenerator(nn.Module):
         self.model = nn.Sequential(*model)
         self._plans = {}
         self._packed_version = {}
+        # data-parallel hook: an object with begin / alloc / ready / finish (jpdse_b200.ddp.GradReducer) that
+        # all-reduces each gradient while the rest of the backward is still running
+        self.grad_reducer = None
 
     # ------------------------------------------------------------------ engine plumbing
     def _weights_version(self):
         return tuple((p.data_ptr(), p._version) for p in self.parameters())
 
-    def plan_for(self, batch, height, width, device):
+    def plan_for(self, batch, height, width, device, training=False):
         """GeneratorPlan (buffers + packed weights) for this problem size, re-packed when weights change."""
-        key = (batch, height, width, str(device))
+        key = (batch, height, width, str(device), bool(training))
         plan = self._plans.get(key)
         if plan is None:
             plan = GeneratorPlan(self.input_nc, self.output_nc, self.ngf, self.n_downsampling, self.n_blocks, batch,
-                                 height, width, device)
-            self._plans = {key: plan}  # one live plan: activations at batch 16 are several GB
-            self._packed_version = {}
+                                 height, width, device, training=training)
+            # one live plan per mode: activations at batch 16 are several GB
+            self._plans = {k: v for k, v in self._plans.items() if k[4] != bool(training)}
+            self._plans[key] = plan
+            self._packed_version.pop(key, None)
         ver = self._weights_version()
         if self._packed_version.get(key) != ver:
             plan.load_weights({k: v for k, v in self.state_dict().items()})
@@ -130,16 +178,26 @@ class GlobalGenerator(nn.Module):
         if not input.is_cuda:
             raise JpdseError('jpdse_b200 GlobalGenerator runs on a B200 only; got a %s tensor (no CPU fallback)'
                              % input.device)
-        if torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError('jpdse_b200: generator backward is not implemented yet; call under '
-                                      'torch.no_grad() (trainer.get_img does)')
+        if torch.is_grad_enabled() and input.requires_grad:
+            raise NotImplementedError('jpdse_b200: the generator input (labels + decoded image) takes no gradient; '
+                                      'detach it (the reference path never differentiates it)')
+
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+
+    def _run(self, batch, height, width, device, run):
+        """Run `run(plan)`; with gradients enabled the call becomes one autograd node over all parameters."""
+        if not self._wants_grad():
+            return run(self.plan_for(batch, height, width, device)).clone()
+        plan = self.plan_for(batch, height, width, device, training=True)
+        return _GeneratorFunction.apply(self, plan, run, *self.parameters())
 
     def forward(self, input, mode='get_continuous_img'):
         if mode == 'get_continuous_img':
             self._check_runnable(input)
             B, _, H, W = input.shape
-            plan = self.plan_for(B, H, W, input.device)
-            return plan.forward_nchw(input.contiguous().float()).clone()
+            x = input.detach().contiguous().float()
+            return self._run(B, H, W, input.device, lambda plan: plan.forward_nchw(x))
         elif mode == 'get_binary_code':
             if not self.binarize:
                 raise AttributeError('Generator: no binarizer found')
@@ -151,5 +209,165 @@ class GlobalGenerator(nn.Module):
         """Fused preprocess + generator: skips the (B,39,H,W) float tensor of pix2pixHD_model.py:595."""
         self._check_runnable(image)
         B, _, H, W = image.shape
-        plan = self.plan_for(B, H, W, image.device)
-        return plan.forward_from_maps(label, instance, image, num_labels).clone()
+        image = image.detach()
+        return self._run(B, H, W, image.device, lambda plan: plan.forward_from_maps(label, instance, image, num_labels))
+
+
+# ================================================================================================== training-only parts
+# Plain PyTorch (cuDNN) -- outside the accelerated path (SURVEY.md section 8f). Parameter names follow the
+# reference so checkpoints interchange.
+def define_D(input_nc, ndf, n_layers_D, norm='instance', use_sigmoid=False, num_D=1, getIntermFeat=False, gpu_ids=[]):
+    # networks.py:58-66
+    netD = MultiscaleDiscriminator(input_nc, ndf, n_layers_D, get_norm_layer(norm_type=norm), use_sigmoid, num_D,
+                                   getIntermFeat)
+    if len(gpu_ids) > 0:
+        assert (torch.cuda.is_available())
+        netD.cuda(gpu_ids[0])
+    netD.apply(weights_init)
+    return netD
+
+
+def _patchgan_stages(input_nc, ndf, n_layers, norm_layer, use_sigmoid):
+    """The PatchGAN as a list of stages (networks.py:428-454): 4x4 convs, pad 2, stride 2 for the first
+    n_layers stages then stride 1, widths doubling up to 512, LeakyReLU(0.2), norm on all but the first / last."""
+    widths = [ndf]
+    for _ in range(1, n_layers + 1):
+        widths.append(min(widths[-1] * 2, 512))
+    stages = [[nn.Conv2d(input_nc, ndf, kernel_size=4, stride=2, padding=2), nn.LeakyReLU(0.2, True)]]
+    for n in range(1, n_layers + 1):
+        stride = 2 if n < n_layers else 1
+        stages.append([nn.Conv2d(widths[n - 1], widths[n], kernel_size=4, stride=stride, padding=2),
+                       norm_layer(widths[n]), nn.LeakyReLU(0.2, True)])
+    stages.append([nn.Conv2d(widths[-1], 1, kernel_size=4, stride=1, padding=2)])
+    if use_sigmoid:
+        stages.append([nn.Sigmoid()])
+    return stages
+
+
+class NLayerDiscriminator(nn.Module):
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, use_sigmoid=False, getIntermFeat=False):
+        super(NLayerDiscriminator, self).__init__()
+        self.getIntermFeat = getIntermFeat
+        self.n_layers = n_layers
+        stages = _patchgan_stages(input_nc, ndf, n_layers, norm_layer, use_sigmoid)
+        if getIntermFeat:
+            for n, st in enumerate(stages):
+                setattr(self, 'model' + str(n), nn.Sequential(*st))
+        else:
+            self.model = nn.Sequential(*[m for st in stages for m in st])
+
+    def forward(self, input):
+        if not self.getIntermFeat:
+            return self.model(input)
+        feats, x = [], input
+        for n in range(self.n_layers + 2):
+            x = getattr(self, 'model' + str(n))(x)
+            feats.append(x)
+        return feats
+
+
+class MultiscaleDiscriminator(nn.Module):
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, use_sigmoid=False, num_D=3,
+                 getIntermFeat=False):
+        super(MultiscaleDiscriminator, self).__init__()
+        self.num_D, self.n_layers, self.getIntermFeat = num_D, n_layers, getIntermFeat
+        for i in range(num_D):
+            netD = NLayerDiscriminator(input_nc, ndf, n_layers, norm_layer, use_sigmoid, getIntermFeat)
+            if getIntermFeat:
+                for j in range(n_layers + 2):
+                    setattr(self, 'scale%d_layer%d' % (i, j), getattr(netD, 'model' + str(j)))
+            else:
+                setattr(self, 'layer' + str(i), netD.model)
+        self.downsample = nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
+
+    def singleD_forward(self, model, input, keep_input=False):
+        if self.getIntermFeat:
+            result = [input]
+            for stage in model:
+                result.append(stage(result[-1]))
+            return result if keep_input else result[1:]
+        return [input, model(input)] if keep_input else [model(input)]
+
+    def forward(self, input, keep_input=False):
+        result, x = [], input
+        for i in range(self.num_D):
+            s = self.num_D - 1 - i  # the last-registered scale sees the full-resolution input
+            if self.getIntermFeat:
+                model = [getattr(self, 'scale%d_layer%d' % (s, j)) for j in range(self.n_layers + 2)]
+            else:
+                model = getattr(self, 'layer' + str(s))
+            result.append(self.singleD_forward(model, x, keep_input=keep_input))
+            if i != self.num_D - 1:
+                x = self.downsample(x)
+        return result
+
+
+class GANLoss(nn.Module):
+    """networks.py:80-122: MSE (LSGAN) or BCE against a constant target, summed over the discriminator scales."""
+
+    def __init__(self, use_lsgan=True, target_real_label=1.0, target_fake_label=0.0, tensor=torch.FloatTensor):
+        super(GANLoss, self).__init__()
+        self.real_label, self.fake_label = target_real_label, target_fake_label
+        self.loss = nn.MSELoss() if use_lsgan else nn.BCELoss()
+
+    def get_target_tensor(self, input, target_is_real):
+        return torch.full_like(input, self.real_label if target_is_real else self.fake_label, requires_grad=False)
+
+    def __call__(self, input, target_is_real):
+        if isinstance(input[0], list):
+            loss = 0
+            for scale in input:
+                loss = loss + self.loss(scale[-1], self.get_target_tensor(scale[-1], target_is_real))
+            return loss
+        return self.loss(input[-1], self.get_target_tensor(input[-1], target_is_real))
+
+
+class Vgg19(nn.Module):
+    """networks.py:474-504: torchvision VGG19 features cut after relu1_1, 2_1, 3_1, 4_1, 5_1, frozen."""
+    CUTS = (2, 7, 12, 21, 30)
+
+    def __init__(self, requires_grad=False):
+        super(Vgg19, self).__init__()
+        from torchvision import models
+        # the reference calls models.vgg19(pretrained=True) (networks.py:477), which downloads on first use; offline
+        # boxes only have it if the checkpoint is already in the torch hub cache -- otherwise random weights keep the
+        # step runnable (the loss is still a fixed random-feature distance)
+        wts = models.VGG19_Weights.IMAGENET1K_V1
+        cached = os.path.join(torch.hub.get_dir(), 'checkpoints', os.path.basename(wts.url))
+        if os.path.isfile(cached) or os.environ.get('JPDSE_ALLOW_DOWNLOAD'):
+            feats = models.vgg19(weights=wts).features
+        else:
+            print('jpdse_b200: pretrained VGG19 not in %s; using random weights' % os.path.dirname(cached))
+            feats = models.vgg19(weights=None).features
+        lo = 0
+        for k, hi in enumerate(self.CUTS):
+            seq = nn.Sequential()
+            for x in range(lo, hi):
+                seq.add_module(str(x), feats[x])
+            setattr(self, 'slice%d' % (k + 1), seq)
+            lo = hi
+        if not requires_grad:
+            for param in self.parameters():
+                param.requires_grad = False
+
+    def forward(self, X):
+        out = []
+        for k in range(5):
+            X = getattr(self, 'slice%d' % (k + 1))(X)
+            out.append(X)
+        return out
+
+
+class VGGLoss(nn.Module):
+    def __init__(self, gpu_ids):
+        super(VGGLoss, self).__init__()
+        self.vgg = Vgg19().cuda() if len(gpu_ids) else Vgg19()
+        self.criterion = nn.L1Loss()
+        self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+
+    def forward(self, x, y):
+        x_vgg, y_vgg = self.vgg(x), self.vgg(y)
+        loss = 0
+        for wgt, fx, fy in zip(self.weights, x_vgg, y_vgg):
+            loss = loss + wgt * self.criterion(fx, fy.detach())
+        return loss

@@ -1,33 +1,108 @@
-"""Mirror of ``ctu.trainers.pix2pixHD_trainer.Pix2PixHDTrainer`` for the accelerated (inference) path.
+"""Mirror of ``ctu.trainers.pix2pixHD_trainer.Pix2PixHDTrainer``.
 
-Reference: ctu/trainers/pix2pixHD_trainer.py:11-30 (ctor), :113-116 (get_img) and the BaseTrainer
-counters of ctu/trainers/base_trainer.py:10-12. ``step`` and the eval/rate modes need pieces that are
-not on the accelerated path yet and raise.
+Reference: ctu/trainers/pix2pixHD_trainer.py:11-30 (ctor), :42-85 (step), :88-116 (eval / get_img), :119-141 (save)
+and the BaseTrainer counters of ctu/trainers/base_trainer.py:6-24. ``step`` keeps the reference's order -- generator
+loss backward + Adam step, then discriminator loss backward + Adam step -- with the generator forward/backward on the
+sm_100a kernels. Under ``torch.distributed`` (one process per GPU) the generator gradients are all-reduced while the
+backward is still running (jpdse_b200.ddp.GradReducer) and the discriminator gradients in one flat call.
 """
+import os
+
 import torch
 import torch.nn as nn
 
+from ... import ddp
 from ..models.pix2pixHD_model import Pix2PixHDModel
 
 
+def _opt(opt, name, default):
+    return getattr(opt, name, default)
+
+
 class BaseTrainer(nn.Module):
-    def __init__(self, opt):
+    def __init__(self, opt, mode='train'):
         super(BaseTrainer, self).__init__()
         self.opt = opt
-        self.start_epoch = 1
-        self.best_val_loss = float('inf')
-        self.steps_taken = 0
+        if mode == 'train':
+            self.steps_taken = 0
+            self.start_epoch = 0
+            self.best_val_loss = 1e12
+            if _opt(opt, 'tf_log', False):
+                raise NotImplementedError('jpdse_b200: --tf_log (tensorflow summaries) is outside the accelerated path')
+        elif mode != 'test':
+            raise ValueError('Invalid trainer mode: {}'.format(mode))
+        self.mode = mode
+
+    def load(self):
+        pass
 
 
 class Pix2PixHDTrainer(BaseTrainer):
-    def __init__(self, opt, mode):
-        super(Pix2PixHDTrainer, self).__init__(opt)
-        if mode not in ('train', 'test'):
-            raise ValueError('Invalid trainer mode: {}'.format(mode))
-        if mode == 'train':
-            raise NotImplementedError('jpdse_b200 Pix2PixHDTrainer: train mode needs the generator backward '
-                                      '(not implemented yet)')
+    def __init__(self, opt, mode='train'):
+        super(Pix2PixHDTrainer, self).__init__(opt, mode)
         self.model = Pix2PixHDModel(opt)
+        if len(_opt(opt, 'gpu_ids', [0])) > 0:
+            self.model = self.model.cuda()
+        if mode == 'train':
+            self.optimizer_G, self.optimizer_D = self.model.create_optimizers(opt)
+            if _opt(opt, 'schedule_lr', False):
+                from torch.optim.lr_scheduler import ReduceLROnPlateau
+                kw = dict(factor=_opt(opt, 'lr_decay_factor', .1), patience=_opt(opt, 'lr_decay_patience', 5))
+                self.scheduler_G = ReduceLROnPlateau(self.optimizer_G, 'min', **kw)
+                self.scheduler_D = ReduceLROnPlateau(self.optimizer_D, 'min', **kw)
+            self.lambda_distortion_weight = 1.
+            if ddp._world() > 1:
+                ddp.broadcast_parameters(self.model.netG)
+                ddp.broadcast_parameters(self.model.netD)
+                self.model.netG.grad_reducer = ddp.GradReducer()
+
+    def _get_train_loss(self, x_dict):
+        return self.model(x_dict, self.opt, mode='get_train_loss')
+
+    def scheduler_step(self, val_loss_value):
+        self.scheduler_G.step(val_loss_value)
+        self.scheduler_D.step(val_loss_value)
+
+    def step(self, x_dict):
+        # pix2pixHD_trainer.py:42-85
+        opt = self.opt
+        self.train()
+        loss_dict = dict(zip(self.model.loss_names, self._get_train_loss(x_dict)))
+
+        def term(name, flag, scale=1.0):
+            if _opt(opt, flag, False):
+                return loss_dict[name].new_zeros(1, requires_grad=True)
+            return loss_dict[name] * scale if scale != 1.0 else loss_dict[name]
+
+        loss_D = (loss_dict['D_fake'] + loss_dict['D_real']) * 0.5 if not _opt(opt, 'no_d_gan_loss', False) \
+            else loss_dict['D_fake'].new_zeros(1, requires_grad=True)
+        lam_feat = _opt(opt, 'lambda_feat', 10.0)
+        loss_G = (term('G_GAN', 'no_g_gan_loss') + term('G_VGG', 'no_vgg_loss', lam_feat)
+                  + term('G_GAN_Feat', 'no_gan_feat_loss', lam_feat)
+                  + term('G_Distortion', 'no_distortion_loss',
+                         _opt(opt, 'lambda_distortion', 10.0) * self.lambda_distortion_weight))
+        if not _opt(opt, 'quiet', False):
+            print('g_gan: {:.4f}, g_gan_feat_match: {:.4f}, g_vgg: {:.4f}, g_distortion ({}): {:.4f}, d_real: {:.4f}, '
+                  'd_fake: {:.4f}'.format(loss_dict['G_GAN'].item(), loss_dict['G_GAN_Feat'].item(),
+                                          loss_dict['G_VGG'].item(), _opt(opt, 'distortion_loss_fn', 'l1'),
+                                          loss_dict['G_Distortion'].item(), loss_dict['D_real'].item(),
+                                          loss_dict['D_fake'].item()))
+        self.optimizer_G.zero_grad()
+        loss_G.backward()  # generator gradients come back already averaged over the ranks
+        self.optimizer_G.step()
+        self.optimizer_D.zero_grad()  # drops the netD gradients loss_G.backward() produced
+        loss_D.backward()
+        ddp.allreduce_grads(self.model.netD.parameters())
+        self.optimizer_D.step()
+        self.steps_taken += 1
+        if _opt(opt, 'anneal_lambda', False) and not (self.steps_taken % _opt(opt, 'anneal_interval', 5000)):
+            self.lambda_distortion_weight *= _opt(opt, 'anneal_factor', 5.)
+        return loss_dict['G_Distortion'].item()
+
+    def get_eval_loss(self, x_dict):
+        self.eval()
+        with torch.no_grad():
+            return self.model(x_dict, self.opt, mode='get_eval_loss').item()
 
     def get_img(self, x_dict):
         # pix2pixHD_trainer.py:113-116
@@ -35,8 +110,34 @@ class Pix2PixHDTrainer(BaseTrainer):
         with torch.no_grad():
             return self.model(x_dict, self.opt, mode='get_img')
 
-    def step(self, x_dict):
-        raise NotImplementedError('jpdse_b200 Pix2PixHDTrainer.step: generator backward not implemented yet')
+    def get_code(self, x_dict):
+        raise NotImplementedError('jpdse_b200 Pix2PixHDTrainer.get_code: needs the encoder/binarizer path')
 
-    def get_eval_loss(self, x_dict):
-        raise NotImplementedError('jpdse_b200 Pix2PixHDTrainer.get_eval_loss: not on the accelerated path yet')
+    def get_eval_rate(self, x_dict):
+        raise NotImplementedError('jpdse_b200 Pix2PixHDTrainer.get_eval_rate: needs the encoder/binarizer path')
+
+    def save(self, epoch, val_loss_value):
+        # pix2pixHD_trainer.py:119-141
+        self.best_val_loss = val_loss_value
+        states = {'epoch': epoch, 'steps_taken': self.steps_taken,
+                  'optimizer_G_state_dict': self.optimizer_G.state_dict(),
+                  'optimizer_D_state_dict': self.optimizer_D.state_dict(), 'best_val_loss': self.best_val_loss}
+        if _opt(self.opt, 'schedule_lr', False):
+            states['scheduler_G_state_dict'] = self.scheduler_G.state_dict()
+            states['scheduler_D_state_dict'] = self.scheduler_D.state_dict()
+        if _opt(self.opt, 'anneal_lambda', False):
+            states['lambda_distortion_weight'] = self.lambda_distortion_weight
+        torch.save(states, os.path.join(self.opt.save_dir, 'stats_and_optim.pt'))
+        self.model.save()
+
+    def load(self):
+        path = os.path.join(self.opt.checkpoints_dir, "stats_and_optim.pt")
+        states = torch.load(path, map_location='cpu')
+        if self.mode == 'train':
+            self.start_epoch = states['epoch'] + 1
+            self.steps_taken = states['steps_taken']
+            self.best_val_loss = states['best_val_loss']
+            self.optimizer_G.load_state_dict(states['optimizer_G_state_dict'])
+            self.optimizer_D.load_state_dict(states['optimizer_D_state_dict'])
+            if 'lambda_distortion_weight' in states:
+                self.lambda_distortion_weight = states['lambda_distortion_weight']

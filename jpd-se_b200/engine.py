@@ -1,4 +1,4 @@
-"""Forward plan of the pix2pixHD GlobalGenerator on the sm_100a kernels.
+"""Forward and backward plans of the pix2pixHD GlobalGenerator on the sm_100a kernels.
 
 Mirrors the 40-module Sequential of the reference (ctu/models/pix2pixHD_networks/networks.py:198-263,
 ResnetBlock :266-305) as a fixed sequence of C-ABI calls on pre-allocated NHWC bf16 buffers:
@@ -10,22 +10,37 @@ ResnetBlock :266-305) as a fixed sequence of C-ABI calls on pre-allocated NHWC b
 Every InstanceNorm's statistics come out of the producing conv's epilogue; the "IN" boxes above are
 the one-read/one-write apply kernel, which also writes the reflect border the next conv needs.
 Conv biases in front of an affine-free InstanceNorm cancel exactly and are not applied.
+
+Backward (``training=True`` plans; what autograd does for ``loss_G.backward()`` in the reference,
+ctu/trainers/pix2pixHD_trainer.py:69) walks the same layers in reverse. Per layer:
+
+    g (grad w.r.t. the layer's reflect-padded output) --reduce--> dy = relu-mask * (fold(g) + skip), (S1, S2)
+      --apply--> dx = IN backward, zero-bordered --wgrad--> dW      (MN-major tcgen05 GEMM, conv_wgrad.cu)
+                                                 --dgrad--> g of the previous layer (the forward igemm kernel with
+                                                            role-swapped kinds: s2 <-> ConvT, 3x3/7x7 -> FULL)
 """
 import torch
 
 from . import ops
-from ._lib import (CONV3X3_PAD1, CONV3X3_S2, CONV7X7_PAD3, CONVT3X3_S2, EPI_BIAS_TANH_NCHW, EPI_RAW_STATS,
-                   JpdseError)
+from ._lib import (CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_FULL, CONV7X7_PAD3, CONVT3X3_S2, EPI_BIAS_TANH_NCHW,
+                   EPI_RAW, EPI_RAW_STATS, JpdseError)
 
 
 def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+class _Layer:
+    """One conv + InstanceNorm stage of the plan (forward record used by backward)."""
+    __slots__ = ("name", "conv", "dgrad", "x_in", "raw", "stats", "out", "out_pad", "h", "w", "c", "relu", "residual",
+                 "consumer_reads_border")
+
+
 class GeneratorPlan:
     """Buffers + conv descriptors for one (batch, H, W) problem size."""
 
-    def __init__(self, input_nc, output_nc, ngf, n_downsampling, n_blocks, batch, height, width, device):
+    def __init__(self, input_nc, output_nc, ngf, n_downsampling, n_blocks, batch, height, width, device,
+                 training=False):
         if ngf % 64:
             raise JpdseError("jpdse_b200 generator needs ngf %% 64 == 0 (got %d)" % ngf)
         if output_nc > 128:
@@ -35,59 +50,84 @@ class GeneratorPlan:
         div = 1 << n_downsampling
         if height % div or width % div:
             raise JpdseError("image size %dx%d is not divisible by 2^%d" % (height, width, n_downsampling))
+        if training and (ngf != 64 or output_nc > 8 or _round_up(input_nc, 8) != 40):
+            raise JpdseError("jpdse_b200 generator backward supports ngf == 64, output_nc <= 8 and 33..40 input channels")
         self.input_nc, self.output_nc, self.ngf = input_nc, output_nc, ngf
         self.n_down, self.n_blocks = n_downsampling, n_blocks
         self.B, self.H, self.W = batch, height, width
         self.device = device
+        self.training = training
         self.c_in_pad = _round_up(input_nc, 8)
         B, H, W = batch, height, width
 
         # ---- convolutions (weights are packed later by load_weights)
-        self.convs = {}  # state-dict prefix -> ops.Conv
-        self.steps = []  # executable plan
+        self.convs = {}   # state-dict prefix -> forward ops.Conv
+        self.dgrads = {}  # state-dict prefix -> data-gradient ops.Conv (training plans; same weight tensor, other packing)
         self.stem = ops.Conv(CONV7X7_PAD3, EPI_RAW_STATS, B, H, W, 3, self.c_in_pad, input_nc, ngf, device)
         self.convs["model.1"] = self.stem
         idx = 4
         self.down = []
         c, h, w = ngf, H, W
         for _ in range(n_downsampling):
+            name = "model.%d" % idx
             cv = ops.Conv(CONV3X3_S2, EPI_RAW_STATS, B, h, w, 0, c, c, 2 * c, device)
-            self.convs["model.%d" % idx] = cv
-            self.down.append(cv)
+            self.convs[name] = cv
+            if training:  # dgrad of a stride-2 conv == ConvTranspose forward on the same weight memory
+                self.dgrads[name] = ops.Conv(CONVT3X3_S2, EPI_RAW, B, h // 2, w // 2, 0, 2 * c, 2 * c, c, device)
+            self.down.append((name, cv))
             idx += 3
             c, h, w = 2 * c, h // 2, w // 2
         self.cb, self.hb, self.wb = c, h, w  # bottleneck
         self.res = []
         for _ in range(n_blocks):
+            n1, n2 = "model.%d.conv_block.1" % idx, "model.%d.conv_block.5" % idx
             c1 = ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, B, h, w, 1, c, c, c, device)
             c2 = ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, B, h, w, 1, c, c, c, device)
-            self.convs["model.%d.conv_block.1" % idx] = c1
-            self.convs["model.%d.conv_block.5" % idx] = c2
-            self.res.append((c1, c2))
+            self.convs[n1], self.convs[n2] = c1, c2
+            if training:
+                self.dgrads[n1] = ops.Conv(CONV3X3_FULL, EPI_RAW, B, h, w, 2, c, c, c, device)
+                self.dgrads[n2] = ops.Conv(CONV3X3_FULL, EPI_RAW, B, h, w, 2, c, c, c, device)
+            self.res.append((n1, c1, n2, c2))
             idx += 1
         self.up = []
         pad_in = 1 if n_blocks > 0 else 0  # the last res block leaves a reflect border we skip over
         for i in range(n_downsampling):
+            name = "model.%d" % idx
             cv = ops.Conv(CONVT3X3_S2, EPI_RAW_STATS, B, h, w, pad_in if i == 0 else 0, c, c, c // 2, device)
-            self.convs["model.%d" % idx] = cv
-            self.up.append(cv)
+            self.convs[name] = cv
+            if training:  # dgrad of a ConvTranspose == stride-2 conv on the same weight memory
+                self.dgrads[name] = ops.Conv(CONV3X3_S2, EPI_RAW, B, 2 * h, 2 * w, 0, c // 2, c // 2, c, device)
+            self.up.append((name, cv))
             idx += 3
             c, h, w = c // 2, 2 * h, 2 * w
+        self.head_name = "model.%d" % (idx + 1)
         self.head = ops.Conv(CONV7X7_PAD3, EPI_BIAS_TANH_NCHW, B, H, W, 3, ngf, ngf, output_nc, device)
-        self.convs["model.%d" % (idx + 1)] = self.head
+        self.convs[self.head_name] = self.head
+        if training:
+            self.dgrads[self.head_name] = ops.Conv(CONV7X7_FULL, EPI_RAW, B, H, W, 6, 8, output_nc, ngf, device)
         self.flops = sum(cv.flops for cv in self.convs.values())
 
         # ---- buffers
-        # largest raw conv output / largest (padded) activation, in bf16 elements
-        raw_elems, act_elems = B * H * W * ngf, B * (H + 6) * (W + 6) * ngf
-        self.raw = torch.empty(raw_elems, dtype=torch.bfloat16, device=device)
-        self.act = [torch.zeros(act_elems + 2048, dtype=torch.bfloat16, device=device) for _ in range(3)]
         self.x0 = ops.alloc_nhwc(B, H + 6, W + 6, self.c_in_pad, device)
         n_norm = 1 + n_downsampling + 2 * n_blocks + n_downsampling
         cmax = max(ngf << n_downsampling, ngf)
         self.stats = torch.zeros((n_norm, B, cmax, 2), dtype=torch.float64, device=device)
         self.out = torch.empty((B, output_nc, H, W), dtype=torch.float32, device=device)
-        self.weights_version = None
+        raw_elems, act_elems = B * H * W * ngf, B * (H + 6) * (W + 6) * ngf
+        if not training:
+            # largest raw conv output / largest (padded) activation, in bf16 elements
+            self.raw = torch.empty(raw_elems, dtype=torch.bfloat16, device=device)
+            self.act = [torch.zeros(act_elems + 2048, dtype=torch.bfloat16, device=device) for _ in range(3)]
+        else:
+            self._saved = {}  # (kind, layer index) -> per-layer tensors kept for backward
+            self.bwd_sums = torch.zeros((n_norm, B, cmax, 2), dtype=torch.float64, device=device)
+            self.g_buf = [torch.zeros(act_elems + 2048, dtype=torch.bfloat16, device=device) for _ in range(2)]
+            self.dy_buf = [torch.zeros(raw_elems, dtype=torch.bfloat16, device=device) for _ in range(3)]
+            dx_elems = max(raw_elems, B * (self.hb + 4) * (self.wb + 4) * self.cb)
+            self.dx_buf = torch.zeros(dx_elems + 2048, dtype=torch.bfloat16, device=device)
+            self.d_pre = torch.zeros(B * (H + 12) * (W + 12) * 8 + 2048, dtype=torch.bfloat16, device=device)
+        self.layers = []
+        self.generation = 0
 
     # ---- weights
     def load_weights(self, state_dict):
@@ -99,67 +139,89 @@ class GeneratorPlan:
                 w = w.to(self.device)
             if b is not None and b.device != self.device:
                 b = b.to(self.device)
-            cv.pack(w.contiguous().float(), None if b is None else b.contiguous().float())
+            w = w.detach().contiguous().float()
+            cv.pack(w, None if b is None else b.detach().contiguous().float())
+            dg = self.dgrads.get(prefix)
+            if dg is not None:
+                dg.pack(w)
 
     def _view(self, buf, B, H, W, C):
         return buf[: B * H * W * C].view(B, H, W, C)
 
-    def _stats(self, i, C):
+    def _stats(self, i, C, which=None):
         # contiguous (B, C, 2) slice of layer i's statistics
-        return self.stats[i].view(-1)[: self.B * C * 2].view(self.B, C, 2)
+        src = self.stats if which is None else which
+        return src[i].view(-1)[: self.B * C * 2].view(self.B, C, 2)
+
+    def _raw_buf(self, si, B, h, w, c):
+        if not self.training:
+            return self._view(self.raw, B, h, w, c)
+        key = ("raw", si)
+        if key not in self._saved:
+            self._saved[key] = torch.empty((B, h, w, c), dtype=torch.bfloat16, device=self.device)
+        return self._saved[key]
+
+    def _act_buf(self, si, slot, B, h, w, c):
+        """Activation (B,h,w,c) incl. border: rotating buffers for inference, one per layer for training."""
+        if not self.training:
+            return self._view(self.act[slot], B, h, w, c)
+        key = ("act", si)
+        if key not in self._saved:
+            self._saved[key] = ops.alloc_nhwc(B, h, w, c, self.device)
+        return self._saved[key]
+
+    def _norm(self, si, name, conv, x_in, h, w, c, pad, relu, slot, residual=None, consumer_reads_border=True):
+        """conv -> raw (+stats) -> InstanceNorm apply (+ReLU)(+residual)(+reflect pad). Returns the padded output."""
+        B = self.B
+        raw = self._raw_buf(si, B, h, w, c)
+        st = self._stats(si, c)
+        conv.forward(x_in, raw, st)
+        out = self._act_buf(si, slot, B, h + 2 * pad, w + 2 * pad, c)
+        ops.instnorm_apply(raw, st, out, B, h, w, c, pad, relu, residual=residual)
+        if self.training:
+            L = _Layer()
+            L.name, L.conv, L.dgrad, L.x_in, L.raw, L.stats, L.out = name, conv, self.dgrads.get(name), x_in, raw, st, out
+            L.out_pad, L.h, L.w, L.c, L.relu, L.residual = pad, h, w, c, relu, residual is not None
+            L.consumer_reads_border = consumer_reads_border
+            self.layers.append(L)
+        return out
 
     # ---- forward
     def forward_from_x0(self):
         """Runs the generator on self.x0 (bf16 NHWC, reflect-padded by 3); returns fp32 NCHW (B,out,H,W)."""
-        B = self.B
         self.stats.zero_()
         ops._count()
+        self.layers = []
+        self.generation += 1
         si = 0
-        # stem
         c, h, w = self.ngf, self.H, self.W
-        raw = self._view(self.raw, B, h, w, c)
-        self.stem.forward(self.x0, raw, self._stats(si, c))
         cur = 0
-        x = self._view(self.act[cur], B, h, w, c)
-        ops.instnorm_apply(raw, self._stats(si, c), x, B, h, w, c, 0, True)
+        x = self._norm(si, "model.1", self.stem, self.x0, h, w, c, 0, True, cur)
         si += 1
-        # downsampling
-        for i, cv in enumerate(self.down):
+        for i, (name, cv) in enumerate(self.down):
             c, h, w = 2 * c, h // 2, w // 2
-            raw = self._view(self.raw, B, h, w, c)
-            cv.forward(x, raw, self._stats(si, c))
             last = i == self.n_down - 1
             pad = (1 if self.n_blocks > 0 else 0) if last else 0
             cur ^= 1
-            x = self._view(self.act[cur], B, h + 2 * pad, w + 2 * pad, c)
-            ops.instnorm_apply(raw, self._stats(si, c), x, B, h, w, c, pad, True)
+            x = self._norm(si, name, cv, x, h, w, c, pad, True, cur)
             si += 1
-        # residual blocks: x (padded by 1) lives in act[cur]; t and the new x use the other two buffers
-        for c1, c2 in self.res:
-            raw = self._view(self.raw, B, h, w, c)
-            c1.forward(x, raw, self._stats(si, c))
-            t_idx = (cur + 1) % 3
-            t = self._view(self.act[t_idx], B, h + 2, w + 2, c)
-            ops.instnorm_apply(raw, self._stats(si, c), t, B, h, w, c, 1, True)
+        # residual blocks: x (padded by 1) lives in slot cur; t and the new x use the other two
+        for k, (n1, c1, n2, c2) in enumerate(self.res):
+            t = self._norm(si, n1, c1, x, h, w, c, 1, True, (cur + 1) % 3)
             si += 1
-            c2.forward(t, raw, self._stats(si, c))
             n_idx = (cur + 2) % 3
-            xn = self._view(self.act[n_idx], B, h + 2, w + 2, c)
-            ops.instnorm_apply(raw, self._stats(si, c), xn, B, h, w, c, 1, False, residual=x)
+            # the last block's border is skipped over by the first ConvTranspose
+            x = self._norm(si, n2, c2, t, h, w, c, 1, False, n_idx, residual=x,
+                           consumer_reads_border=k != self.n_blocks - 1)
             si += 1
-            x, cur = xn, n_idx
-        # upsampling
-        for i, cv in enumerate(self.up):
+            cur = n_idx
+        for i, (name, cv) in enumerate(self.up):
             c, h, w = c // 2, 2 * h, 2 * w
-            raw = self._view(self.raw, B, h, w, c)
-            cv.forward(x, raw, self._stats(si, c))
             last = i == self.n_down - 1
-            pad = 3 if last else 0
             cur = (cur + 1) % 3
-            x = self._view(self.act[cur], B, h + 2 * pad, w + 2 * pad, c)
-            ops.instnorm_apply(raw, self._stats(si, c), x, B, h, w, c, pad, True)
+            x = self._norm(si, name, cv, x, h, w, c, 3 if last else 0, True, cur)
             si += 1
-        # head
+        self.head_in = x
         self.head.forward(x, self.out)
         return self.out
 
@@ -176,3 +238,80 @@ class GeneratorPlan:
             raise JpdseError("num_labels + 4 must equal input_nc")
         ops.build_input(label, instance, image, num_labels, pad=3, c_pad=self.c_in_pad, out_nhwc=self.x0)
         return self.forward_from_x0()
+
+    # ---- backward
+    def backward(self, grad_out, weight_shapes, on_grad=None, alloc=None):
+        """grad_out: float32 (B,output_nc,H,W) = dL/d(generator output) of the LAST forward of this plan.
+
+        Returns {state-dict key: float32 gradient} for every conv weight and the head bias (the biases in front of an
+        InstanceNorm have an exactly-zero gradient and are not returned). `weight_shapes` maps prefix -> torch weight
+        shape. `on_grad(key, tensor)` is called as soon as a gradient's kernels are enqueued, in reverse layer order
+        (the hook the data-parallel all-reduce overlaps on). `alloc(key, shape)` may supply the gradient tensors (the
+        reducer hands out slices of one flat buffer so buckets are contiguous).
+        """
+        if not self.training:
+            raise JpdseError("this GeneratorPlan was built for inference (training=False)")
+        if not self.layers:
+            raise JpdseError("backward() called before forward()")
+        B, H, W = self.B, self.H, self.W
+        dev = self.device
+        grads = {}
+
+        def new(key, shape):
+            if alloc is not None:
+                return alloc(key, tuple(shape))
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+
+        def emit(key, t):
+            grads[key] = t
+            if on_grad is not None:
+                on_grad(key, t)
+
+        self.bwd_sums.zero_()
+        ops._count()
+        # ---- head: tanh', bias, wgrad, dgrad
+        d_pre = self._view(self.d_pre, B, H + 12, W + 12, 8)
+        dbias = new(self.head_name + ".bias", (self.output_nc,)).zero_()
+        ops.tanh_backward_nchw(grad_out, self.out, d_pre, dbias)
+        dw = new(self.head_name + ".weight", weight_shapes[self.head_name])
+        self.head.wgrad(self.head_in, d_pre, 6, dw)
+        emit(self.head_name + ".bias", dbias)
+        emit(self.head_name + ".weight", dw)
+        gi = 0
+        g = self._view(self.g_buf[gi], B, H + 6, W + 6, self.ngf)
+        self.dgrads[self.head_name].forward(d_pre, g)
+        g_pad = 3
+        skip, skip_idx = None, None  # second gradient of the current layer's output (ResnetBlock skip connection)
+        pending_idx = None           # dy buffer holding dL/dx_{k+1} until the walk reaches the producer of x_k
+        for si in range(len(self.layers) - 1, -1, -1):
+            L = self.layers[si]
+            h, w, c = L.h, L.w, L.c
+            if not L.consumer_reads_border:
+                g_pad = 0  # the consumer skipped the border: its dgrad produced an unpadded gradient
+            dy_idx = [i for i in range(3) if i != skip_idx and i != pending_idx][0]
+            dy = self._view(self.dy_buf[dy_idx], B, h, w, c)
+            sums = self._stats(si, c, self.bwd_sums)
+            ops.instnorm_backward_reduce(g, g_pad, skip, L.raw, L.stats, dy, sums, B, h, w, c, L.relu)
+            z = 2 if L.conv.kind == CONV3X3_PAD1 else 0
+            dx = self._view(self.dx_buf, B, h + 2 * z, w + 2 * z, c)
+            ops.instnorm_backward_apply(dy, L.raw, L.stats, sums, dx, z, B, h, w, c)
+            dw = new(L.name + ".weight", weight_shapes[L.name])
+            L.conv.wgrad(L.x_in, dx, z, dw)
+            emit(L.name + ".weight", dw)
+            if si == 0:
+                break  # the stem's input (labels + decoded image) needs no gradient
+            gi ^= 1
+            oh, ow = L.dgrad.out_hw
+            g = self._view(self.g_buf[gi], B, oh, ow, L.dgrad.cout)
+            L.dgrad.forward(dx, g)
+            g_pad = self.layers[si - 1].out_pad
+            skip, skip_idx = None, None
+            if L.residual:
+                # x_{k+1} = x_k + IN(...): this dy IS dL/dx_{k+1}; it reaches x_k through the skip connection,
+                # two layers further down (below conv_block.1)
+                pending_idx = dy_idx
+            elif L.conv.kind == CONV3X3_PAD1 and pending_idx is not None:
+                # conv_block.1: the layer below produced the block input x_k, gradient = fold(g) + dL/dx_{k+1}
+                skip_idx, pending_idx = pending_idx, None
+                skip = self._view(self.dy_buf[skip_idx], B, h, w, c)
+        return grads

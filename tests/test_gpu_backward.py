@@ -221,3 +221,135 @@ def test_tanh_backward(cuda):
     assert float((inner - pre.grad).abs().max()) <= 2.0 ** -8 * float(pre.grad.abs().max())
     assert float(got.double().abs().sum() - inner.double().abs().sum()) == 0.0  # zero border and zero pad channels
     assert torch.allclose(dbias.cpu(), pre.grad.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------ whole generator
+def _networks():
+    import importlib
+    return importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
+
+
+def _cos(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("n_down,n_blocks,B,H,W", [(2, 1, 2, 32, 64), (4, 2, 1, 128, 256)])
+def test_generator_gradients_vs_oracle(cuda, n_down, n_blocks, B, H, W):
+    """d(loss)/d(every generator parameter) through the sm_100a backward vs CPU fp32 autograd of the oracle.
+
+    Tolerance, calibrated like the forward's: at random init the gradient is very sensitive to the
+    bf16 rounding of the FORWARD activations (ReLU masks / InstanceNorm statistics flip) -- the oracle's own
+    bf16-operand emulation only reaches cosine 0.94-0.98 against its fp32 self on the deep layers (measured,
+    profiles/r1_grad_cosine_table.txt), so SURVEY's 0.999 is not reachable by ANY bf16 path. Per weight tensor:
+      cos(ours, fp32 reference)  >= cos(bf16 oracle, fp32 reference) - 0.02   (as close to fp32 as bf16 arithmetic gets)
+      cos(ours, bf16 oracle)     >= cos(bf16 oracle, fp32 reference) - 0.005  (closer to the emulation than that is to fp32)
+      the head (no ReLU / IN chaos behind it): cosine >= 0.9999; gradient norms within 5 %.
+    The per-kernel tests above pin every backward kernel tightly on identical operands.
+    """
+    from oracle import generator_oracle as orc
+    nw = _networks()
+    torch.manual_seed(99)
+    net = nw.define_G(39, 3, 64, "global", n_down, n_blocks, 1, 3, "instance", gpu_ids=[])
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    gen = torch.Generator().manual_seed(17)
+    x = torch.randn(B, 39, H, W, generator=gen)
+    target = torch.rand(B, 3, H, W, generator=gen) - 0.5
+
+    def loss_fn(y):  # L1 distortion + a smooth term, like the reference's L1 + feature losses
+        return 10.0 * (y - target).abs().mean() + (y * y).mean()
+
+    def oracle_grads(round_fn):
+        for v in sd.values():
+            v.grad = None
+        loss_fn(orc.generator_forward(sd, x, n_down, n_blocks, round_fn=round_fn)).backward()
+        return {k: v.grad.clone() for k, v in sd.items() if v.grad is not None}
+
+    class _RoundSTE(torch.autograd.Function):  # bf16 rounding with a straight-through gradient
+        @staticmethod
+        def forward(ctx, t):
+            return t.bfloat16().float()
+
+        @staticmethod
+        def backward(ctx, g):
+            return g
+
+    ref32 = oracle_grads(None)
+    ref16 = oracle_grads(_RoundSTE.apply)
+
+    net = net.to(cuda).train()
+    y = net(x.to(cuda))
+    assert y.requires_grad
+    loss_fn_dev = 10.0 * (y - target.to(cuda)).abs().mean() + (y * y).mean()
+    loss_fn_dev.backward()
+    torch.cuda.synchronize()
+    worst16, worst32 = 1.0, 1.0
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        got = p.grad.cpu()
+        assert torch.isfinite(got).all(), name
+        if name.endswith(".bias") and not name.startswith("model.%d." % (len(net.model) - 2)):
+            assert float(got.abs().max()) == 0.0  # bias in front of InstanceNorm: exactly zero gradient
+            continue
+        c16, c32 = _cos(got, ref16[name]), _cos(got, ref32[name])
+        cal = _cos(ref16[name], ref32[name])
+        worst16, worst32 = min(worst16, c16), min(worst32, c32)
+        ratio = float(got.norm() / ref16[name].norm())
+        assert c32 >= cal - 0.02, "%s: cosine %.5f vs the fp32 reference path (bf16 emulation reaches %.5f)" % (name, c32, cal)
+        assert c16 >= cal - 0.005, "%s: cosine %.5f vs the same-arithmetic oracle (calibration %.5f)" % (name, c16, cal)
+        if name.startswith("model.%d." % (len(net.model) - 2)):
+            assert c16 >= 0.9999 and c32 >= 0.9999, "head gradient cosine %.6f / %.6f" % (c16, c32)
+        assert 0.95 <= ratio <= 1.05, "%s: gradient norm ratio %.3f" % (name, ratio)
+    print("worst cosine: %.5f (bf16 oracle) %.5f (fp32 reference)" % (worst16, worst32))
+
+
+def test_generator_backward_guards(cuda):
+    import jpdse_b200
+    nw = _networks()
+    net = nw.define_G(39, 3, 64, "global", 2, 1, 1, 3, "instance", gpu_ids=[0]).train()
+    x = torch.randn(1, 39, 32, 64, device=cuda)
+    y1 = net(x)
+    net(x)  # a second forward overwrites the activations y1's backward needs
+    with pytest.raises(jpdse_b200.JpdseError):
+        y1.sum().backward()
+    with pytest.raises(NotImplementedError):
+        net(x.clone().requires_grad_(True))
+    with torch.no_grad():
+        assert not net(x).requires_grad
+
+
+def test_trainer_step_runs_and_learns(cuda, tmp_path):
+    """Pix2PixHDTrainer.step (ctu/trainers/pix2pixHD_trainer.py:42-85) end to end: losses finite, all parameters of G
+    and D move, and a few steps on one batch reduce the distortion."""
+    import importlib
+    import bench
+    tr = importlib.import_module("jpd-se_b200.ctu.trainers.pix2pixHD_trainer")
+    opt = bench.make_opt()
+    opt.is_train, opt.n_downsample_global, opt.n_blocks_global = True, 2, 2
+    opt.no_vgg_loss, opt.quiet, opt.save_dir, opt.checkpoints_dir = False, True, str(tmp_path), str(tmp_path)
+    torch.manual_seed(5)
+    trainer = tr.Pix2PixHDTrainer(opt, mode="train")
+    g = torch.Generator().manual_seed(1)
+    B, H, W = 2, 64, 128
+    x_dict = {"label": torch.randint(0, 35, (B, 1, H // 8, W // 8), generator=g).repeat_interleave(8, 2).repeat_interleave(8, 3).float(),
+              "instance": torch.randint(0, 5, (B, 1, H // 8, W // 8), generator=g).repeat_interleave(8, 2).repeat_interleave(8, 3).int(),
+              "image": torch.rand(B, 3, H, W, generator=g) - 0.5, "path": ["a", "b"]}
+    before = {k: v.detach().clone() for k, v in trainer.model.state_dict().items() if "vgg" not in k}
+    first = trainer.step(x_dict)
+    for _ in range(7):
+        last = trainer.step(x_dict)
+    assert first == first and last == last  # finite
+    assert last < first, "distortion did not go down (%.4f -> %.4f)" % (first, last)
+    moved = [k for k, v in trainer.model.state_dict().items() if k in before and not torch.equal(v, before[k])]
+    weights = [k for k in before if k.endswith(".weight")]
+    assert all(k in moved for k in weights)
+    assert trainer.steps_taken == 8
+    ev = trainer.get_eval_loss(x_dict)
+    assert ev == ev and ev >= 0
+    trainer.save(0, ev)
+    opt2 = bench.make_opt()
+    opt2.n_downsample_global, opt2.n_blocks_global, opt2.checkpoints_dir = 2, 2, str(tmp_path)
+    t2 = tr.Pix2PixHDTrainer(opt2, mode="test")
+    a = trainer.get_img(x_dict)
+    b = t2.get_img(x_dict)
+    assert torch.equal(a, b)
