@@ -156,6 +156,75 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_traffic(batch, height, width):
+    """DRAM bytes per launch of the roofline kernel from the committed `ncu --set full` capture (profiles/), only
+    when the capture was taken at this workload; else None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        d = json.load(f)
+    if (d.get("batch"), d.get("height"), d.get("width")) != (batch, height, width):
+        return None
+    return d.get("dram_bytes_per_launch")
+
+
+def train_measure(args, dev, local, rank, world, barrier):
+    """Generator forward+backward on the sm_100a kernels and the whole Pix2PixHDTrainer.step (netD / VGG / losses /
+    Adam in stock PyTorch), data-parallel over `world` GPUs with the gradient all-reduce overlapped with backward.
+    Not the headline metric: reported under "train"."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    tr = importlib.import_module("jpd-se_b200.ctu.trainers.pix2pixHD_trainer")
+    opt = make_opt()
+    opt.gpu_ids, opt.is_train, opt.quiet = [local], True, True
+    torch.manual_seed(1234)
+    trainer = tr.Pix2PixHDTrainer(opt, mode="train")
+    net = trainer.model.netG
+    B, H, W = args.train_batch, args.height, args.width
+    label, inst, image = synth_inputs(B, H, W, seed=4321 + rank)
+    x_dict = {"label": label.to(dev), "instance": inst.to(dev), "image": image.to(dev)}
+    steps = max(3, min(args.steps, 10))
+
+    def g_fwd_bwd():
+        for p in net.parameters():
+            p.grad = None
+        y = net.forward_from_maps(x_dict["label"], x_dict["instance"], x_dict["image"], 35)
+        ((y - x_dict["image"]).abs().mean() * 10.0).backward()
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    g_ms = timed(g_fwd_bwd)
+    step_ms = timed(lambda: trainer.step(x_dict))
+    scale = (H * W) / (512.0 * 1024.0)
+    # backward = dgrad + wgrad of every conv except the stem's dgrad (SURVEY.md 8d)
+    g_flops = (3 * FWD_FLOPS_PER_IMAGE - 128245039104.0) * scale * B
+    del trainer
+    torch.cuda.empty_cache()
+    return {"batch_per_gpu": B, "steps": steps, "generator_fwd_bwd_ms": g_ms,
+            "generator_fwd_bwd_images_per_s": world * B / (g_ms * 1e-3),
+            "generator_fwd_bwd_tflops_per_gpu": g_flops / (g_ms * 1e-3) / 1e12,
+            "trainer_step_ms": step_ms, "trainer_step_images_per_s": world * B / (step_ms * 1e-3),
+            "allreduce": "none (1 GPU)" if world == 1 else "730 MB fp32 generator gradients, bucketed, overlapped with backward (NCCL)",
+            "note": "generator forward/backward = jpdse_b200 kernels; netD, VGG (random weights offline), losses, Adam = PyTorch"}
+
+
 def workload_config(args):
     return {"workload": "pix2pixHD-BPG QF36 semantic-aware generator inference, batch %d at %dx%d, 35-class label map "
                         "+ instance edges + RGB, random-init weights" % (args.batch, args.width, args.height),
@@ -173,6 +242,8 @@ def main():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the (extra, non-headline) training-step measurement")
+    ap.add_argument("--train-batch", type=int, default=2, help="images per GPU of the training-step measurement")
     ap.add_argument("--layers", action="store_true", help="print a per-kernel-type time breakdown to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -219,7 +290,7 @@ def main():
         ops.launch_count = 0
         # events around the residual-block convs (the roofline kernel), on the launching stream
         res_events = []
-        res_convs = [cv for pair in plan.res for cv in pair]
+        res_convs = [cv for (_n1, c1, _n2, c2) in plan.res for cv in (c1, c2)]
         orig_forward = {id(cv): cv.forward for cv in res_convs}
 
         def timed(cv):
@@ -318,7 +389,14 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in pin.values())
     d2h = host_out[0].numel() * host_out[0].element_size()
 
+    # ---------------------------------------------------------------- training step (BASELINE.json configs[3]; extra)
+    train = None
+    if not args.no_train:
+        train = train_measure(args, dev, local, rank, world, barrier)
+
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     sustained, burst, peak_kind = load_peaks()
     scale = (H * W) / (512.0 * 1024.0)
@@ -332,8 +410,10 @@ def main():
             "roofline": {"kernel": "igemm_kernel<256> (ResnetBlock 3x3 conv 1024->1024)", "bound": "tensor",
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                          "frac_of_burst_peak": achieved / burst, "peak_source": peak_kind + " (bf16_tflops_sustained)",
-                         "launch_ms": res_ms, "flops_per_launch": res_flops, "traffic": None,
+                         "launch_ms": res_ms, "flops_per_launch": res_flops, "traffic": ncu_traffic(B, H, W),
                          "whole_forward_tflops": FWD_FLOPS_PER_IMAGE * scale * B / (ms_per_step * 1e-3) / 1e12}}
+    if train is not None:
+        line["train"] = train
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sec = cpu_reference_time(1, H, W, steps=3, warmup=1, weights={k: v.cpu() for k, v in netG.state_dict().items()})

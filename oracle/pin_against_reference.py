@@ -90,6 +90,41 @@ def main():
         assert torch.equal(Gf(xf), orc.generator_forward(Gf.state_dict(), xf, 4, 9))
     print("generator (full 182.6M-param architecture): oracle == reference (bit-exact)")
 
+    # ---------------------------------------------------------------- generator backward (autograd through the reference)
+    # loss_G.backward() (pix2pixHD_trainer.py:69) is autograd over the same modules: the oracle's functional forward
+    # must give the reference's gradients bit for bit on CPU.
+    G.train()
+    tgt = torch.rand(1, 3, 32, 64, generator=g) - 0.5
+    for p_ in G.parameters():
+        p_.grad = None
+    (10.0 * (G(x) - tgt).abs().mean()).backward()
+    sdg = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    (10.0 * (orc.generator_forward(sdg, x, cfg["n_down"], cfg["n_blocks"]) - tgt).abs().mean()).backward()
+    gsum = {}
+    for name, p_ in G.named_parameters():
+        assert torch.equal(p_.grad, sdg[name].grad), "oracle gradient != reference gradient for %s" % name
+        gsum[name] = np.array([float(p_.grad.double().sum()), float(p_.grad.double().abs().sum())])
+    np.savez_compressed(os.path.join(GOLDEN, "generator_small_grads.npz"), target=tgt.numpy(),
+                        names=np.array(list(gsum.keys())), sums=np.stack(list(gsum.values())))
+    G.eval()
+    print("generator backward: oracle autograd == reference autograd (bit-exact); golden gradient checksums written")
+
+    # ---------------------------------------------------------------- training-step networks of the mirror
+    torch.manual_seed(7)
+    Dr = networks.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[])
+    torch.manual_seed(7)
+    Do = ours.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[])
+    sr, so = Dr.state_dict(), Do.state_dict()
+    assert list(sr.keys()) == list(so.keys()) and all(torch.equal(sr[k], so[k]) for k in sr), "netD init/keys differ"
+    xd = torch.randn(2, 39, 64, 128, generator=g)
+    for keep in (False, True):
+        fr, fo = Dr(xd, keep), Do(xd, keep)
+        assert all(torch.equal(a, b) for s_, t_ in zip(fr, fo) for a, b in zip(s_, t_)), "netD outputs differ"
+    gr, go = networks.GANLoss(use_lsgan=True), ours.GANLoss(use_lsgan=True)
+    for target_is_real in (True, False):
+        assert torch.equal(gr(Dr(xd), target_is_real), go(Do(xd), target_is_real)), "GANLoss differs"
+    print("training mirror: define_D / MultiscaleDiscriminator / GANLoss == reference (bit-exact)")
+
     # ---------------------------------------------------------------- quantisers
     q = (torch.randn(4099, generator=g) * 3).float()
     q[:10] = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, 1.4, 1.6, 0.0, -0.0, float("nan")])

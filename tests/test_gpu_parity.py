@@ -267,11 +267,17 @@ def test_generator_state_dict_round_trip_and_repack(cuda, tmp_path):
     assert torch.equal(ya, yb2)
 
 
-def test_training_mode_fails_loudly(cuda):
+def test_unsupported_training_inputs_fail_loudly(cuda):
+    import jpdse_b200
     nw = _networks()
     net = nw.define_G(39, 3, 64, "global", 1, 0, 1, 3, "instance", gpu_ids=[0])
-    with pytest.raises(NotImplementedError):
-        net(torch.zeros(1, 39, 128, 128, device=cuda))  # grad enabled: backward not available -> refuse, no fallback
+    with pytest.raises(NotImplementedError):  # the generator input takes no gradient on this path: refuse, no fallback
+        net(torch.zeros(1, 39, 128, 128, device=cuda, requires_grad=True))
+    wide = nw.define_G(39, 3, 128, "global", 1, 0, 1, 3, "instance", gpu_ids=[0])
+    with pytest.raises(jpdse_b200.JpdseError):  # backward kernels are built for ngf == 64
+        wide(torch.zeros(1, 39, 128, 128, device=cuda))
+    with torch.no_grad():
+        assert wide(torch.zeros(1, 39, 128, 128, device=cuda)).shape == (1, 3, 128, 128)
 
 
 def test_trainer_get_img_matches_oracle(cuda):

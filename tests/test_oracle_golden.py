@@ -60,6 +60,23 @@ def test_generator_golden(golden_dir):
     assert np.allclose(y.numpy(), g["y"], atol=1e-5, rtol=0)
 
 
+def test_generator_gradient_golden(golden_dir):
+    """Oracle autograd reproduces the reference's gradient checksums (sum, abs-sum per parameter) for L1 x 10."""
+    import importlib
+    g = _load(golden_dir, "generator_small.npz")
+    gg = _load(golden_dir, "generator_small_grads.npz")
+    nw = importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
+    torch.manual_seed(int(g["seed"]))
+    net = nw.define_G(39, 3, 64, "global", int(g["n_down"]), int(g["n_blocks"]), 1, 3, "instance", gpu_ids=[])
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    y = orc.generator_forward(sd, torch.from_numpy(g["x"]), int(g["n_down"]), int(g["n_blocks"]))
+    (10.0 * (y - torch.from_numpy(gg["target"])).abs().mean()).backward()
+    for name, (s1, s2) in zip(gg["names"], gg["sums"]):
+        grad = sd[str(name)].grad.double()
+        assert abs(float(grad.abs().sum()) - s2) <= 1e-4 * max(s2, 1e-6) + 1e-9, name
+        assert abs(float(grad.sum()) - s1) <= 1e-4 * max(s2, 1e-6) + 1e-9, name
+
+
 def test_generator_bf16_emulation_close_to_fp32(golden_dir):
     import importlib
     g = _load(golden_dir, "generator_small.npz")
