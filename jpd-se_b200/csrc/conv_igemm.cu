@@ -136,16 +136,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         mt /= p.tiles_w;
         const int th = mt % p.tiles_h;
         const int b = mt / p.tiles_h;
-        int base[5] = {0, 0, 0, 0, 0};
-        base[p.dim_w] += tw * p.tile_w;
-        base[p.dim_h] += th * p.tile_h;
-        base[p.dim_b] += b;
+        // Tile origin in tensor-map coordinates, straight-line (a dynamically indexed local array here costs the single
+        // producer thread hundreds of cycles of dependent local-memory traffic per tile -- fatal for the low-K convs).
+        // rank 3 (flat): {k, position, image}; rank 4: {c, w, h, b}; rank 5: {c, w, parity, h, b}
+        int b1 = tw * p.tile_w, b2, b3 = 0, b4 = 0;
+        if (p.a_rank == 3) {
+          b2 = b;
+        } else if (p.a_rank == 4) {
+          b2 = th * p.tile_h;
+          b3 = b;
+        } else {
+          b2 = 0;
+          b3 = th * p.tile_h;
+          b4 = b;
+        }
         int kb = 0;
         for (int t = 0; t < p.ntaps; ++t) {
-          const int c1 = base[1] + p.tap_off[t][1];
-          const int c2 = base[2] + p.tap_off[t][2];
-          const int c3 = base[3] + p.tap_off[t][3];
-          const int c4 = base[4] + p.tap_off[t][4];
+          const int c1 = b1 + p.tap_off[t][1];
+          const int c2 = b2 + p.tap_off[t][2];
+          const int c3 = b3 + p.tap_off[t][3];
+          const int c4 = b4 + p.tap_off[t][4];
+          const int c0t = p.tap_off[t][0];
           for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb) {
             const long long tw0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -153,7 +164,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kABytes;
             mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            const int c0 = base[0] + p.tap_off[t][0] + ch * kBlockK;
+            const int c0 = c0t + ch * kBlockK;
             if (p.a_rank == 3)
               tma_load_3d(&tm_a, &full_bar[stage], sa, c0, c1, c2);
             else if (p.a_rank == 4)

@@ -81,16 +81,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
-__device__ __forceinline__ void wg_load_box(const CUtensorMap* tm, const WgView& v, uint64_t* bar, void* dst, const int* off,
-                                            int c0_extra, int pw, int ph, int b) {
-  int c[5] = {off[0] + c0_extra, off[1], off[2], off[3], off[4]};
-  c[v.dim_w] += pw;
-  c[v.dim_h] += ph;
-  c[v.dim_b] += b;
-  if (v.rank == 4)
-    tma_load_4d(tm, bar, dst, c[0], c[1], c[2], c[3]);
+// Both views keep the pixel column in dim 1; rank 4 = {c, w, h, b}, rank 5 = {c, w, parity, h, b}. Coordinates are
+// built with straight-line code: the single producer thread must never touch local memory (a dynamically indexed
+// coordinate array costs ~300 cycles of dependent local loads per box and serialises the whole pipeline).
+__device__ __forceinline__ void wg_load_box(const CUtensorMap* tm, int rank, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3, int c4, int pw, int ph, int b) {
+  if (rank == 4)
+    tma_load_4d(tm, bar, dst, c0, c1 + pw, c2 + ph, c3 + b);
   else
-    tma_load_5d(tm, bar, dst, c[0], c[1], c[2], c[3], c[4]);
+    tma_load_5d(tm, bar, dst, c0, c1 + pw, c2, c3 + ph, c4 + b);
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -149,23 +148,48 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         const int g = rem / p.m_tiles;
         const int kb0 = static_cast<int>(static_cast<long long>(kb_total) * s / p.splits);
         const int kb1 = static_cast<int>(static_cast<long long>(kb_total) * (s + 1) / p.splits);
+        // per-item box coordinates in registers
+        int ao[2][5], bo[4][5];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) ao[j][q] = p.a_off[g][j][q];
+          ao[j][0] += mt * p.a_tile_stride;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int q = 0; q < 5; ++q) bo[j][q] = p.b_off[g][j][q];
+          bo[j][0] += nt * p.b_tile_stride;
+        }
+        const int per_img = p.nbh * p.nbw;
+        int b = kb0 / per_img;
+        int r2 = kb0 - b * per_img;
+        int rh = r2 / p.nbw;
+        int rw = r2 - rh * p.nbw;
         for (int kb = kb0; kb < kb1; ++kb) {
-          const int b = kb / (p.nbh * p.nbw);
-          const int r2 = kb - b * (p.nbh * p.nbw);
-          const int rh = r2 / p.nbw;
-          const int pw = (r2 - rh * p.nbw) * p.kw_cols;
+          const int pw = rw * p.kw_cols;
           const int ph = rh * p.kh_rows;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * kWgStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
-            wg_load_box(&tm_a, p.a, &full_bar[stage], st + j * kWgBox, p.a_off[g][j], mt * p.a_tile_stride, pw, ph, b);
-          for (int j = 0; j < p.nb; ++j)
-            wg_load_box(&tm_b, p.b, &full_bar[stage], st + (2 + j) * kWgBox, p.b_off[g][j], nt * p.b_tile_stride, pw, ph, b);
+            wg_load_box(&tm_a, p.a.rank, &full_bar[stage], st + j * kWgBox, ao[j][0], ao[j][1], ao[j][2], ao[j][3], ao[j][4], pw, ph, b);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < p.nb)
+              wg_load_box(&tm_b, p.b.rank, &full_bar[stage], st + (2 + j) * kWgBox, bo[j][0], bo[j][1], bo[j][2], bo[j][3], bo[j][4], pw, ph, b);
           if (++stage == kWgStages) {
             stage = 0;
             phase ^= 1;
+          }
+          if (++rw == p.nbw) {
+            rw = 0;
+            if (++rh == p.nbh) {
+              rh = 0;
+              ++b;
+            }
           }
         }
       }
