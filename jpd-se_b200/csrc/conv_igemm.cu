@@ -34,11 +34,15 @@ constexpr int kBlockK = 64;         // bf16 elements per k-block = one 128-byte 
 constexpr int kUmmaK = 16;          // K of one tcgen05.mma for 16-bit inputs
 constexpr int kABytes = kTileM * kBlockK * 2;
 constexpr int kMaxTaps = 9;
-constexpr int kThreads = 320;       // two epilogue warpgroups (one per TMEM accumulator) + 2 control warps
+constexpr int kThreads = 352;       // two epilogue warpgroups (one per TMEM accumulator) + 3 control warps
 // The control warps get the HIGHEST warp ids: the sub-partition arbiter favours high ids, and the single TMA /
 // MMA threads are the critical path of the low-K convs.
+// TWO producer threads (warps 8 and 9) fill alternate pipeline stages: one thread's wait -> expect_tx -> 2 x TMA issue
+// round costs ~500 cycles per k-block whatever the box size (measured with the MMA and the epilogue switched off),
+// which is slower than the MMAs of every N <= 128 conv and barely matches N = 256.
 constexpr int kProducerWarp = 8;
-constexpr int kMmaWarp = 9;
+constexpr int kNumProducers = 2;
+constexpr int kMmaWarp = 10;
 
 struct IgemmParams {
   // tile grid
@@ -57,6 +61,8 @@ struct IgemmParams {
   int ldc;      // channels of the output tensor
   int n_valid;  // valid output channels (<= n_tiles * BN)
   int epilogue;
+  int tma_store;   // 1: bf16 NHWC output leaves through shared memory + TMA store (tm_c), BN in {64, 128}
+  int c_rank;      // 4: {c, w, h, b}; 5: {2c (col parity major), w, row parity, h, b} (ConvTranspose phases)
   void* out;
   double* stats;
   const float* bias;
@@ -68,11 +74,14 @@ template <int BN>
 struct IgemmCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 6 : 8);
+  // BN <= 128 gives up pipeline stages for the epilogue's output staging (2 groups x 2 buffers x 16 KiB)
+  static constexpr bool kStaged = (BN == 64 || BN == 128);
+  static constexpr int kStageOutBytes = kStaged ? 4 * kABytes : 0;
+  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 4 : (BN >= 64 ? 6 : 8));
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kRedFloats = 8 * 32 * 17;  // per-epilogue-warp transpose scratch: 32 rows x 16 bf16x2 (+1 pad)
   // 1024 B alignment slack + stages + transpose scratch + barriers
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kRedFloats * 4 + 256;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kStageOutBytes + kRedFloats * 4 + 256;
 };
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -80,13 +89,14 @@ __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(_
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-             const __grid_constant__ IgemmParams p) {
+             const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ IgemmParams p) {
   using Cfg = IgemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment as an OFFSET from the shared window (keeps the pointer in the shared address space -> LDS/STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint32_t* s_red = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kRedFloats * 4);
+  uint8_t* s_out = smem + Cfg::kStages * Cfg::kStageBytes;  // output staging (1024 B aligned: all stage sizes are)
+  uint32_t* s_red = reinterpret_cast<uint32_t*>(s_out + Cfg::kStageOutBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + Cfg::kStageOutBytes + Cfg::kRedFloats * 4);
   uint64_t* full_bar = bars;                       // [kStages]  TMA -> MMA
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]        MMA -> epilogue
@@ -99,6 +109,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    if (p.tma_store) tma_prefetch_desc(&tm_c);
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
@@ -122,11 +133,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   const int m_tiles = p.batch * p.tiles_h * p.tiles_w;
   const int total_tiles = m_tiles * p.n_tiles;
 
-  if (warp == kProducerWarp) {
-    // ================================================================== TMA producer
+  if (warp >= kProducerWarp && warp < kProducerWarp + kNumProducers) {
+    // ================================================================== TMA producers (alternate k-blocks)
     if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
+      const uint32_t my = static_cast<uint32_t>(warp - kProducerWarp);
+      uint32_t it = 0;  // global k-block counter: stage = it % kStages, phase = (it / kStages) & 1
       long long dbg_prod = 0;
       const long long dbg_t0 = p.dbg ? clock64() : 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -136,7 +147,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         mt /= p.tiles_w;
         const int th = mt % p.tiles_h;
         const int b = mt / p.tiles_h;
-        // Tile origin in tensor-map coordinates, straight-line (a dynamically indexed local array here costs the single
+        // Tile origin in tensor-map coordinates, straight-line (a dynamically indexed local array here costs the
         // producer thread hundreds of cycles of dependent local-memory traffic per tile -- fatal for the low-K convs).
         // rank 3 (flat): {k, position, image}; rank 4: {c, w, h, b}; rank 5: {c, w, parity, h, b}
         int b1 = tw * p.tile_w, b2, b3 = 0, b4 = 0;
@@ -157,13 +168,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           const int c3 = b3 + p.tap_off[t][3];
           const int c4 = b4 + p.tap_off[t][4];
           const int c0t = p.tap_off[t][0];
-          for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb) {
+          for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb, ++it) {
+            if ((it % kNumProducers) != my) continue;
+            const uint32_t stage = it % Cfg::kStages;
+            const uint32_t phase = (it / Cfg::kStages) & 1u;
             const long long tw0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (p.dbg) dbg_prod += clock64() - tw0;
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], (p.dbg_flags & 32) ? kABytes : Cfg::kStageBytes);
             const int c0 = c0t + ch * kBlockK;
             if (p.a_rank == 3)
               tma_load_3d(&tm_a, &full_bar[stage], sa, c0, c1, c2);
@@ -171,17 +185,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
               tma_load_4d(&tm_a, &full_bar[stage], sa, c0, c1, c2, c3);
             else
               tma_load_5d(&tm_a, &full_bar[stage], sa, c0, c1, c2, c3, c4);
-            tma_load_2d(&tm_b, &full_bar[stage], sb, p.b_k_offset + kb * kBlockK, nt * BN);
-            if (++stage == Cfg::kStages) {
-              stage = 0;
-              phase ^= 1;
-            }
+            if (!(p.dbg_flags & 32)) tma_load_2d(&tm_b, &full_bar[stage], sb, p.b_k_offset + kb * kBlockK, nt * BN);
           }
         }
       }
-      if (p.dbg) {
-        p.dbg[blockIdx.x * 8 + 0] = dbg_prod;
-        p.dbg[blockIdx.x * 8 + 1] = clock64() - dbg_t0;
+      if (p.dbg && my == 0) {
+        p.dbg[blockIdx.x * 16 + 0] = dbg_prod;
+        p.dbg[blockIdx.x * 16 + 1] = clock64() - dbg_t0;
       }
     }
     __syncwarp();
@@ -209,13 +219,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_smem_desc_sw128(sa);
           const uint64_t bdesc = umma_smem_desc_sw128(sa + kABytes);
+          if (!(p.dbg_flags & 16)) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (>>4) address field
-            umma_bf16<1>(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
-                         (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              // advancing K inside the 128-byte swizzle row: +32 bytes = +2 in the (>>4) address field
+              umma_bf16<1>(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          if (p.dbg_flags & 64)
+            mbar_arrive(&empty_bar[stage]);  // experiment (only valid with the MMAs switched off)
+          else
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
           if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -226,9 +241,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         if (acc == 0) acc_phase ^= 1;
       }
       if (p.dbg) {
-        p.dbg[blockIdx.x * 8 + 2] = dbg_full;
-        p.dbg[blockIdx.x * 8 + 3] = dbg_tempty;
-        p.dbg[blockIdx.x * 8 + 4] = clock64() - dbg_t0;
+        p.dbg[blockIdx.x * 16 + 2] = dbg_full;
+        p.dbg[blockIdx.x * 16 + 3] = dbg_tempty;
+        p.dbg[blockIdx.x * 16 + 4] = clock64() - dbg_t0;
       }
     }
     __syncwarp();
@@ -260,8 +275,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         }
       }
     };
+    // column sums of a 32-row x 32-column bf16x2 chunk (pk: this lane's row) through a 32x16-word shared transpose
+    // (bank-conflict free): lane l then owns column pair (l & 15) over rows 16*(l >> 4) .. +15
+    auto chunk_stats = [&](uint32_t (&pk)[16], int ch) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) s_t[lane * 17 + j] = pk[j];
+      __syncwarp();
+      float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+      const uint32_t* col = s_t + (lane >> 4) * (16 * 17) + (lane & 15);
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const uint32_t w2 = col[t * 17];
+        const float lo = __uint_as_float(w2 << 16), hi = __uint_as_float(w2 & 0xffff0000u);
+        s1a += lo;
+        s1b += hi;
+        s2a = fmaf(lo, lo, s2a);
+        s2b = fmaf(hi, hi, s2b);
+      }
+      s1a += __shfl_xor_sync(0xffffffffu, s1a, 16);
+      s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
+      s2a += __shfl_xor_sync(0xffffffffu, s2a, 16);
+      s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
+      run_s1a[ch] += s1a;
+      run_s1b[ch] += s1b;
+      run_s2a[ch] += s2a;
+      run_s2b[ch] += s2b;
+    };
     int tile_i = 0;
-    long long dbg_epi = 0;
+    int out_buf = 0;  // running index of this group's output staging buffer
+    long long dbg_epi = 0, dbg_read = 0, dbg_tiles = 0;
     const long long dbg_t0 = p.dbg ? clock64() : 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_i) {
       if ((tile_i & 1) != group) continue;
@@ -284,12 +327,74 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       const int n0 = nt * BN;
 
       const long long tw2 = p.dbg ? clock64() : 0;
-      mbar_wait_parked(&tfull_bar[acc], acc_phase);
-      if (p.dbg) dbg_epi += clock64() - tw2;
+      if (p.dbg_flags & 4)
+        mbar_wait(&tfull_bar[acc], acc_phase);
+      else
+        mbar_wait_parked(&tfull_bar[acc], acc_phase);
+      const long long tr0 = p.dbg ? clock64() : 0;
+      if (p.dbg) dbg_epi += tr0 - tw2;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
-      if (p.epilogue == JPDSE_EPI_RAW_STATS || p.epilogue == JPDSE_EPI_RAW) {
+      if (p.dbg_flags & 8) {  // experiment: hand the accumulator straight back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      } else if (Cfg::kStaged && p.tma_store) {
+        // ---- bf16 NHWC tile -> swizzled shared-memory staging -> one TMA store per 64-channel half. Per-lane global
+        // stores (16 B at a pixel stride) cost the epilogue warps ~2-3k cycles per 32-column chunk and made every
+        // low-K conv epilogue-bound; here the warps only convert and write shared memory.
+        if constexpr (Cfg::kStaged) {
+          const bool want_stats = p.epilogue == JPDSE_EPI_RAW_STATS;
+          if (want_stats && (b != cur_b || n0 != cur_n0)) {
+            flush();
+            cur_b = b;
+            cur_n0 = n0;
+          }
+          const bool issuer = quarter == 0 && lane == 0;
+#pragma unroll
+          for (int half = 0; half < BN / 64; ++half) {
+            uint8_t* buf = s_out + (group * 2 + (out_buf & 1)) * kABytes;
+            if (issuer) tma_store_wait_read<1>();  // the store that last read this buffer (two halves ago) is done
+            named_bar_sync(1 + group, 128);
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+              const int ch = half * 2 + c2;
+              uint32_t v[32];
+              tmem_ld_32x32b_x32(taddr + ch * 32, v);
+              tmem_ld_wait();
+              uint32_t pk[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                pk[j] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              // row m of the staged box = 128 B; SWIZZLE_128B: 16-byte chunk index ^= (row & 7)
+              uint4* rowp = reinterpret_cast<uint4*>(buf + m * 128);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                rowp[(c2 * 4 + j) ^ (m & 7)] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              if (want_stats && !(p.dbg_flags & 1)) chunk_stats(pk, ch);
+            }
+            if (half == BN / 64 - 1) {  // accumulator fully read: hand it back before the store is even issued
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1 + group, 128);
+            if (issuer && !(p.dbg_flags & 2)) {
+              const int c0 = n0 + half * 64;
+              if (p.c_rank == 4)
+                tma_store_4d(&tm_c, buf, c0, tw * p.tile_w, th * p.tile_h, b);
+              else
+                tma_store_5d(&tm_c, buf, p.op_w * p.ldc + c0, tw * p.tile_w, p.op_h, th * p.tile_h, b);
+              tma_store_commit();
+            }
+            ++out_buf;
+          }
+        }
+      } else if (p.epilogue == JPDSE_EPI_RAW_STATS || p.epilogue == JPDSE_EPI_RAW) {
         const bool want_stats = p.epilogue == JPDSE_EPI_RAW_STATS;
         if (want_stats && (b != cur_b || n0 != cur_n0)) {
           flush();
@@ -320,31 +425,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
 #pragma unroll
               for (int j = 0; j < 16; ++j) pk[j] = 0u;
             }
-            // column sums of the bf16-rounded tile through a 32x16-word shared transpose (bank-conflict free):
-            // lane l then owns column pair (l & 15) over rows 16*(l >> 4) .. +15
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) s_t[lane * 17 + j] = pk[j];
-            __syncwarp();
-            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-            const uint32_t* col = s_t + (lane >> 4) * (16 * 17) + (lane & 15);
-#pragma unroll
-            for (int t = 0; t < 16; ++t) {
-              const uint32_t w2 = col[t * 17];
-              const float lo = __uint_as_float(w2 << 16), hi = __uint_as_float(w2 & 0xffff0000u);
-              s1a += lo;
-              s1b += hi;
-              s2a = fmaf(lo, lo, s2a);
-              s2b = fmaf(hi, hi, s2b);
-            }
-            s1a += __shfl_xor_sync(0xffffffffu, s1a, 16);
-            s1b += __shfl_xor_sync(0xffffffffu, s1b, 16);
-            s2a += __shfl_xor_sync(0xffffffffu, s2a, 16);
-            s2b += __shfl_xor_sync(0xffffffffu, s2b, 16);
-            run_s1a[ch] += s1a;
-            run_s1b[ch] += s1b;
-            run_s2a[ch] += s2a;
-            run_s2b[ch] += s2b;
+            chunk_stats(pk, ch);
           }
         }
         tc_fence_before();
@@ -385,11 +466,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       }
       acc_phase ^= 1;
+      if (p.dbg) {
+        dbg_read += clock64() - tr0;
+        ++dbg_tiles;
+      }
     }
     if (p.epilogue == JPDSE_EPI_RAW_STATS) flush();
+    if (p.tma_store && quarter == 0 && lane == 0) tma_store_wait_read<0>();  // staging must outlive its readers
     if (p.dbg && lane == 0 && (warp == 0 || warp == 4)) {
-      p.dbg[blockIdx.x * 8 + 5 + group] = dbg_epi;
-      if (group == 0) p.dbg[blockIdx.x * 8 + 7] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 16 + 5 + group] = dbg_epi;
+      if (group == 0) p.dbg[blockIdx.x * 16 + 7] = clock64() - dbg_t0;
+      p.dbg[blockIdx.x * 16 + 8 + group] = dbg_read;
+      p.dbg[blockIdx.x * 16 + 10 + group] = dbg_tiles;
     }
   }
 
@@ -567,7 +655,8 @@ static long long* g_dbg = nullptr;  // role counters of the LAST igemm launch wh
 static bool g_dbg_enabled = false;
 
 template <int BN>
-static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p, cudaStream_t stream) {
+static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const IgemmParams& p,
+                        cudaStream_t stream) {
   using Cfg = IgemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -578,18 +667,18 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Igem
   const int total = p.batch * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = num_sms();
   if (grid > total) grid = total;
-  igemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  igemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
   return check_launch("igemm_kernel");
 }
 
-static int launch_igemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& p,
-                           cudaStream_t stream) {
+static int launch_igemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                           const IgemmParams& p, cudaStream_t stream) {
   switch (bn) {
-    case 256: return launch_igemm<256>(ta, tb, p, stream);
-    case 128: return launch_igemm<128>(ta, tb, p, stream);
-    case 64: return launch_igemm<64>(ta, tb, p, stream);
-    case 32: return launch_igemm<32>(ta, tb, p, stream);
-    case 16: return launch_igemm<16>(ta, tb, p, stream);
+    case 256: return launch_igemm<256>(ta, tb, tc, p, stream);
+    case 128: return launch_igemm<128>(ta, tb, tc, p, stream);
+    case 64: return launch_igemm<64>(ta, tb, tc, p, stream);
+    case 32: return launch_igemm<32>(ta, tb, tc, p, stream);
+    case 16: return launch_igemm<16>(ta, tb, tc, p, stream);
   }
   return fail(JPDSE_ERR_INVALID, "no igemm instantiation for BN=%d", bn);
 }
@@ -686,12 +775,12 @@ using namespace jpdse;
 // epilogue0 wait-tmem-full, epilogue1 wait-tmem-full, epilogue total] x 148 CTAs.
 extern "C" int jpdse_debug_role_counters(int enable, long long* host_out, int max_values) {
   if (g_dbg == nullptr) {
-    if (cudaMalloc(&g_dbg, sizeof(long long) * 8 * 256) != cudaSuccess) return fail(JPDSE_ERR_CUDA, "debug buffer alloc failed");
-    cudaMemset(g_dbg, 0, sizeof(long long) * 8 * 256);
+    if (cudaMalloc(&g_dbg, sizeof(long long) * 16 * 256) != cudaSuccess) return fail(JPDSE_ERR_CUDA, "debug buffer alloc failed");
+    cudaMemset(g_dbg, 0, sizeof(long long) * 16 * 256);
   }
   if (host_out != nullptr && max_values > 0) {
     cudaDeviceSynchronize();
-    cudaMemcpy(host_out, g_dbg, sizeof(long long) * (max_values < 8 * 256 ? max_values : 8 * 256), cudaMemcpyDeviceToHost);
+    cudaMemcpy(host_out, g_dbg, sizeof(long long) * (max_values < 16 * 256 ? max_values : 16 * 256), cudaMemcpyDeviceToHost);
   }
   g_dbg_enabled = enable != 0;
   return JPDSE_OK;
@@ -777,6 +866,9 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     p.dbg_flags = flags;
   }
 
+  // bf16 NHWC outputs of the BN = 64 / 128 instantiations leave through shared memory + TMA store
+  const bool staged_out = (g.bn == 64 || g.bn == 128) && !flat && (d->cout % 64) == 0 &&
+                          (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW);
   const uint64_t C = static_cast<uint64_t>(d->cin);
   const uint64_t H = static_cast<uint64_t>(d->in_h), W = static_cast<uint64_t>(d->in_w), B = static_cast<uint64_t>(d->batch);
   // physical (stored) extent of x and the address of its logical pixel (0,0)
@@ -795,6 +887,18 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     if (rc != JPDSE_OK) return rc;
     p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
     p.os_h = p.os_w = 2;
+    CUtensorMap tc = ta;
+    if (staged_out) {
+      // output (B,2H,2W,Cout) as {2*Cout (column parity major), W, 2 (row parity), H, B}: a phase's tile is one box
+      const uint64_t Co = static_cast<uint64_t>(d->cout);
+      uint64_t cd[5] = {2 * Co, W, 2, H, B};
+      uint64_t cs[4] = {2 * Co * 2, 2 * W * Co * 2, 2 * 2 * W * Co * 2, 2 * H * 2 * W * Co * 2};
+      uint32_t cb[5] = {64, static_cast<uint32_t>(p.tile_w), 1, static_cast<uint32_t>(p.tile_h), 1};
+      rc = make_tmap_bf16(&tc, y, 5, cd, cs, cb);
+      if (rc != JPDSE_OK) return rc;
+      p.tma_store = 1;
+      p.c_rank = 5;
+    }
     size_t k_elems_before = 0;  // rows * K of the previous phase blocks
     for (int pidx = 0; pidx < 4; ++pidx) {
       const int ph = pidx >> 1, pw = pidx & 1;
@@ -815,7 +919,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       rc = make_tmap_bf16(&tb, static_cast<const uint8_t*>(w_packed) + k_elems_before * 2, 2, bd, bs, bb);
       if (rc != JPDSE_OK) return rc;
       p.b_k_offset = 0;
-      rc = launch_igemm_bn(g.bn, ta, tb, p, stream);
+      rc = launch_igemm_bn(g.bn, ta, tb, tc, p, stream);
       if (rc != JPDSE_OK) return rc;
       k_elems_before += static_cast<size_t>(g.rows) * kp;
     }
@@ -901,5 +1005,16 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
   rc = make_tmap_bf16(&tb, w_packed, 2, bd, bs, bb);
   if (rc != JPDSE_OK) return rc;
-  return launch_igemm_bn(g.bn, ta, tb, p, stream);
+  CUtensorMap tc = ta;
+  if (staged_out) {
+    const uint64_t Co = static_cast<uint64_t>(d->cout), OW = static_cast<uint64_t>(g.out_w), OH = static_cast<uint64_t>(g.out_h);
+    uint64_t cd[4] = {Co, OW, OH, B};
+    uint64_t cs[3] = {Co * 2, OW * Co * 2, OH * OW * Co * 2};
+    uint32_t cb[4] = {64, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
+    rc = make_tmap_bf16(&tc, y, 4, cd, cs, cb);
+    if (rc != JPDSE_OK) return rc;
+    p.tma_store = 1;
+    p.c_rank = 4;
+  }
+  return launch_igemm_bn(g.bn, ta, tb, tc, p, stream);
 }

@@ -24,6 +24,7 @@ CASES = [("convT 128->64 @256x512", CONVT3X3_S2, 256, 512, 0, 128, 64),
          ("convT 512->256 @64x128", CONVT3X3_S2, 64, 128, 0, 512, 256),
          ("conv s2 64->128 @512x1024", CONV3X3_S2, 512, 1024, 0, 64, 128),
          ("conv s2 128->256 @256x512", CONV3X3_S2, 256, 512, 0, 128, 256),
+         ("3x3 64->256 @128x256", CONV3X3_PAD1, 128, 256, 1, 64, 256),
          ("res 1024->1024 @32x64", CONV3X3_PAD1, 32, 64, 1, 1024, 1024)]
 for name, kind, H, W, pad, cin, cout in CASES:
     cv = ops.Conv(kind, EPI_RAW_STATS, B, H, W, pad, cin, cin, cout, dev)
@@ -44,11 +45,11 @@ for name, kind, H, W, pad, cin, cout in CASES:
     ms = e0.elapsed_time(e1)
     lib.jpdse_debug_role_counters(1, None, 0)
     cv.forward(x, y, st)  # for ConvT the counters are those of the LAST phase launch (4 taps)
-    buf = (ctypes.c_longlong * (8 * 148))()
-    lib.jpdse_debug_role_counters(0, buf, 8 * 148)
-    v = torch.tensor(list(buf), dtype=torch.float64).view(148, 8)
+    buf = (ctypes.c_longlong * (16 * 148))()
+    lib.jpdse_debug_role_counters(0, buf, 16 * 148)
+    v = torch.tensor(list(buf), dtype=torch.float64).view(148, 16)
     m = v.mean(dim=0)
     print("%-28s %.3f ms | producer: wait-empty %4.0f%% of %8.0f cyc | mma: wait-full %4.0f%% wait-tmem %4.0f%% of %8.0f | "
-          "epilogue: wait-tile g0 %4.0f%% g1 %4.0f%% of %8.0f" % (
+          "epilogue: wait-tile g0 %4.0f%% g1 %4.0f%% of %8.0f | drain %6.0f cyc/tile over %4.0f tiles/group" % (
               name, ms, 100 * m[0] / max(m[1], 1), m[1], 100 * m[2] / max(m[4], 1), 100 * m[3] / max(m[4], 1), m[4],
-              100 * m[5] / max(m[7], 1), 100 * m[6] / max(m[7], 1), m[7]))
+              100 * m[5] / max(m[7], 1), 100 * m[6] / max(m[7], 1), m[7], m[8] / max(m[10], 1), m[10]))
