@@ -606,6 +606,7 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
       g->gemm_w = d->in_w;
       g->cpt = d->cin / 64;
       g->ktot = 9 * d->cin;
+      if (convt_fused_applicable(d)) g->path = kPathConvtFused;
       break;
     case JPDSE_CONV7X7_PAD3:
       if ((d->cin * 2) % 16) return fail(JPDSE_ERR_UNSUPPORTED, "conv7x7: cin*2 bytes must be a multiple of 16");
@@ -805,6 +806,7 @@ extern "C" int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w,
   int rc = conv_geom(d, &g);
   if (rc != JPDSE_OK) return rc;
   if (w == nullptr || w_packed == nullptr) return fail(JPDSE_ERR_INVALID, "pack_weights: NULL pointer");
+  if (g.path == kPathConvtFused) return convt_fused_pack(d, w, w_packed, static_cast<cudaStream_t>(stream));
   PackParams q{d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt, g.path};
   const size_t total = static_cast<size_t>(g.rows) * g.ktot;
   int blocks = static_cast<int>((total + 255) / 256);
@@ -825,6 +827,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       (reinterpret_cast<uintptr_t>(y) & 15))
     return fail(JPDSE_ERR_INVALID, "conv_forward: pointers must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (g.path == kPathConvtFused) return convt_fused_forward(d, x, w_packed, y, stats, stream);
   if (g.path != kPathIgemm) return rowconv_forward(d, g.path == kPathRowHead, x, w_packed, bias, y, stats, stream);
 
   IgemmParams p;

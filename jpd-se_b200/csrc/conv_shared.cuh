@@ -13,7 +13,8 @@ namespace jpdse {
 enum ConvPath {
   kPathIgemm = 0,    // generic per-tap implicit GEMM (conv_igemm.cu)
   kPathRowHead = 1,  // row-stationary 7x7, (kw,cout) polyphase columns, bias+tanh (conv_rowstat.cu)
-  kPathRowStem = 2   // row-stationary 7x7, window-K, 32-channel splits, raw+stats (conv_rowstat.cu)
+  kPathRowStem = 2,  // row-stationary 7x7, window-K, 32-channel splits, raw+stats (conv_rowstat.cu)
+  kPathConvtFused = 3  // ConvTranspose with all four output phases per tile and halo-shared A boxes (conv_convt.cu)
 };
 
 struct ConvGeom {
@@ -31,6 +32,11 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g);
 // bf16 tensor map, 128-byte swizzle, zero OOB fill. dims/box innermost first; strides (bytes) for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                    const uint32_t* box);
+
+bool convt_fused_applicable(const jpdse_conv_desc* d);
+int convt_fused_pack(const jpdse_conv_desc* d, const float* w, void* w_packed, cudaStream_t stream);
+int convt_fused_forward(const jpdse_conv_desc* d, const void* x, const void* w_packed, void* y, double* stats,
+                        cudaStream_t stream);
 
 int rowconv_forward(const jpdse_conv_desc* d, bool head, const void* x, const void* w_packed, const float* bias, void* y,
                     double* stats, cudaStream_t stream);

@@ -103,6 +103,7 @@ def test_conv_wgrad(cuda, case):
 # ------------------------------------------------------------------------------------------------ data gradients
 @pytest.mark.parametrize("case", [("conv3x3", 2, 8, 16, 64, 64), ("conv3x3", 1, 32, 64, 256, 128), ("conv3x3", 2, 12, 20, 128, 128),
                                   ("convs2", 2, 16, 32, 64, 128), ("convs2", 1, 32, 64, 256, 512),
+                                  ("convs2", 1, 6, 256, 64, 128), ("convs2", 2, 10, 512, 128, 256),  # dgrad through the fused-phase ConvT kernel
                                   ("convt", 2, 8, 16, 128, 64), ("convt", 1, 16, 32, 512, 256),
                                   ("head", 2, 8, 16, 64, 3), ("head", 1, 40, 72, 64, 3)])
 def test_conv_dgrad(cuda, case):

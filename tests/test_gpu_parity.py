@@ -140,6 +140,7 @@ def _conv_case(ops, cuda, kind_name, B, H, W, cin, cout, cin_real=None, seed=0):
     ("conv3x3", 2, 8, 16, 64, 64), ("conv3x3", 2, 16, 16, 128, 256), ("conv3x3", 1, 32, 64, 1024, 1024),
     ("convs2", 2, 16, 32, 64, 128), ("convs2", 1, 32, 64, 128, 256),
     ("convt", 2, 8, 16, 128, 64), ("convt", 1, 16, 32, 256, 128),
+    ("convt", 2, 5, 128, 128, 64), ("convt", 1, 9, 256, 256, 128), ("convt", 2, 3, 128, 64, 64),  # fused-phase kernel (W % 128 == 0, Cout <= 128)
     ("conv7x7", 2, 8, 16, 40, 64, 39), ("conv7x7", 1, 16, 128, 40, 64, 39),
     ("conv7x7", 2, 140, 256, 40, 64, 39),  # row-stationary stem path: 2 strips, a full and a ragged row chunk
 ])
