@@ -79,7 +79,7 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  const int pix0 = blockIdx.x * (ppi * kBwdIters);
+  for (int pix0 = blockIdx.x * (ppi * kBwdIters); pix0 < npix; pix0 += gridDim.x * (ppi * kBwdIters))
   for (int it = 0; it < kBwdIters; ++it) {
     const int pp = pix0 + it * ppi + psub;
     if (pp >= npix) break;
@@ -173,7 +173,7 @@ instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
   const uint4* dy4 = reinterpret_cast<const uint4*>(dy) + static_cast<size_t>(b) * H * W * vpp;
   const uint4* raw4 = reinterpret_cast<const uint4*>(raw) + static_cast<size_t>(b) * H * W * vpp;
   uint4* dx4 = reinterpret_cast<uint4*>(dx) + static_cast<size_t>(b) * npix * vpp;
-  const int pix0 = blockIdx.x * (ppi * kBwdIters);
+  for (int pix0 = blockIdx.x * (ppi * kBwdIters); pix0 < npix; pix0 += gridDim.x * (ppi * kBwdIters))
 #pragma unroll 4
   for (int it = 0; it < kBwdIters; ++it) {
     const int pp = pix0 + it * ppi + psub;
@@ -272,7 +272,15 @@ extern "C" int jpdse_instnorm_backward_reduce(const void* g, int g_pad, const vo
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int vpp = channels / 8, ppi = kBwdThreads / vpp;
   const int per_block = ppi * kBwdIters;
-  dim3 grid((height * width + per_block - 1) / per_block, batch);
+  int gx = (height * width + per_block - 1) / per_block;
+  static int per_sm_r = 0;
+  if (per_sm_r == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_r, instnorm_backward_reduce_kernel<true, true>, kBwdThreads, 0);
+    if (per_sm_r < 1) per_sm_r = 1;
+  }
+  const int wave = (num_sms() * per_sm_r) / batch > 0 ? (num_sms() * per_sm_r) / batch : 1;
+  if (batch >= 8 && channels >= 128 && gx > wave) gx = wave;  // the single-wave grid only pays at inference-size batches
+  dim3 grid(gx, batch);
   const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(g);
   const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(skip);
   const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(raw);
@@ -302,7 +310,15 @@ extern "C" int jpdse_instnorm_backward_apply(const void* dy, const void* raw, co
   const int vpp = channels / 8, ppi = kBwdThreads / vpp;
   const int per_block = ppi * kBwdIters;
   const int npix = (height + 2 * dx_pad) * (width + 2 * dx_pad);
-  dim3 grid((npix + per_block - 1) / per_block, batch);
+  int gx = (npix + per_block - 1) / per_block;
+  static int per_sm_a = 0;
+  if (per_sm_a == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, instnorm_backward_apply_kernel, kBwdThreads, 0);
+    if (per_sm_a < 1) per_sm_a = 1;
+  }
+  const int wave = (num_sms() * per_sm_a) / batch > 0 ? (num_sms() * per_sm_a) / batch : 1;
+  if (batch >= 8 && channels >= 128 && gx > wave) gx = wave;
+  dim3 grid(gx, batch);
   instnorm_backward_apply_kernel<<<grid, kBwdThreads, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(raw), stats, sums, static_cast<__nv_bfloat16*>(dx),
       dx_pad, height, width, channels, eps);

@@ -337,7 +337,8 @@ class Vgg19(nn.Module):
         if os.path.isfile(cached) or os.environ.get('JPDSE_ALLOW_DOWNLOAD'):
             feats = models.vgg19(weights=wts).features
         else:
-            print('jpdse_b200: pretrained VGG19 not in %s; using random weights' % os.path.dirname(cached))
+            import sys
+            print('jpdse_b200: pretrained VGG19 not in %s; using random weights' % os.path.dirname(cached), file=sys.stderr)
             feats = models.vgg19(weights=None).features
         lo = 0
         for k, hi in enumerate(self.CUTS):
