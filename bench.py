@@ -275,6 +275,7 @@ def main():
     label, inst, image = synth_inputs(B, H, W, seed=1234 + rank)
     d_label, d_inst, d_image = label.to(dev), inst.to(dev), image.to(dev)
     plan = netG.plan_for(B, H, W, dev)
+    plan.use_graph = False  # the device-resident loop times the res-block convs with events around their launches
 
     def barrier():
         if world > 1:
@@ -330,6 +331,7 @@ def main():
     ms_per_step = elapsed_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
+    plan.use_graph = True   # the e2e path below is the user-facing call: CUDA-graph replay of the same launches
     # ---------------------------------------------------------------- end to end through the ctu API
     # Every step: H2D of that step's pinned host inputs, trainer.get_img(x_dict) (the call test.py makes), D2H of the
     # output image. Copies run on their own streams with double-buffered device inputs, so step i+1's upload and

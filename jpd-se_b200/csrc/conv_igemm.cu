@@ -70,14 +70,16 @@ struct IgemmParams {
   int dbg_flags;   // developer experiments: bit0 skip statistics, bit1 skip output stores
 };
 
-template <int BN>
+// STG = 1: bf16 NHWC output through shared-memory staging + TMA store (always for BN = 64 / 128; for BN = 256 it
+// costs one pipeline stage, so only the low-K layers -- whose epilogue is exposed -- use it)
+template <int BN, int STG>
 struct IgemmCfg {
   static constexpr int kBBytes = BN * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // BN <= 128 gives up pipeline stages for the epilogue's output staging (2 groups x 2 buffers x 16 KiB)
-  static constexpr bool kStaged = (BN == 64 || BN == 128);
+  static constexpr bool kStaged = (BN == 64 || BN == 128 || (BN == 256 && STG == 1));
   static constexpr int kStageOutBytes = kStaged ? 4 * kABytes : 0;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 128 ? 4 : (BN >= 64 ? 6 : 8));
+  static constexpr int kStages = (BN >= 256) ? (kStaged ? 3 : 4) : (BN >= 128 ? 4 : (BN >= 64 ? 6 : 8));
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int kRedFloats = 8 * 32 * 17;  // per-epilogue-warp transpose scratch: 32 rows x 16 bf16x2 (+1 pad)
   // 1024 B alignment slack + stages + transpose scratch + barriers
@@ -86,11 +88,11 @@ struct IgemmCfg {
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-template <int BN>
+template <int BN, int STG>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
              const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ IgemmParams p) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, STG>;
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment as an OFFSET from the shared window (keeps the pointer in the shared address space -> LDS/STS)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -629,6 +631,12 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
     default:
       return fail(JPDSE_ERR_INVALID, "conv desc: unknown kind %d", d->kind);
   }
+  // Small problems (batch 1-2 at the bottleneck): with N = 256 tiles fewer than ~3/4 of the SMs get a tile; halve N so
+  // the tile count doubles (an N = 128 MMA costs about half an N = 256 one, so a lone tile also finishes sooner)
+  if (g->bn == 256 && g->path == kPathIgemm) {
+    const long long m_tiles = (static_cast<long long>(d->batch) * g->gemm_h * g->gemm_w + 127) / 128;
+    if (m_tiles * (g->rows / 256) * 4 < static_cast<long long>(num_sms()) * 3) g->bn = 128;
+  }
   if (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW) {
     if (d->cout % g->bn || g->bn < 32)
       return fail(JPDSE_ERR_UNSUPPORTED, "raw+stats epilogue needs cout %% %d == 0 (got %d)", g->bn, d->cout);
@@ -655,31 +663,31 @@ static int pick_tile(int gh, int gw, int* th, int* tw) {
 static long long* g_dbg = nullptr;  // role counters of the LAST igemm launch when enabled (tools/role_times.py)
 static bool g_dbg_enabled = false;
 
-template <int BN>
+template <int BN, int STG>
 static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const IgemmParams& p,
                         cudaStream_t stream) {
-  using Cfg = IgemmCfg<BN>;
+  using Cfg = IgemmCfg<BN, STG>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
     configured = true;
   }
   const int total = p.batch * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = num_sms();
   if (grid > total) grid = total;
-  igemm_kernel<BN><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
+  igemm_kernel<BN, STG><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, tc, p);
   return check_launch("igemm_kernel");
 }
 
 static int launch_igemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                            const IgemmParams& p, cudaStream_t stream) {
   switch (bn) {
-    case 256: return launch_igemm<256>(ta, tb, tc, p, stream);
-    case 128: return launch_igemm<128>(ta, tb, tc, p, stream);
-    case 64: return launch_igemm<64>(ta, tb, tc, p, stream);
-    case 32: return launch_igemm<32>(ta, tb, tc, p, stream);
-    case 16: return launch_igemm<16>(ta, tb, tc, p, stream);
+    case 256: return p.tma_store ? launch_igemm<256, 1>(ta, tb, tc, p, stream) : launch_igemm<256, 0>(ta, tb, tc, p, stream);
+    case 128: return launch_igemm<128, 1>(ta, tb, tc, p, stream);
+    case 64: return launch_igemm<64, 1>(ta, tb, tc, p, stream);
+    case 32: return launch_igemm<32, 0>(ta, tb, tc, p, stream);
+    case 16: return launch_igemm<16, 0>(ta, tb, tc, p, stream);
   }
   return fail(JPDSE_ERR_INVALID, "no igemm instantiation for BN=%d", bn);
 }
@@ -870,7 +878,10 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   }
 
   // bf16 NHWC outputs of the BN = 64 / 128 instantiations leave through shared memory + TMA store
-  const bool staged_out = (g.bn == 64 || g.bn == 128) && !flat && (d->cout % 64) == 0 &&
+  // (BN = 256 gives up a pipeline stage for the staging, so only where the epilogue is exposed: <= 48 k-blocks a tile)
+  const int kblocks_per_tile = (d->kind == JPDSE_CONV1X1 ? 1 : 9) * g.cpt;
+  const bool staged_out = (g.bn == 64 || g.bn == 128 || (g.bn == 256 && kblocks_per_tile <= 48)) && !flat &&
+                          (d->cout % 64) == 0 && d->kind != JPDSE_CONV7X7_PAD3 &&
                           (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW);
   const uint64_t C = static_cast<uint64_t>(d->cin);
   const uint64_t H = static_cast<uint64_t>(d->in_h), W = static_cast<uint64_t>(d->in_w), B = static_cast<uint64_t>(d->batch);

@@ -29,6 +29,7 @@ def main():
     B, H, W = args.batch, args.height, args.width
     label, inst, image = [t.to(dev) for t in bench.synth_inputs(B, H, W)]
     plan = net.plan_for(B, H, W, dev)
+    plan.use_graph = False
     names = {id(cv): k for k, cv in plan.convs.items()}
     records = []
 
