@@ -18,7 +18,7 @@
 namespace jpdse {
 
 constexpr int kBwdThreads = 256;
-constexpr int kBwdIters = 32;
+constexpr int kBwdItersMax = 32;  // pixel groups per CTA pass; the host lowers it for small tensors so the grid fills the SMs
 
 __device__ __forceinline__ uint32_t bwd_pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
@@ -61,7 +61,7 @@ template <bool kRelu, bool kSkip>
 __global__ void __launch_bounds__(kBwdThreads)
 instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, const __nv_bfloat16* __restrict__ skip,
                                 const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
-                                __nv_bfloat16* __restrict__ dy, double* __restrict__ sums, int H, int W, int C, float eps) {
+                                __nv_bfloat16* __restrict__ dy, double* __restrict__ sums, int H, int W, int C, float eps, int iters) {
   __shared__ float s_red[kBwdThreads][17];
   const int vpp = C >> 3;
   const int ppi = kBwdThreads / vpp;
@@ -79,8 +79,8 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  for (int pix0 = blockIdx.x * (ppi * kBwdIters); pix0 < npix; pix0 += gridDim.x * (ppi * kBwdIters))
-  for (int it = 0; it < kBwdIters; ++it) {
+  for (int pix0 = blockIdx.x * (ppi * iters); pix0 < npix; pix0 += gridDim.x * (ppi * iters))
+  for (int it = 0; it < iters; ++it) {
     const int pp = pix0 + it * ppi + psub;
     if (pp >= npix) break;
     const int h = pp / W, w = pp - h * W;
@@ -151,7 +151,7 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
 __global__ void __launch_bounds__(kBwdThreads)
 instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ raw,
                                const double* __restrict__ stats, const double* __restrict__ sums,
-                               __nv_bfloat16* __restrict__ dx, int zpad, int H, int W, int C, float eps) {
+                               __nv_bfloat16* __restrict__ dx, int zpad, int H, int W, int C, float eps, int iters) {
   const int vpp = C >> 3;
   const int ppi = kBwdThreads / vpp;
   const int vec = threadIdx.x % vpp;
@@ -173,9 +173,9 @@ instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
   const uint4* dy4 = reinterpret_cast<const uint4*>(dy) + static_cast<size_t>(b) * H * W * vpp;
   const uint4* raw4 = reinterpret_cast<const uint4*>(raw) + static_cast<size_t>(b) * H * W * vpp;
   uint4* dx4 = reinterpret_cast<uint4*>(dx) + static_cast<size_t>(b) * npix * vpp;
-  for (int pix0 = blockIdx.x * (ppi * kBwdIters); pix0 < npix; pix0 += gridDim.x * (ppi * kBwdIters))
+  for (int pix0 = blockIdx.x * (ppi * iters); pix0 < npix; pix0 += gridDim.x * (ppi * iters))
 #pragma unroll 4
-  for (int it = 0; it < kBwdIters; ++it) {
+  for (int it = 0; it < iters; ++it) {
     const int pp = pix0 + it * ppi + psub;
     if (pp >= npix) break;
     const int ph = pp / Wz, pw = pp - ph * Wz;
@@ -247,6 +247,13 @@ tanh_backward_nchw_kernel(const float* __restrict__ gout, const float* __restric
   }
 }
 
+// pixel groups per CTA: as many as kBwdItersMax, fewer while the grid would leave SMs idle
+static int pick_iters(int npix, int ppi, int batch) {
+  int iters = kBwdItersMax;
+  while (iters > 2 && static_cast<long long>((npix + ppi * iters - 1) / (ppi * iters)) * batch < 1LL * num_sms()) iters >>= 1;
+  return iters;
+}
+
 static int check_channels(int channels, const char* what) {
   if (channels % 8 || channels > 8 * kBwdThreads || (kBwdThreads % (channels / 8)))
     return fail(JPDSE_ERR_UNSUPPORTED, "%s: channels must be 8*2^k <= %d (got %d)", what, 8 * kBwdThreads, channels);
@@ -271,7 +278,8 @@ extern "C" int jpdse_instnorm_backward_reduce(const void* g, int g_pad, const vo
     return fail(JPDSE_ERR_INVALID, "instnorm_backward_reduce: pointers must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int vpp = channels / 8, ppi = kBwdThreads / vpp;
-  const int per_block = ppi * kBwdIters;
+  const int iters = pick_iters(height * width, ppi, batch);
+  const int per_block = ppi * iters;
   int gx = (height * width + per_block - 1) / per_block;
   static int per_sm_r = 0;
   if (per_sm_r == 0) {
@@ -286,13 +294,13 @@ extern "C" int jpdse_instnorm_backward_reduce(const void* g, int g_pad, const vo
   const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(raw);
   __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dy);
   if (relu && skip)
-    instnorm_backward_reduce_kernel<true, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps);
+    instnorm_backward_reduce_kernel<true, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters);
   else if (relu)
-    instnorm_backward_reduce_kernel<true, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps);
+    instnorm_backward_reduce_kernel<true, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters);
   else if (skip)
-    instnorm_backward_reduce_kernel<false, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps);
+    instnorm_backward_reduce_kernel<false, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters);
   else
-    instnorm_backward_reduce_kernel<false, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps);
+    instnorm_backward_reduce_kernel<false, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters);
   return check_launch("instnorm_backward_reduce_kernel");
 }
 
@@ -308,8 +316,9 @@ extern "C" int jpdse_instnorm_backward_apply(const void* dy, const void* raw, co
     return fail(JPDSE_ERR_INVALID, "instnorm_backward_apply: pointers must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int vpp = channels / 8, ppi = kBwdThreads / vpp;
-  const int per_block = ppi * kBwdIters;
   const int npix = (height + 2 * dx_pad) * (width + 2 * dx_pad);
+  const int iters = pick_iters(npix, ppi, batch);
+  const int per_block = ppi * iters;
   int gx = (npix + per_block - 1) / per_block;
   static int per_sm_a = 0;
   if (per_sm_a == 0) {
@@ -321,7 +330,7 @@ extern "C" int jpdse_instnorm_backward_apply(const void* dy, const void* raw, co
   dim3 grid(gx, batch);
   instnorm_backward_apply_kernel<<<grid, kBwdThreads, 0, stream>>>(
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(raw), stats, sums, static_cast<__nv_bfloat16*>(dx),
-      dx_pad, height, width, channels, eps);
+      dx_pad, height, width, channels, eps, iters);
   return check_launch("instnorm_backward_apply_kernel");
 }
 

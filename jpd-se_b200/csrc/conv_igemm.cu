@@ -631,9 +631,11 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
     default:
       return fail(JPDSE_ERR_INVALID, "conv desc: unknown kind %d", d->kind);
   }
-  // Small problems (batch 1-2 at the bottleneck): with N = 256 tiles fewer than ~3/4 of the SMs get a tile; halve N so
-  // the tile count doubles (an N = 128 MMA costs about half an N = 256 one, so a lone tile also finishes sooner)
-  if (g->bn == 256 && g->path == kPathIgemm) {
+  // Small problems (batch 1 at the bottleneck): with N = 256 tiles fewer than ~3/4 of the SMs get a tile; halve N so
+  // the tile count doubles (an N = 128 MMA costs about half an N = 256 one, so a lone tile also finishes sooner).
+  // (A wave-quantisation-aware choice for the flat data-gradient kinds was tried and lost: N = 128 doubles the unique
+  // A traffic and falls back to per-lane stores there.)
+  if (g->bn == 256 && g->path == kPathIgemm && d->kind != JPDSE_CONV3X3_FULL) {
     const long long m_tiles = (static_cast<long long>(d->batch) * g->gemm_h * g->gemm_w + 127) / 128;
     if (m_tiles * (g->rows / 256) * 4 < static_cast<long long>(num_sms()) * 3) g->bn = 128;
   }

@@ -63,6 +63,7 @@ struct WgParams {
   short a_tap[kWgMaxGroups][2], b_tap[kWgMaxGroups][4];  // output tap contribution, < 0 = box unused
   short a_ch[kWgMaxGroups][2], b_ch[kWgMaxGroups][4];    // workspace row / column offset of the box
   int m_tot, n_tot;      // workspace extents: ws[tap][m_tot][n_tot]
+  int direct;            // 1: no split-K -> every workspace element has exactly one writer: plain stores, no memset
   float* ws;
 };
 
@@ -268,9 +269,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           float* dst = p.ws + (static_cast<size_t>(a_tap + b_tap) * p.m_tot + m) * p.n_tot + n0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
-            if (n0 + j < p.n_tot)  // n_tot is a multiple of 4
-              red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                         __uint_as_float(v[j + 3]));
+            if (n0 + j < p.n_tot) {  // n_tot is a multiple of 4
+              if (p.direct)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              else
+                red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                           __uint_as_float(v[j + 3]));
+            }
         }
       }
       tc_fence_before();
@@ -297,25 +303,34 @@ struct WgFinalize {
 };
 
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, WgFinalize f) {
-  const size_t total = static_cast<size_t>(f.m_real) * f.n_real * (f.mode == 0 ? f.taps : 49);
+  if (f.mode == 0) {
+    // one thread per (m, n): coalesced reads along n in every tap plane, `taps` consecutive floats written
+    const size_t mn_total = static_cast<size_t>(f.m_real) * f.n_real;
+    const size_t plane = static_cast<size_t>(f.m_tot) * f.n_tot;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < mn_total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+      const int n = static_cast<int>(i % f.n_real), m = static_cast<int>(i / f.n_real);
+      const float* src = ws + static_cast<size_t>(m) * f.n_tot + n;
+      float* dst = dw + i * f.taps;
+      for (int t = 0; t < f.taps; ++t) {
+        const float v = src[t * plane];
+        dst[t] = f.accumulate ? dst[t] + v : v;
+      }
+    }
+    return;
+  }
+  const size_t total = static_cast<size_t>(f.m_real) * f.n_real * 49;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // dw index i = ((co * cin + ci) * 7 + kh) * 7 + kw ; m_real = cout, n_real = cin
+    const int kw = static_cast<int>(i % 7), kh = static_cast<int>((i / 7) % 7);
+    const size_t cc = i / 49;
+    const int ci = static_cast<int>(cc % f.n_real), co = static_cast<int>(cc / f.n_real);
     float v;
-    if (f.mode == 0) {
-      const int tap = static_cast<int>(i % f.taps);
-      const size_t mn = i / f.taps;
-      const int n = static_cast<int>(mn % f.n_real), m = static_cast<int>(mn / f.n_real);
-      v = ws[(static_cast<size_t>(tap) * f.m_tot + m) * f.n_tot + n];
-    } else {
-      // dw index i = ((co * cin + ci) * 7 + kh) * 7 + kw ; m_real = cout, n_real = cin
-      const int kw = static_cast<int>(i % 7), kh = static_cast<int>((i / 7) % 7);
-      const size_t cc = i / 49;
-      const int ci = static_cast<int>(cc % f.n_real), co = static_cast<int>(cc / f.n_real);
-      if (f.mode == 1)
-        v = ws[(static_cast<size_t>(kh) * f.m_tot + co) * f.n_tot + kw * f.cin_st + ci];
-      else
-        v = ws[(static_cast<size_t>(kh) * f.m_tot + ci) * f.n_tot + (6 - kw) * 8 + co];
-    }
+    if (f.mode == 1)
+      v = ws[(static_cast<size_t>(kh) * f.m_tot + co) * f.n_tot + kw * f.cin_st + ci];
+    else
+      v = ws[(static_cast<size_t>(kh) * f.m_tot + ci) * f.n_tot + (6 - kw) * 8 + co];
     dw[i] = f.accumulate ? dw[i] + v : v;
   }
 }
@@ -556,6 +571,10 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
     if (splits < 1) splits = 1;
   }
   p.splits = splits;
+  // with one split every (tap, m, n) of the workspace that finalize reads is written by exactly one item -- true for
+  // the generic forms; the 7x7 window forms keep the reduction path (their unused boxes leave holes finalize skips,
+  // but rows of two filter taps share an item only through distinct workspace planes, so they qualify too)
+  p.direct = splits == 1 ? 1 : 0;
   w->ws_bytes = static_cast<size_t>(f.taps) * p.m_tot * p.n_tot * sizeof(float);
   return JPDSE_OK;
 }
@@ -587,8 +606,11 @@ extern "C" int jpdse_conv_wgrad(const jpdse_conv_desc* d, const void* x, const v
   if (rc != JPDSE_OK) return rc;
   rc = make_tmap_bf16(&tb, b_ptr, w.p.b.rank, w.b_dims, w.b_strides, w.b_box);
   if (rc != JPDSE_OK) return rc;
-  cudaError_t e = cudaMemsetAsync(workspace, 0, w.ws_bytes, stream);
-  if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "conv_wgrad: memset failed: %s", cudaGetErrorString(e));
+  cudaError_t e = cudaSuccess;
+  if (!w.p.direct) {
+    e = cudaMemsetAsync(workspace, 0, w.ws_bytes, stream);
+    if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "conv_wgrad: memset failed: %s", cudaGetErrorString(e));
+  }
   w.p.ws = static_cast<float*>(workspace);
   static bool configured = false;
   if (!configured) {
@@ -603,7 +625,7 @@ extern "C" int jpdse_conv_wgrad(const jpdse_conv_desc* d, const void* x, const v
   rc = check_launch("wgrad_kernel");
   if (rc != JPDSE_OK) return rc;
   w.f.accumulate = accumulate ? 1 : 0;
-  const size_t total = static_cast<size_t>(w.f.m_real) * w.f.n_real * (w.f.mode == 0 ? w.f.taps : 49);
+  const size_t total = static_cast<size_t>(w.f.m_real) * w.f.n_real * (w.f.mode == 0 ? 1 : 49);
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
   wgrad_finalize_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), dw, w.f);

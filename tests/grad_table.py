@@ -1,5 +1,5 @@
 """Per-parameter gradient agreement table: sm_100a backward vs CPU oracle autograd (fp32 and bf16-emulated forward).
-Usage: python tools/grad_table.py n_down n_blocks B H W"""
+Usage: python tests/grad_table.py n_down n_blocks B H W"""
 import importlib
 import os
 import sys
