@@ -200,6 +200,20 @@ int jpdse_s2hvq_encode(const float* x, const float* code_book, size_t rows, int 
 int jpdse_s2hvq_decode(const float* code_raw, const float* code_book, size_t rows, int center_size,
                        int n_center, float* out, int64_t* index, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Eval-metric path (validation / test loops: train.py:63-76, test.py:115-125).
+ * tensor2im (ctu/utils/misc.py:64-95): out = uint8(clip((x*std + mean)*255, 0, 255)) in float64, C truncation;
+ *   x float32 NCHW (B, channels<=3, H, W); out uint8 (B, H, W, channels) (tensor2im returns HWC images);
+ *   mean / std: HOST arrays of `channels` doubles (opt.normalize_mean / opt.normalize_std).
+ * distortion: *sum += sum over all elements of |ua - ub| (mode 0, L1Loss) or (ua - ub)^2 (mode 1, MSELoss) where
+ *   ua / ub are the tensor2im bytes of a / b (pix2pixHD_model.py:636-641); exact integer; the loss is
+ *   sum / (B*channels*H*W). `sum` is a device counter zeroed by the caller. */
+int jpdse_tensor2im_u8(const float* x, uint8_t* out, int batch, int channels, int height, int width,
+                       const double* mean, const double* std, void* stream);
+int jpdse_distortion_u8(const float* a, const float* b, unsigned long long* sum, int batch, int channels,
+                        int height, int width, int mode, const double* mean, const double* std,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

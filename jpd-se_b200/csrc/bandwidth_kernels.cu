@@ -555,3 +555,88 @@ extern "C" int jpdse_s2hvq_decode(const float* code_raw, const float* code_book,
       code_raw, code_book, rows, center_size, n_center, out, reinterpret_cast<long long*>(index));
   return check_launch("s2hvq_decode_kernel");
 }
+
+// ------------------------------------------------------------------------------------------ eval-metric path
+// tensor2im (ctu/utils/misc.py:64-95): uint8( clip( (x * std + mean) * 255, 0, 255 ) ) with numpy's float64 arithmetic and
+// C truncation, and the distortion the reference then takes between two such images (pix2pixHD_model.py:636-641,
+// test.py:115-123): L1Loss / MSELoss (mean over all elements) of the uint8 values.
+namespace jpdse {
+
+__device__ __forceinline__ uint8_t to_u8(float x, double mean, double std) {
+  double v = (static_cast<double>(x) * std + mean) * 255.0;
+  v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);  // np.clip; NaN falls through both compares like numpy's minimum/maximum do not,
+  return static_cast<uint8_t>(v);                // but a NaN pixel is outside the reference's domain (tanh output / normalised image)
+}
+
+__global__ void __launch_bounds__(256)
+tensor2im_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int B, int C, int H, int W, double m0, double m1,
+                    double m2, double s0, double s1, double s2) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * plane;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / plane, hw = i % plane;
+    const float* src = x + b * C * plane + hw;
+    uint8_t* dst = out + i * C;  // (B, H, W, C) like tensor2im's HWC images
+    for (int c = 0; c < C; ++c) {
+      const double mean = c == 0 ? m0 : (c == 1 ? m1 : m2), std = c == 0 ? s0 : (c == 1 ? s1 : s2);
+      dst[c] = to_u8(__ldg(src + c * plane), mean, std);
+    }
+  }
+}
+
+// sum over all elements of |a - b| (mode 0) or (a - b)^2 (mode 1) of the de-normalised uint8 images, exact in int64
+__global__ void __launch_bounds__(256)
+distortion_u8_kernel(const float* __restrict__ a, const float* __restrict__ b, unsigned long long* __restrict__ acc, int B, int C,
+                     int H, int W, int mode, double m0, double m1, double m2, double s0, double s1, double s2) {
+  __shared__ unsigned long long s_part[8];
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * C * plane;
+  unsigned long long sum = 0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>((i / plane) % C);
+    const double mean = c == 0 ? m0 : (c == 1 ? m1 : m2), std = c == 0 ? s0 : (c == 1 ? s1 : s2);
+    const int d = static_cast<int>(to_u8(__ldg(a + i), mean, std)) - static_cast<int>(to_u8(__ldg(b + i), mean, std));
+    sum += static_cast<unsigned long long>(mode == 0 ? (d < 0 ? -d : d) : d * d);
+  }
+  for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    atomicAdd(acc, t);
+  }
+}
+
+}  // namespace jpdse
+
+extern "C" int jpdse_tensor2im_u8(const float* x, uint8_t* out, int batch, int channels, int height, int width,
+                                  const double* mean, const double* std, void* stream) {
+  if (x == nullptr || out == nullptr || mean == nullptr || std == nullptr) return fail(JPDSE_ERR_INVALID, "tensor2im_u8: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0 || channels < 1 || channels > 3)
+    return fail(JPDSE_ERR_INVALID, "tensor2im_u8: bad sizes (channels must be 1..3)");
+  const size_t total = static_cast<size_t>(batch) * height * width;
+  const int grid = grid_for(total, 256, 4);
+  const double m[3] = {mean[0], channels > 1 ? mean[1] : 0.0, channels > 2 ? mean[2] : 0.0};
+  const double s[3] = {std[0], channels > 1 ? std[1] : 1.0, channels > 2 ? std[2] : 1.0};
+  tensor2im_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, batch, channels, height, width, m[0], m[1], m[2],
+                                                                            s[0], s[1], s[2]);
+  return check_launch("tensor2im_u8_kernel");
+}
+
+extern "C" int jpdse_distortion_u8(const float* a, const float* b, unsigned long long* sum, int batch, int channels,
+                                   int height, int width, int mode, const double* mean, const double* std, void* stream) {
+  if (a == nullptr || b == nullptr || sum == nullptr || mean == nullptr || std == nullptr)
+    return fail(JPDSE_ERR_INVALID, "distortion_u8: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0 || channels < 1 || channels > 3 || mode < 0 || mode > 1)
+    return fail(JPDSE_ERR_INVALID, "distortion_u8: bad sizes / mode");
+  const size_t total = static_cast<size_t>(batch) * channels * height * width;
+  const int grid = grid_for(total, 256, 8);
+  const double m[3] = {mean[0], channels > 1 ? mean[1] : 0.0, channels > 2 ? mean[2] : 0.0};
+  const double s[3] = {std[0], channels > 1 ? std[1] : 1.0, channels > 2 ? std[2] : 1.0};
+  distortion_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, sum, batch, channels, height, width, mode, m[0],
+                                                                             m[1], m[2], s[0], s[1], s[2]);
+  return check_launch("distortion_u8_kernel");
+}

@@ -232,14 +232,11 @@ class Pix2PixHDModel(nn.Module):
         loss_G_distortion = self.criterionDistortion(fake_image, real_image)
         return loss_G_GAN, loss_G_GAN_Feat, loss_G_VGG, loss_G_distortion, loss_D_real, loss_D_fake
 
-    def _to_uint8_float(self, t):
-        """tensor2im (ctu/utils/misc.py:64-95) on-device: (x*std+mean)*255 in float64, clip, TRUNCATE to uint8."""
-        mean = torch.tensor(_opt(self.opt, 'normalize_mean', (0.5, 0.5, 0.5)), dtype=torch.float64, device=t.device)
-        std = torch.tensor(_opt(self.opt, 'normalize_std', (1.0, 1.0, 1.0)), dtype=torch.float64, device=t.device)
-        x = (t.detach().float().double() * std.view(1, -1, 1, 1) + mean.view(1, -1, 1, 1)) * 255.0
-        return x.clamp_(0, 255).to(torch.uint8).to(torch.float)
-
     def get_eval_loss(self, x_dict):
+        """pix2pixHD_model.py:621-641: distortion AFTER de-normalisation and uint8 truncation (tensor2im,
+        ctu/utils/misc.py:64-95), computed on-device by jpdse_distortion_u8 -- no GPU->CPU->numpy->GPU round trip."""
         recon = self.get_img(x_dict)
-        real = x_dict['image'].cuda(non_blocking=True).float()
-        return self.criterionDistortion(self._to_uint8_float(recon), self._to_uint8_float(real))
+        real = x_dict['image'].cuda(non_blocking=True).float().contiguous()
+        mode = 'l1' if _opt(self.opt, 'distortion_loss_fn', 'l1') == 'l1' else 'mse'
+        return ops.distortion_u8(recon.contiguous(), real, mode, _opt(self.opt, 'normalize_mean', (0.5, 0.5, 0.5)),
+                                 _opt(self.opt, 'normalize_std', (1.0, 1.0, 1.0))).float()

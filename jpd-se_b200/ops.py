@@ -298,3 +298,36 @@ def s2hvq_decode(code_raw_rows, code_book, want_index=False):
     check(lib.jpdse_s2hvq_decode(_ptr(code_raw_rows), _ptr(code_book), rows, d, L, _ptr(out), _ptr(idx), _stream()))
     _count()
     return (out, idx) if want_index else out
+
+
+# ------------------------------------------------------------------------------------------------ eval metric
+def _dvec(v, n):
+    v = list(v)[:n]
+    return (ctypes.c_double * n)(*[float(a) for a in v])
+
+
+def tensor2im_u8(x, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
+    """ctu/utils/misc.py tensor2im on-device: float32 (B,C,H,W) -> uint8 (B,H,W,C), bit-exact with numpy."""
+    lib = _lib.load()
+    _need(x, "x", torch.float32)
+    B, C, H, W = x.shape
+    out = torch.empty((B, H, W, C), dtype=torch.uint8, device=x.device)
+    check(lib.jpdse_tensor2im_u8(_ptr(x), _ptr(out), B, C, H, W, _dvec(mean, C), _dvec(std, C), _stream()))
+    _count()
+    return out
+
+
+def distortion_u8(a, b, mode="l1", mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
+    """L1 / MSE between the tensor2im bytes of two float32 (B,C,H,W) images, as a 0-dim float64 tensor (no host sync)."""
+    lib = _lib.load()
+    _need(a, "a", torch.float32)
+    _need(b, "b", torch.float32)
+    if a.shape != b.shape:
+        raise JpdseError("distortion_u8: shapes differ")
+    B, C, H, W = a.shape
+    acc = torch.zeros(1, dtype=torch.int64, device=a.device)
+    check(lib.jpdse_distortion_u8(_ptr(a), _ptr(b), _ptr(acc), B, C, H, W, {"l1": 0, "mse": 1}[mode], _dvec(mean, C),
+                                  _dvec(std, C), _stream()))
+    _count(2)
+    # tensor / tensor: a true IEEE division (torch turns tensor / python-scalar into a multiply by the reciprocal)
+    return acc[0].double() / torch.tensor(float(a.numel()), dtype=torch.float64, device=a.device)

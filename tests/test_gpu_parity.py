@@ -411,3 +411,24 @@ def test_s2hvq_random_floats_match_up_to_near_ties(cuda):
     gap = (sc.gather(1, idx[:, None]) - sc.gather(1, ref_idx[:, None])).abs().squeeze(1)
     assert bool(((gap <= 1e-5 * sc.min(dim=-1).values.abs().clamp_min(1.0)) | same).all())
     assert torch.allclose(out["soft"].cpu(), torch.softmax(-3.0 * sc, dim=-1), atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ eval-metric path
+def test_tensor2im_and_distortion_bit_exact(cuda):
+    """tensor2im (float64 de-normalise, clip, TRUNCATE) and the L1 / MSE taken on its bytes."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    B, H, W = 3, 37, 53
+    a = (torch.rand(B, 3, H, W, generator=g) * 1.3 - 0.65)   # beyond [-0.5, 0.5]: exercises the clip on both sides
+    b = torch.tanh(torch.randn(B, 3, H, W, generator=g))
+    a[0, 0, 0, :6] = torch.tensor([-0.5, 0.5, 0.0, 0.4999999, 127.5 / 255 - 0.5, 1.0 / 255 - 0.5])
+    for mean, std in (((0.5, 0.5, 0.5), (1.0, 1.0, 1.0)), ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))):
+        ua = np.stack([orc.tensor2im_uint8(t, mean, std) for t in a])
+        ub = np.stack([orc.tensor2im_uint8(t, mean, std) for t in b])
+        got = ops.tensor2im_u8(a.to(cuda), mean, std).cpu().numpy()
+        assert np.array_equal(got, ua)
+        for mode in ("l1", "mse"):
+            d = ua.astype(np.float64) - ub.astype(np.float64)
+            want = np.abs(d).mean() if mode == "l1" else (d * d).mean()
+            val = float(ops.distortion_u8(a.to(cuda), b.to(cuda), mode, mean, std))
+            assert val == want, (mode, val, want)
