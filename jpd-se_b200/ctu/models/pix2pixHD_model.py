@@ -47,9 +47,12 @@ class Pix2PixHDModel(nn.Module):
             if _opt(opt, flag, want) != want:
                 raise NotImplementedError('jpdse_b200 Pix2PixHDModel: option %s=%r is outside the accelerated path '
                                           '(shipped scripts use %r)' % (flag, getattr(opt, flag), want))
-        if self.is_train and (_opt(opt, 'fp16', False) or _opt(opt, 'niter_fix_global', 0) > 0):
-            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: --fp16 (apex) / --niter_fix_global are outside the '
-                                      'accelerated path')
+        if self.is_train and _opt(opt, 'niter_fix_global', 0) > 0:
+            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: --niter_fix_global is outside the accelerated path')
+        # --fp16 in the reference = apex AMP O1 around the whole step (pix2pixHD_trainer.py:65-67,75-76). Here the
+        # generator already computes in bf16 operands / fp32 accumulate; the flag puts the PyTorch-side networks (netD,
+        # VGG) under torch.autocast(bfloat16) -- no loss scaling needed for bf16. Off by default like the reference.
+        self.amp = bool(self.is_train and _opt(opt, 'fp16', False))
         self.num_labels = opt.num_labels + 1 if _opt(opt, 'contain_dontcare_label', False) else opt.num_labels
         netG_input_nc = self.num_labels
         if not _opt(opt, 'no_instance', False):
@@ -80,6 +83,13 @@ class Pix2PixHDModel(nn.Module):
             self.criterionGAN = networks.GANLoss(use_lsgan=not _opt(opt, 'no_lsgan', False))
             self.criterionFeat = torch.nn.L1Loss()
             self.criterionVGG = networks.VGGLoss(self.gpu_ids)
+            # The PyTorch-side networks (netD, VGG) are 70 % of a step: run them channels_last with cuDNN autotuning.
+            # Same fp32/TF32 arithmetic and parameter shapes -- a layout choice only (JPDSE_NO_CHANNELS_LAST=1 disables).
+            self.channels_last = len(self.gpu_ids) > 0 and os.environ.get('JPDSE_NO_CHANNELS_LAST', '0') != '1'
+            if self.channels_last:
+                torch.backends.cudnn.benchmark = True
+                self.netD.to(memory_format=torch.channels_last)
+                self.criterionVGG.vgg.to(memory_format=torch.channels_last)
         else:
             self.loss_names = ('G_Distortion')  # sic: a plain string in the reference (:215)
         fn = _opt(opt, 'distortion_loss_fn', 'l1')
@@ -200,35 +210,54 @@ class Pix2PixHDModel(nn.Module):
         image = x_dict['image'].cuda(non_blocking=True).float().contiguous()
         return label, inst, image
 
+    def _cl(self, t):
+        return t.contiguous(memory_format=torch.channels_last) if getattr(self, 'channels_last', False) else t
+
     def discriminate(self, input_label, test_image, use_pool=False, keep_input=False):
         # cuts the graph of both inputs: this is the discriminator's own loss
         input_concat = torch.cat((input_label.detach(), test_image.detach()), dim=1)
-        return self.netD.forward(input_concat, keep_input)
+        return self.netD.forward(self._cl(input_concat), keep_input)
 
     def get_train_loss(self, x_dict):
         opt = self.opt
-        if _opt(opt, 'use_compressed', False) or _opt(opt, 'zero_vis', False) or _opt(opt, 'zero_sem', False) \
-                or _opt(opt, 'zero_ins', False) or _opt(opt, 'no_instance', False):
-            raise NotImplementedError('jpdse_b200: get_train_loss supports the shipped training configuration only')
-        label, inst, real_image = self._fast_inputs(x_dict)
-        # one input-build launch gives the reference's input_label (for netD) AND the stem operand
-        bad = torch.zeros(1, dtype=torch.int32, device=real_image.device)
-        _, nchw = ops.build_input(label, inst, real_image, self.num_labels, nhwc=False, nchw=True, bad_count=bad)
-        input_label = nchw[:, :self.num_labels + 1]
-        fake_image = self.netG.forward_from_maps(label, inst, real_image, self.num_labels)
+        if _opt(opt, 'use_compressed', False) and 'compressed_img' not in x_dict:
+            raise JpdseError("x_dict['compressed_img'] is required with --use_compressed: libbpg is outside this path, "
+                             "supply the decoded image tensor")
+        plain = not (_opt(opt, 'zero_vis', False) or _opt(opt, 'zero_sem', False) or _opt(opt, 'zero_ins', False)
+                     or _opt(opt, 'no_instance', False) or _opt(opt, 'use_compressed', False))
+        if plain:
+            label, inst, real_image = self._fast_inputs(x_dict)
+            # one input-build launch gives the reference's input_label (for netD), a second one the stem operand
+            bad = torch.zeros(1, dtype=torch.int32, device=real_image.device)
+            _, nchw = ops.build_input(label, inst, real_image, self.num_labels, nhwc=False, nchw=True, bad_count=bad)
+            input_label = nchw[:, :self.num_labels + 1]
+            fake_image = self.netG.forward_from_maps(label, inst, real_image, self.num_labels)
+        else:
+            # the reference's own route (pix2pixHD_model.py:711-712): preprocess -> _get_img (zeroing switches,
+            # compressed input) -> netG on the (B,39,H,W) tensor; the generator still runs on the sm_100a kernels
+            pre = self.preprocess(x_dict)
+            if _opt(opt, 'use_compressed', False):
+                pre['compressed_img'] = x_dict['compressed_img'].cuda(non_blocking=True).float()
+            real_image = pre['real_image']
+            fake_image, input_label = self._get_img(pre)
         keep_input = bool(_opt(opt, 'match_raw_feat', False))
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.amp):
+            return self._losses(input_label, fake_image, real_image, keep_input)
+
+    def _losses(self, input_label, fake_image, real_image, keep_input):
+        opt = self.opt
         pred_fake_pool = self.discriminate(input_label, fake_image, use_pool=True)
         loss_D_fake = self.criterionGAN(pred_fake_pool, False)
         pred_real = self.discriminate(input_label, real_image, keep_input=keep_input)
         loss_D_real = self.criterionGAN(pred_real, True)
-        pred_fake = self.netD.forward(torch.cat((input_label, fake_image), dim=1), keep_input=keep_input)
+        pred_fake = self.netD.forward(self._cl(torch.cat((input_label, fake_image), dim=1)), keep_input=keep_input)
         loss_G_GAN = self.criterionGAN(pred_fake, True)
         loss_G_GAN_Feat = 0.
         D_weights = 1.0 / _opt(opt, 'num_D', 2)
         for i in range(_opt(opt, 'num_D', 2)):
             for j in range(len(pred_fake[i]) - 1):
                 loss_G_GAN_Feat = loss_G_GAN_Feat + D_weights * self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
-        loss_G_VGG = self.criterionVGG(fake_image, real_image)
+        loss_G_VGG = self.criterionVGG(self._cl(fake_image), self._cl(real_image))
         loss_G_distortion = self.criterionDistortion(fake_image, real_image)
         return loss_G_GAN, loss_G_GAN_Feat, loss_G_VGG, loss_G_distortion, loss_D_real, loss_D_fake
 

@@ -354,3 +354,27 @@ def test_trainer_step_runs_and_learns(cuda, tmp_path):
     a = trainer.get_img(x_dict)
     b = t2.get_img(x_dict)
     assert torch.equal(a, b)
+
+
+def test_train_loss_reference_route_matches_fused_route(cuda, tmp_path):
+    """get_train_loss through preprocess -> _get_img -> netG(input_concat) (the reference's own route, taken for the
+    zero_* / compressed switches) gives the same losses as the fused input-build route, and zero_sem changes them."""
+    import importlib
+    import bench
+    p2p = importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_model")
+    opt = bench.make_opt()
+    opt.is_train, opt.n_downsample_global, opt.n_blocks_global, opt.quiet = True, 2, 1, True
+    torch.manual_seed(3)
+    model = p2p.Pix2PixHDModel(opt).cuda()
+    label, inst, image = bench.synth_inputs(1, 64, 128, seed=4)
+    x = {"label": label, "instance": inst, "image": image}
+    with torch.no_grad():
+        fused = [float(v) for v in model(dict(x), opt, mode="get_train_loss")]
+        opt.use_compressed = True  # forces the reference route; the "decoded" image is the same tensor
+        ref_route = [float(v) for v in model(dict(x, compressed_img=image), opt, mode="get_train_loss")]
+        opt.use_compressed = False
+        opt.zero_sem = True
+        zeroed = [float(v) for v in model(dict(x), opt, mode="get_train_loss")]
+        opt.zero_sem = False
+    assert all(abs(a - b) <= 2e-3 * max(1.0, abs(a)) for a, b in zip(fused, ref_route)), (fused, ref_route)
+    assert abs(zeroed[3] - fused[3]) > 1e-5  # the distortion moves when the semantics are zeroed

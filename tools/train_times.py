@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--width", type=int, default=1024)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--no-step", action="store_true")
+    ap.add_argument("--fp16", action="store_true", help="opt.fp16: netD / VGG under bf16 autocast")
     args = ap.parse_args()
     import torch
     import jpdse_b200  # noqa: F401
@@ -27,7 +28,7 @@ def main():
     dev = torch.device("cuda")
     torch.manual_seed(1234)
     opt = bench.make_opt()
-    opt.is_train, opt.quiet = True, True
+    opt.is_train, opt.quiet, opt.fp16 = True, True, args.fp16
     trainer = tr.Pix2PixHDTrainer(opt, mode="train")
     net = trainer.model.netG
     B, H, W = args.batch, args.height, args.width
