@@ -185,9 +185,13 @@ instnorm_apply_kernel(const __nv_bfloat16* __restrict__ raw, const double* __res
     for (int it = 0; it < kNormIters; ++it) {
       const int pp = pix0 + it * ppi + psub;
       if (pp >= npix) break;
-      const int ph = pp / Wp, pw = pp - ph * Wp;
-      const int h = reflect_index(ph - pad, H), w = reflect_index(pw - pad, W);
-      const uint4 x = __ldg(raw4 + (static_cast<size_t>(h) * W + w) * vpp + vec);
+      size_t src = static_cast<size_t>(pp);  // pad == 0: output pixel == raw pixel, no index arithmetic
+      if (pad > 0) {
+        const int ph = pp / Wp, pw = pp - ph * Wp;
+        const int h = reflect_index(ph - pad, H), w = reflect_index(pw - pad, W);
+        src = static_cast<size_t>(h) * W + w;
+      }
+      const uint4 x = __ldg(raw4 + src * vpp + vec);
       uint4 rs = make_uint4(0, 0, 0, 0);
       if (kResidual) rs = __ldg(res4 + static_cast<size_t>(pp) * vpp + vec);
       const uint32_t xw[4] = {x.x, x.y, x.z, x.w};
