@@ -432,3 +432,47 @@ def test_tensor2im_and_distortion_bit_exact(cuda):
             want = np.abs(d).mean() if mode == "l1" else (d * d).mean()
             val = float(ops.distortion_u8(a.to(cuda), b.to(cuda), mode, mean, std))
             assert val == want, (mode, val, want)
+
+
+def test_cuda_graph_replay_equals_eager_launches(cuda):
+    """Inference plans replay a captured CUDA graph; the result must be bit-identical to the eager launch sequence, for
+    changing inputs, both entry points, and across a weight update (graphs are re-captured)."""
+    import bench
+    nw = _networks()
+    torch.manual_seed(11)
+    net = nw.define_G(39, 3, 64, "global", 4, 2, 1, 3, "instance", gpu_ids=[0]).eval()
+    outs = {}
+    for use_graph in (True, False):
+        with torch.no_grad():
+            res = []
+            for seed in (1, 2, 1):
+                label, inst, image = [t.to(cuda) for t in bench.synth_inputs(2, 128, 256, seed=seed)]
+                plan = net.plan_for(2, 128, 256, cuda)
+                plan.use_graph = use_graph
+                res.append(net.forward_from_maps(label, inst, image, 35).clone())
+                res.append(net(torch.randn(2, 39, 128, 256, generator=torch.Generator().manual_seed(seed)).to(cuda)).clone())
+            outs[use_graph] = res
+    assert all(torch.equal(a, b) for a, b in zip(outs[True], outs[False]))
+    assert torch.equal(outs[True][0], outs[True][4]) and not torch.equal(outs[True][0], outs[True][2])
+    with torch.no_grad():
+        label, inst, image = [t.to(cuda) for t in bench.synth_inputs(2, 128, 256, seed=1)]
+        net.plan_for(2, 128, 256, cuda).use_graph = True
+        before = net.forward_from_maps(label, inst, image, 35).clone()
+        for p in net.parameters():
+            p.mul_(1.01)
+        after = net.forward_from_maps(label, inst, image, 35)
+    assert not torch.equal(before, after)
+
+
+def test_full_res_2048x1024_batch_independence(cuda):
+    """BASELINE.json configs[2] size: image i of a batch equals the same image run alone."""
+    import bench
+    nw = _networks()
+    torch.manual_seed(1234)
+    net = nw.define_G(39, 3, 64, "global", 4, 9, 1, 3, "instance", gpu_ids=[0]).eval()
+    label, inst, image = [t.to(cuda) for t in bench.synth_inputs(2, 1024, 2048, seed=5)]
+    with torch.no_grad():
+        both = net.forward_from_maps(label, inst, image, 35).clone()
+        one = net.forward_from_maps(label[1:].contiguous(), inst[1:].contiguous(), image[1:].contiguous(), 35)
+    assert both.shape == (2, 3, 1024, 2048) and torch.isfinite(both).all()
+    assert torch.equal(both[1:], one)
