@@ -11,13 +11,19 @@
 //   * B tiles (BN output channels x 64, bf16) come from a pre-packed K-major weight matrix.
 //   * tcgen05.mma (M=128, N=BN, K=16) accumulates in TMEM (fp32); two accumulator buffers let the
 //     epilogue of tile i overlap the main loop of tile i+1.
-//   * The epilogue reads TMEM with tcgen05.ld, writes bf16 NHWC and reduces the InstanceNorm
-//     statistics (sum, sum of squares per (image, channel)) with a warp-shuffle transpose-reduce,
-//     or applies bias+tanh / sign for the two terminal convs.
+//   * The epilogue reads TMEM with tcgen05.ld and reduces the InstanceNorm statistics (sum, sum of squares per
+//     (image, channel)) through a 32x16-word shared-memory transpose, or applies bias+tanh / sign for the two terminal
+//     convs. bf16 NHWC tiles of the N <= 128 instantiations (and of N = 256 where a tile has <= 48 k-blocks) are written
+//     into swizzled shared-memory staging and leave through ONE TMA store per 64-channel half: per-lane global stores
+//     (16 B at a pixel stride) cost the epilogue warps 2-3k cycles per 32-column chunk and made the low-K convs
+//     epilogue-bound. The res-block convs (144 k-blocks a tile) keep the fourth pipeline stage and per-lane stores.
+//   * The same kernel is the data-gradient conv of the backward pass: JPDSE_CONV3X3_FULL / CONV7X7_FULL run over flat
+//     positions of the zero-bordered gradient (any H, W), and stride-2 <-> ConvTranspose swap roles on one weight tensor.
 //
 // Warp roles (320 threads): warps 0..3 and 4..7 = two epilogue warpgroups, one per TMEM accumulator buffer (TMEM
-// lane quarter = warp_idx % 4); warp 8 = TMA producer, warp 9 = TMEM owner + MMA issuer. For the low-K convs
-// (full-resolution ConvT / stride-2 layers) the epilogue, not the MMA, is the critical path.
+// lane quarter = warp_idx % 4); warp 8 = TMA producer, warp 9 = TMEM owner + MMA issuer.
+// What bounds it: the res-block convs the tensor pipe (81-85 % active); every conv whose A tiles are unique to a CTA the
+// L2 -> SM fabric (~43 B/clk/SM of unique bytes), see conv_convt.cu for the layers where that was worth a new kernel.
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -34,15 +40,16 @@ constexpr int kBlockK = 64;         // bf16 elements per k-block = one 128-byte 
 constexpr int kUmmaK = 16;          // K of one tcgen05.mma for 16-bit inputs
 constexpr int kABytes = kTileM * kBlockK * 2;
 constexpr int kMaxTaps = 9;
-constexpr int kThreads = 352;       // two epilogue warpgroups (one per TMEM accumulator) + 3 control warps
+constexpr int kThreads = 320;       // two epilogue warpgroups (one per TMEM accumulator) + 2 control warps
 // The control warps get the HIGHEST warp ids: the sub-partition arbiter favours high ids, and the single TMA /
 // MMA threads are the critical path of the low-K convs.
-// TWO producer threads (warps 8 and 9) fill alternate pipeline stages: one thread's wait -> expect_tx -> 2 x TMA issue
-// round costs ~500 cycles per k-block whatever the box size (measured with the MMA and the epilogue switched off),
-// which is slower than the MMAs of every N <= 128 conv and barely matches N = 256.
+// kNumProducers > 1 makes that many warps fill alternate pipeline stages. Measured: a second producer changes nothing
+// (0.496 ms either way with MMAs and epilogue off) -- the ~480-cycle floor per 16 KiB A box is the L2 -> SM fabric's
+// unique-byte cap, not the issuing thread -- so one producer it is; the code path stays for the experiment.
 constexpr int kProducerWarp = 8;
-constexpr int kNumProducers = 2;
-constexpr int kMmaWarp = 10;
+constexpr int kNumProducers = 1;
+constexpr int kMmaWarp = kProducerWarp + kNumProducers;
+static_assert(kThreads == 32 * (kMmaWarp + 1), "warp roles and block size out of step");
 
 struct IgemmParams {
   // tile grid
@@ -67,7 +74,11 @@ struct IgemmParams {
   double* stats;
   const float* bias;
   long long* dbg;  // optional per-CTA role wait counters (tools only), else nullptr
-  int dbg_flags;   // developer experiments: bit0 skip statistics, bit1 skip output stores
+  // developer experiments (env JPDSE_DEBUG_FLAGS, read once per process; 0 in production):
+  //   1 skip statistics | 2 skip output stores | 4 spin instead of parked wait in the epilogue | 8 epilogue hands the
+  //   accumulator straight back (no TMEM read) | 16 skip the MMAs | 32 skip the B (weight) TMA load | 64 plain
+  //   mbarrier arrive instead of tcgen05.commit for the stage release (only with 16)
+  int dbg_flags;
 };
 
 // STG = 1: bf16 NHWC output through shared-memory staging + TMA store (always for BN = 64 / 128; for BN = 256 it
@@ -881,8 +892,13 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
 
   // bf16 NHWC outputs of the BN = 64 / 128 instantiations leave through shared memory + TMA store
   // (BN = 256 gives up a pipeline stage for the staging, so only where the epilogue is exposed: <= 48 k-blocks a tile)
+  static int staged_limit = -1;  // k-blocks per tile up to which N = 256 trades its fourth stage for the staged epilogue
+  if (staged_limit < 0) {
+    const char* e = getenv("JPDSE_STAGED_KBLOCKS");
+    staged_limit = e ? atoi(e) : 48;
+  }
   const int kblocks_per_tile = (d->kind == JPDSE_CONV1X1 ? 1 : 9) * g.cpt;
-  const bool staged_out = (g.bn == 64 || g.bn == 128 || (g.bn == 256 && kblocks_per_tile <= 48)) && !flat &&
+  const bool staged_out = (g.bn == 64 || g.bn == 128 || (g.bn == 256 && kblocks_per_tile <= staged_limit)) && !flat &&
                           (d->cout % 64) == 0 && d->kind != JPDSE_CONV7X7_PAD3 &&
                           (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW);
   const uint64_t C = static_cast<uint64_t>(d->cin);

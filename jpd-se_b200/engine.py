@@ -196,6 +196,10 @@ class GeneratorPlan:
     # ---- forward
     def forward_from_x0(self):
         """Runs the generator on self.x0 (bf16 NHWC, reflect-padded by 3); returns fp32 NCHW (B,out,H,W)."""
+        with ops.stream_cached():
+            return self._forward_from_x0()
+
+    def _forward_from_x0(self):
         self.stats.zero_()
         ops._count()
         self.layers = []
@@ -296,6 +300,10 @@ class GeneratorPlan:
             raise JpdseError("this GeneratorPlan was built for inference (training=False)")
         if not self.layers:
             raise JpdseError("backward() called before forward()")
+        with ops.stream_cached():
+            return self._backward(grad_out, weight_shapes, on_grad, alloc)
+
+    def _backward(self, grad_out, weight_shapes, on_grad, alloc):
         B, H, W = self.B, self.H, self.W
         dev = self.device
         grads = {}

@@ -19,8 +19,30 @@ _INST_DTYPES = {torch.int32: 0, torch.int16: 1, torch.int64: 2, torch.float32: 3
 launch_count = 0
 
 
+_cached_stream = None
+
+
 def _stream():
+    if _cached_stream is not None:
+        return _cached_stream
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class stream_cached:
+    """Query torch's current stream once for a whole kernel sequence (a plan forward / backward issues 60-250 C-ABI
+    calls; the per-call lookup is a measurable part of the host time at small batch). Not re-entrant across streams:
+    the sequence inside the block must stay on the stream that was current on entry."""
+
+    def __enter__(self):
+        global _cached_stream
+        self.prev = _cached_stream
+        _cached_stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return self
+
+    def __exit__(self, *exc):
+        global _cached_stream
+        _cached_stream = self.prev
+        return False
 
 
 def _ptr(t):
