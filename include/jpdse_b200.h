@@ -102,6 +102,8 @@ int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w, void* w_pa
 /* y = conv(x). `bias` is only read by JPDSE_EPI_BIAS_TANH_NCHW; `stats` only by RAW_STATS. */
 int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const void* w_packed,
                        const float* bias, void* y, double* stats, void* stream);
+/* Kernel launches one jpdse_conv_forward enqueues (4 for the per-phase ConvTranspose path, else 1). 0 on error. */
+int jpdse_conv_launch_count(const jpdse_conv_desc* d);
 /* FLOPs (2*MAC, algorithmic: real taps and real channels only) of one jpdse_conv_forward. */
 double jpdse_conv_flops(const jpdse_conv_desc* d);
 

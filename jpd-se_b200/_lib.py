@@ -33,6 +33,7 @@ SIGNATURES = {
     "jpdse_conv_forward": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                    c_void_p]),
     "jpdse_conv_flops": (c_double, [ctypes.POINTER(ConvDesc)]),
+    "jpdse_conv_launch_count": (c_int, [ctypes.POINTER(ConvDesc)]),
     "jpdse_conv_wgrad_workspace_bytes": (c_size_t, [ctypes.POINTER(ConvDesc), c_int]),
     "jpdse_conv_wgrad": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p,
                                  c_size_t, c_void_p]),

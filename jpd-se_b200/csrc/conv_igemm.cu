@@ -814,6 +814,12 @@ extern "C" size_t jpdse_conv_packed_weight_bytes(const jpdse_conv_desc* d) {
   return static_cast<size_t>(g.rows) * g.ktot * 2;
 }
 
+extern "C" int jpdse_conv_launch_count(const jpdse_conv_desc* d) {
+  ConvGeom g;
+  if (conv_geom(d, &g) != JPDSE_OK) return 0;
+  return (d->kind == JPDSE_CONVT3X3_S2 && g.path == kPathIgemm) ? 4 : 1;  // generic ConvTranspose = one launch per phase
+}
+
 extern "C" double jpdse_conv_flops(const jpdse_conv_desc* d) {
   ConvGeom g;
   if (conv_geom(d, &g) != JPDSE_OK) return 0.0;

@@ -116,6 +116,7 @@ class Conv:
         self.w_packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=device)
         self.bias = None
         self.flops = self.lib.jpdse_conv_flops(ctypes.byref(self.desc))
+        self.launches = self.lib.jpdse_conv_launch_count(ctypes.byref(self.desc))
         self.kind, self.epilogue = kind, epilogue
         self.out_hw = {CONV3X3_S2: (in_h // 2, in_w // 2), CONVT3X3_S2: (in_h * 2, in_w * 2),
                        CONV3X3_FULL: (in_h + 2, in_w + 2), CONV7X7_FULL: (in_h + 6, in_w + 6)}.get(kind, (in_h, in_w))
@@ -135,7 +136,7 @@ class Conv:
         _need(y, "y")
         check(self.lib.jpdse_conv_forward(ctypes.byref(self.desc), _ptr(x), _ptr(self.w_packed), _ptr(self.bias), _ptr(y),
                                           _ptr(stats), _stream()))
-        _count(4 if self.kind == CONVT3X3_S2 else 1)
+        _count(self.launches)
         return y
 
     def wgrad(self, x, dy, dy_pad, dw, accumulate=False):
