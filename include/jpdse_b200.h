@@ -185,6 +185,15 @@ int jpdse_sign_f32(const float* x, float* y, size_t n, void* stream);
 /* SoftSignFunction.forward with the uniform noise given: y = +1 if (1-x)/2 <= u else -1
  * (ctu/quantizers/binarize.py:20-24). */
 int jpdse_softsign_f32(const float* x, const float* u, float* y, size_t n, void* stream);
+/* Binarizer in train() mode (ctu/quantizers/binarize.py:44-65): the 1x1 conv is jpdse_conv_forward (JPDSE_CONV1X1,
+ * JPDSE_EPI_RAW -> pre_nhwc, bf16 (B,H,W,C)); forward: tanh_out = tanh(pre), y = +1 if (1 - tanh_out)/2 <= noise else -1,
+ * both float32 NCHW (B,C,H,W), noise ~ U[0,1) float32 NCHW supplied by the caller; backward (straight-through sign,
+ * :26-28): d_pre_nhwc (bf16 NHWC) = grad_y * (1 - tanh_out^2); the conv's gradients are jpdse_conv_wgrad and a
+ * jpdse_conv_forward with the transposed 1x1 weight. */
+int jpdse_binarizer_train_forward(const void* pre_nhwc, const float* noise, float* y, float* tanh_out,
+                                  int batch, int channels, int height, int width, void* stream);
+int jpdse_binarizer_train_backward(const float* grad_y, const float* tanh_out, void* d_pre_nhwc, int batch,
+                                   int channels, int height, int width, void* stream);
 /* Binary codes exported as bytes: (x+1)/2 for x in {-1,+1} (pix2pixHD_model.py:614, test.py:103-110). */
 int jpdse_sign_to_bits_u8(const float* x, uint8_t* y, size_t n, void* stream);
 /* S2HVQ (ctu/quantizers/s2h_vq.py): x is (rows, center_size) float32 = x_mtrx flattened over

@@ -53,6 +53,9 @@ SIGNATURES = {
     "jpdse_sign_to_bits_u8": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "jpdse_s2hvq_encode": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_float, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p]),
+    "jpdse_binarizer_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                              c_void_p]),
+    "jpdse_binarizer_train_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "jpdse_tensor2im_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.POINTER(c_double),
                                    ctypes.POINTER(c_double), c_void_p]),
     "jpdse_distortion_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

@@ -349,3 +349,75 @@ extern "C" int jpdse_tanh_backward_nchw(const float* grad_out, const float* out,
       grad_out, out, static_cast<__nv_bfloat16*>(d_pre), dbias, batch, channels, height, width);
   return check_launch("tanh_backward_nchw_kernel");
 }
+
+// ------------------------------------------------------------------------------------------ Binarizer, training mode
+// ctu/quantizers/binarize.py:44-65 in train(): y = SoftSign(tanh(conv1x1(x))). The 1x1 conv is the implicit-GEMM kernel
+// (raw bf16 NHWC output); these two kernels are the rest: tanh + stochastic sign forward (noise supplied by the caller,
+// drawn like the reference), and the straight-through backward  d_pre = dy * (1 - tanh^2)  (binarize.py:26-28).
+namespace jpdse {
+
+__global__ void __launch_bounds__(256)
+binarizer_train_fwd_kernel(const __nv_bfloat16* __restrict__ pre, const float* __restrict__ u, float* __restrict__ y,
+                           float* __restrict__ t_out, int B, int C, int H, int W) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * C * plane;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // i indexes NCHW (the module's output layout); the conv output is NHWC
+    const size_t hw = i % plane;
+    const size_t bc = i / plane;
+    const int c = static_cast<int>(bc % C);
+    const size_t b = bc / C;
+    const float t = tanhf(__bfloat162float(pre[(b * plane + hw) * C + c]));
+    t_out[i] = t;
+    const float thr = (1.f - t) / 2.f;  // SoftSignFunction.forward
+    y[i] = thr <= __ldg(u + i) ? 1.f : -1.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+binarizer_train_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ t, __nv_bfloat16* __restrict__ dpre, int B,
+                           int C, int H, int W) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * C * plane;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // i indexes NHWC (coalesced writes of the conv-gradient operand)
+    const int c = static_cast<int>(i % C);
+    const size_t p = i / C;
+    const size_t hw = p % plane, b = p / plane;
+    const size_t src = (b * C + c) * plane + hw;
+    const float tv = __ldg(t + src);
+    dpre[i] = __float2bfloat16_rn(__ldg(gy + src) * (1.f - tv * tv));
+  }
+}
+
+}  // namespace jpdse
+
+extern "C" int jpdse_binarizer_train_forward(const void* pre_nhwc, const float* noise, float* y, float* tanh_out, int batch,
+                                             int channels, int height, int width, void* stream) {
+  if (pre_nhwc == nullptr || noise == nullptr || y == nullptr || tanh_out == nullptr)
+    return fail(JPDSE_ERR_INVALID, "binarizer_train_forward: NULL pointer");
+  if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return fail(JPDSE_ERR_INVALID, "binarizer_train_forward: bad sizes");
+  const size_t total = static_cast<size_t>(batch) * channels * height * width;
+  size_t blocks = (total + 1023) / 1024;
+  const size_t cap = static_cast<size_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  binarizer_train_fwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(pre_nhwc), noise, y, tanh_out, batch, channels, height, width);
+  return check_launch("binarizer_train_fwd_kernel");
+}
+
+extern "C" int jpdse_binarizer_train_backward(const float* grad_y, const float* tanh_out, void* d_pre_nhwc, int batch,
+                                              int channels, int height, int width, void* stream) {
+  if (grad_y == nullptr || tanh_out == nullptr || d_pre_nhwc == nullptr)
+    return fail(JPDSE_ERR_INVALID, "binarizer_train_backward: NULL pointer");
+  if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0) return fail(JPDSE_ERR_INVALID, "binarizer_train_backward: bad sizes");
+  const size_t total = static_cast<size_t>(batch) * channels * height * width;
+  size_t blocks = (total + 1023) / 1024;
+  const size_t cap = static_cast<size_t>(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  binarizer_train_bwd_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      grad_y, tanh_out, static_cast<__nv_bfloat16*>(d_pre_nhwc), batch, channels, height, width);
+  return check_launch("binarizer_train_bwd_kernel");
+}

@@ -42,8 +42,8 @@ class Pix2PixHDModel(nn.Module):
         self.gpu_ids = list(_opt(opt, 'gpu_ids', [0]))
         self.is_train = _opt(opt, 'is_train', False)
         self.use_features = not _opt(opt, 'no_feat', False)
-        for flag, want in (('no_label_encoding', True), ('no_feat_encoding', True), ('no_generator_binarization', True),
-                           ('sem_masking', False), ('no_label', False)):
+        for flag, want in (('no_label_encoding', True), ('no_feat_encoding', True), ('sem_masking', False),
+                           ('no_label', False)):
             if _opt(opt, flag, want) != want:
                 raise NotImplementedError('jpdse_b200 Pix2PixHDModel: option %s=%r is outside the accelerated path '
                                           '(shipped scripts use %r)' % (flag, getattr(opt, flag), want))
@@ -63,7 +63,12 @@ class Pix2PixHDModel(nn.Module):
             netG_input_nc, _opt(opt, 'num_out_channels', 3), _opt(opt, 'ngf', 64), _opt(opt, 'netG', 'global'),
             _opt(opt, 'n_downsample_global', 4), _opt(opt, 'n_blocks_global', 9), _opt(opt, 'n_local_enhancers', 1),
             _opt(opt, 'n_blocks_local', 3), _opt(opt, 'norm', 'instance'), gpu_ids=self.gpu_ids,
-            binarize_generator=False)
+            binarize_generator=not _opt(opt, 'no_generator_binarization', True),
+            bin_generator_before_res=_opt(opt, 'bin_generator_before_res', False),
+            generator_binarizer_out_channels=_opt(opt, 'generator_binarizer_out_channels', 128))
+        if self.is_train and not _opt(opt, 'no_generator_binarization', True):
+            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: training a binarizing generator is outside the '
+                                      'accelerated path (inference / get_code / get_eval_rate are supported)')
         if self.is_train:
             # pix2pixHD_model.py:151-162: D sees semantics (+edge) + image
             netD_input_nc = self.num_labels + _opt(opt, 'num_out_channels', 3)
@@ -135,9 +140,10 @@ class Pix2PixHDModel(nn.Module):
             return self.get_train_loss(x_dict)
         if mode == 'get_eval_loss':
             return self.get_eval_loss(x_dict)
-        if mode in ('get_code', 'get_eval_rate'):
-            # only meaningful with encoders / binarizers, which the shipped scripts disable
-            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: mode %r needs the encoder/binarizer path' % mode)
+        if mode == 'get_code':
+            return self.get_code(self.preprocess(x_dict))
+        if mode == 'get_eval_rate':
+            return self.get_eval_rate(self.preprocess(x_dict))
         raise ValueError('Invalid forward mode: {}'.format(mode))
 
     # ------------------------------------------------------------------ preprocessing with reference outputs
@@ -168,8 +174,10 @@ class Pix2PixHDModel(nn.Module):
 
     # ------------------------------------------------------------------ generator call (pix2pixHD_model.py:508-618)
     def _get_img(self, x_dict, mode='get_continuous_img'):
-        if mode != 'get_continuous_img':
-            raise NotImplementedError('jpdse_b200: mode %r not on the accelerated path' % mode)
+        if mode not in ('get_continuous_img', 'get_binary_code'):
+            raise ValueError('Invalid forward mode: {}'.format(mode))
+        if mode == 'get_binary_code' and _opt(self.opt, 'no_generator_binarization', True):
+            return []  # no encoders on this path: the generator's Binarizer is the only code source (:581-582)
         input_label, real_image = x_dict['input_label'], x_dict['real_image']
         if _opt(self.opt, 'use_compressed', False):
             real_image = x_dict['compressed_img']
@@ -183,8 +191,32 @@ class Pix2PixHDModel(nn.Module):
             input_concat = torch.cat((input_label, feat_map), dim=1)
         else:
             input_concat = torch.cat((input_label, feat_map), dim=1)
+        if mode == 'get_binary_code':
+            # pix2pixHD_model.py:611-617: codes flattened per image and mapped {-1,+1} -> {0,1}
+            code = self.netG.forward(input_concat, mode='get_binary_code')
+            return [(code.view(code.size(0), -1) + 1) / 2.]
         fake_image = self.netG.forward(input_concat)
         return fake_image, input_label
+
+    def get_code(self, x_dict):
+        # pix2pixHD_model.py:493-505
+        with torch.no_grad():
+            return self._get_img(x_dict, mode='get_binary_code')
+
+    def get_eval_rate(self, x_dict):
+        """pix2pixHD_model.py:466-490: per-image Shannon bits-per-pixel of the binary code and the raw bpp."""
+        with torch.no_grad():
+            real_image = x_dict['real_image']
+            shannon_bpp_total, actual_bpp_total = 0., 0.
+            for codes_ in self.get_code(x_dict):
+                for j in range(real_image.size(0)):
+                    code = codes_[j]
+                    original_img_size = real_image[j].size(-2) * real_image[j].size(-1)
+                    code_p = torch.mean(code)
+                    code_entropy = - code_p * torch.log(code_p) - (1 - code_p) * torch.log(1 - code_p)
+                    shannon_bpp_total = shannon_bpp_total + code_entropy * code.size(-1) / original_img_size
+                    actual_bpp_total += code.size(-1) / original_img_size
+            return shannon_bpp_total / real_image.size(0), actual_bpp_total / real_image.size(0)
 
     def get_img(self, x_dict):
         """pix2pixHD_model.py:463-465. Fast path: ids + image -> fused input build -> generator."""

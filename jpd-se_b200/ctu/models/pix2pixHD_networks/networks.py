@@ -121,9 +121,11 @@ class GlobalGenerator(nn.Module):
                  padding_type='reflect', binarize=False, binarizer_out_channels=128, bin_before_res=True):
         assert (n_blocks >= 0)
         super(GlobalGenerator, self).__init__()
-        if binarize:
-            raise NotImplementedError('jpdse_b200: a Binarizer inside the generator is not wired yet; '
-                                      'use ctu.quantizers.binarize.Binarizer stand-alone')
+        if binarize and bin_before_res:
+            # the reference builds ResnetBlock(binarizer_out_channels) followed by ResnetBlock(ngf * mult)
+            # (networks.py:226-229): it only runs when the two widths coincide, and no shipped script enables it
+            raise NotImplementedError('jpdse_b200: bin_before_res=True is outside the accelerated path (the reference '
+                                      'wiring is only consistent for binarizer_out_channels == ngf * 2**n_downsampling)')
         activation = nn.ReLU(True)
         self.binarize = binarize
         self.bin_before_res = bin_before_res
@@ -140,9 +142,15 @@ class GlobalGenerator(nn.Module):
         mult = 2 ** n_downsampling
         for i in range(n_blocks):
             model += [ResnetBlock(ngf * mult, padding_type=padding_type, activation=activation, norm_layer=norm_layer)]
+        self.binarizer_out_channels = None
+        if binarize:  # behind the res blocks (networks.py:231-238)
+            from ....ctu.quantizers.binarize import Binarizer
+            model += [Binarizer(in_channels=ngf * mult, out_channels=binarizer_out_channels)]
+            self.binarizer_out_channels = binarizer_out_channels
         for i in range(n_downsampling):
             mult = 2 ** (n_downsampling - i)
-            model += [nn.ConvTranspose2d(ngf * mult, int(ngf * mult / 2), kernel_size=3, stride=2, padding=1,
+            in_channels = binarizer_out_channels if (i == 0 and binarize) else ngf * mult
+            model += [nn.ConvTranspose2d(in_channels, int(ngf * mult / 2), kernel_size=3, stride=2, padding=1,
                                          output_padding=1),
                       norm_layer(int(ngf * mult / 2)), activation]
         model += [nn.ReflectionPad2d(3), nn.Conv2d(ngf, output_nc, kernel_size=7, padding=0, bias=True), nn.Tanh()]
@@ -163,7 +171,8 @@ class GlobalGenerator(nn.Module):
         plan = self._plans.get(key)
         if plan is None:
             plan = GeneratorPlan(self.input_nc, self.output_nc, self.ngf, self.n_downsampling, self.n_blocks, batch,
-                                 height, width, device, training=training)
+                                 height, width, device, training=training,
+                                 binarizer_out_channels=self.binarizer_out_channels)
             # one live plan per mode: activations at batch 16 are several GB
             self._plans = {k: v for k, v in self._plans.items() if k[4] != bool(training)}
             self._plans[key] = plan
@@ -185,6 +194,11 @@ class GlobalGenerator(nn.Module):
     def _wants_grad(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
+    def train(self, mode=True):
+        # nn.Module.train flips the Binarizer to its stochastic mode; inside the generator plan it always runs the
+        # deterministic sign (inference-only there), so training a binarizing generator raises in plan_for instead
+        return super(GlobalGenerator, self).train(mode)
+
     def _run(self, batch, height, width, device, run):
         """Run `run(plan)`; with gradients enabled the call becomes one autograd node over all parameters."""
         if not self._wants_grad():
@@ -201,7 +215,10 @@ class GlobalGenerator(nn.Module):
         elif mode == 'get_binary_code':
             if not self.binarize:
                 raise AttributeError('Generator: no binarizer found')
-            raise NotImplementedError('jpdse_b200: generator binarizer not wired')
+            self._check_runnable(input)
+            B, _, H, W = input.shape
+            plan = self.plan_for(B, H, W, input.device)
+            return plan.binary_code_nchw(input.detach().contiguous().float()).clone()
         else:
             raise ValueError('Invalid generator mode: {}'.format(mode))
 

@@ -110,11 +110,20 @@ class Pix2PixHDTrainer(BaseTrainer):
         with torch.no_grad():
             return self.model(x_dict, self.opt, mode='get_img')
 
+    def _get_code(self, x_dict):
+        self.eval()
+        with torch.no_grad():
+            return self.model(x_dict, self.opt, mode='get_code')
+
     def get_code(self, x_dict):
-        raise NotImplementedError('jpdse_b200 Pix2PixHDTrainer.get_code: needs the encoder/binarizer path')
+        # pix2pixHD_trainer.py:100-103 (raises on an empty list like the reference's torch.cat)
+        return torch.cat([c for c in self._get_code(x_dict) if c is not None], dim=-1)
 
     def get_eval_rate(self, x_dict):
-        raise NotImplementedError('jpdse_b200 Pix2PixHDTrainer.get_eval_rate: needs the encoder/binarizer path')
+        # pix2pixHD_trainer.py:106-110
+        self.eval()
+        with torch.no_grad():
+            return self.model(x_dict, self.opt, mode='get_eval_rate')
 
     def save(self, epoch, val_loss_value):
         # pix2pixHD_trainer.py:119-141

@@ -24,8 +24,8 @@ import os
 import torch
 
 from . import ops
-from ._lib import (CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_FULL, CONV7X7_PAD3, CONVT3X3_S2, EPI_BIAS_TANH_NCHW,
-                   EPI_RAW, EPI_RAW_STATS, JpdseError)
+from ._lib import (CONV1X1, CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_FULL, CONV7X7_PAD3, CONVT3X3_S2,
+                   EPI_BIAS_TANH_NCHW, EPI_RAW, EPI_RAW_STATS, EPI_SIGN_NCHW, JpdseError)
 
 
 def _round_up(x, m):
@@ -42,7 +42,7 @@ class GeneratorPlan:
     """Buffers + conv descriptors for one (batch, H, W) problem size."""
 
     def __init__(self, input_nc, output_nc, ngf, n_downsampling, n_blocks, batch, height, width, device,
-                 training=False):
+                 training=False, binarizer_out_channels=None):
         if ngf % 64:
             raise JpdseError("jpdse_b200 generator needs ngf %% 64 == 0 (got %d)" % ngf)
         if output_nc > 128:
@@ -93,9 +93,27 @@ class GeneratorPlan:
             idx += 1
         self.up = []
         pad_in = 1 if n_blocks > 0 else 0  # the last res block leaves a reflect border we skip over
+        # Binarizer behind the res blocks (networks.py:231-238, bin_before_res=False): 1x1 conv + tanh + sign as ONE
+        # implicit-GEMM launch; the +-1 codes are then the input of the first ConvTranspose
+        self.binarizer = None
+        if binarizer_out_channels is not None:
+            if training:
+                raise JpdseError("jpdse_b200: a Binarizer inside the generator is inference-only (its stochastic "
+                                 "train mode is available on the stand-alone Binarizer module)")
+            if binarizer_out_channels % 64:
+                raise JpdseError("generator binarizer needs out_channels %% 64 == 0")
+            self.binarizer_name = "model.%d.conv" % idx
+            self.binarizer = ops.Conv(CONV1X1, EPI_SIGN_NCHW, B, h, w, pad_in, c, c, binarizer_out_channels, device)
+            self.convs[self.binarizer_name] = self.binarizer
+            self.codes = torch.empty((B, binarizer_out_channels, h, w), dtype=torch.float32, device=device)
+            self.codes_nhwc = ops.alloc_nhwc(B, h, w, binarizer_out_channels, device)
+            idx += 1
+            pad_in = 0
+        c_up = c if self.binarizer is None else binarizer_out_channels
         for i in range(n_downsampling):
             name = "model.%d" % idx
-            cv = ops.Conv(CONVT3X3_S2, EPI_RAW_STATS, B, h, w, pad_in if i == 0 else 0, c, c, c // 2, device)
+            cv = ops.Conv(CONVT3X3_S2, EPI_RAW_STATS, B, h, w, pad_in if i == 0 else 0, c_up if i == 0 else c,
+                          c_up if i == 0 else c, c // 2, device)
             self.convs[name] = cv
             if training:  # dgrad of a ConvTranspose == stride-2 conv on the same weight memory
                 self.dgrads[name] = ops.Conv(CONV3X3_S2, EPI_RAW, B, 2 * h, 2 * w, 0, c // 2, c // 2, c, device)
@@ -130,6 +148,7 @@ class GeneratorPlan:
             self.d_pre = torch.zeros(B * (H + 12) * (W + 12) * 8 + 2048, dtype=torch.bfloat16, device=device)
         self.layers = []
         self.generation = 0
+        self._codes_only = False  # mode='get_binary_code': stop behind the Binarizer
         # CUDA-graph replay of the inference forward (63 launches are host-bound below batch ~4: 2.5 -> ~1.2 ms at
         # batch 1); JPDSE_NO_GRAPH=1 or plan.use_graph = False runs every launch eagerly
         self.use_graph = not training and os.environ.get("JPDSE_NO_GRAPH", "0") != "1"
@@ -226,6 +245,11 @@ class GeneratorPlan:
                            consumer_reads_border=k != self.n_blocks - 1)
             si += 1
             cur = n_idx
+        if self.binarizer is not None:
+            self.binarizer.forward(x, self.codes)  # sign(tanh(conv1x1(x))), float32 NCHW like the reference's codes
+            if self._codes_only:
+                return self.codes
+            x = ops.nchw_to_nhwc_bf16(self.codes, out=self.codes_nhwc)
         for i, (name, cv) in enumerate(self.up):
             c, h, w = c // 2, 2 * h, 2 * w
             last = i == self.n_down - 1
@@ -265,6 +289,16 @@ class GeneratorPlan:
     def _eager_nchw(self, inp):
         ops.nchw_to_nhwc_bf16(inp, pad_reflect=3, c_pad=self.c_in_pad, out=self.x0)
         return self.forward_from_x0()
+
+    def binary_code_nchw(self, inp):
+        """GlobalGenerator.forward(mode='get_binary_code') (networks.py:252-261): the prefix up to the Binarizer."""
+        if self.binarizer is None:
+            raise JpdseError("this plan has no binarizer")
+        self._codes_only = True
+        try:
+            return self._eager_nchw(inp)
+        finally:
+            self._codes_only = False
 
     def forward_nchw(self, inp):
         """inp: float32 (B, input_nc, H, W) -- the tensor the reference feeds netG (pix2pixHD_model.py:609)."""

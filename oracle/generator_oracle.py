@@ -71,8 +71,9 @@ def _inorm(x, eps=1e-5):
     return F.instance_norm(x, eps=eps)
 
 
-def generator_layers(sd, n_downsampling, n_blocks):
-    """Yields (kind, prefix) in execution order for a GlobalGenerator state dict (networks.py:210-246)."""
+def generator_layers(sd, n_downsampling, n_blocks, binarize=False):
+    """Yields (kind, prefix) in execution order for a GlobalGenerator state dict (networks.py:210-246); with
+    binarize=True a Binarizer sits behind the res blocks (bin_before_res=False, networks.py:231-238)."""
     yield ("stem", "model.1")
     idx = 4
     for _ in range(n_downsampling):
@@ -81,13 +82,16 @@ def generator_layers(sd, n_downsampling, n_blocks):
     for _ in range(n_blocks):
         yield ("res", "model.%d" % idx)
         idx += 1
+    if binarize:
+        yield ("bin", "model.%d" % idx)
+        idx += 1
     for _ in range(n_downsampling):
         yield ("up", "model.%d" % idx)
         idx += 3
     yield ("head", "model.%d" % (idx + 1))
 
 
-def generator_forward(sd, x, n_downsampling=4, n_blocks=9, round_fn=None, collect=None):
+def generator_forward(sd, x, n_downsampling=4, n_blocks=9, round_fn=None, collect=None, binarize=False, codes_only=False):
     """GlobalGenerator.forward(mode='get_continuous_img'), networks.py:249-251, functional form.
 
     sd: state dict (torch tensors, reference keys); x: torch float32 (B,C,H,W).
@@ -106,7 +110,15 @@ def generator_forward(sd, x, n_downsampling=4, n_blocks=9, round_fn=None, collec
         bias = None if (emulate and not head) else sd[prefix + ".bias"]
         return F.conv2d(r(t), r(sd[prefix + ".weight"]), bias, **kw)
 
-    for kind, prefix in generator_layers(sd, n_downsampling, n_blocks):
+    for kind, prefix in generator_layers(sd, n_downsampling, n_blocks, binarize):
+        if kind == "bin":
+            # Binarizer eval (ctu/quantizers/binarize.py:51-54): sign(tanh(conv1x1_nobias(x)))
+            x = torch.sign(torch.tanh(F.conv2d(r(x), r(sd[prefix + ".conv.weight"]))))
+            if collect is not None:
+                collect[prefix] = x
+            if codes_only:
+                return x
+            continue
         if kind == "stem":
             x = F.relu(_inorm(r(conv(F.pad(x, (3, 3, 3, 3), mode="reflect"), prefix))))
         elif kind == "down":

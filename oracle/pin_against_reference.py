@@ -90,6 +90,21 @@ def main():
         assert torch.equal(Gf(xf), orc.generator_forward(Gf.state_dict(), xf, 4, 9))
     print("generator (full 182.6M-param architecture): oracle == reference (bit-exact)")
 
+    # binarizing generator (parser default when --no_generator_binarization is absent): Binarizer behind the res blocks
+    torch.manual_seed(11)
+    Gb = networks.define_G(39, 3, 64, "global", 4, 2, 1, 3, "instance", gpu_ids=[], binarize_generator=True,
+                           bin_generator_before_res=False).eval()
+    torch.manual_seed(11)
+    Gb2 = ours.define_G(39, 3, 64, "global", 4, 2, 1, 3, "instance", gpu_ids=[], binarize_generator=True,
+                        bin_generator_before_res=False)
+    assert list(Gb.state_dict().keys()) == list(Gb2.state_dict().keys())
+    assert all(torch.equal(v, Gb2.state_dict()[k]) for k, v in Gb.state_dict().items())
+    with torch.no_grad():
+        assert torch.equal(Gb(x), orc.generator_forward(Gb.state_dict(), x, 4, 2, binarize=True))
+        assert torch.equal(Gb(x, mode="get_binary_code"),
+                           orc.generator_forward(Gb.state_dict(), x, 4, 2, binarize=True, codes_only=True))
+    print("binarizing generator: oracle == reference (image and get_binary_code, bit-exact), same keys and init")
+
     # ---------------------------------------------------------------- generator backward (autograd through the reference)
     # loss_G.backward() (pix2pixHD_trainer.py:69) is autograd over the same modules: the oracle's functional forward
     # must give the reference's gradients bit for bit on CPU.

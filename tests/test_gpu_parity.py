@@ -476,3 +476,60 @@ def test_full_res_2048x1024_batch_independence(cuda):
         one = net.forward_from_maps(label[1:].contiguous(), inst[1:].contiguous(), image[1:].contiguous(), 35)
     assert both.shape == (2, 3, 1024, 2048) and torch.isfinite(both).all()
     assert torch.equal(both[1:], one)
+
+
+def test_binarizing_generator_inference(cuda):
+    """binarize_generator=True, bin_before_res=False (the parser default when --no_generator_binarization is absent):
+    Binarizer behind the res blocks, codes in {-1,+1}; mode='get_binary_code' returns them (networks.py:252-261).
+    Codes are signs of pre-activations, so against the fp32 reference only symbols whose pre-activation is within the
+    bf16 error of zero may flip: agreement >= 97 %; the decoded image is checked through the same-codes property
+    (image from OUR codes == oracle up-path on OUR codes within the bf16 tolerance)."""
+    nw = _networks()
+    torch.manual_seed(11)
+    net = nw.define_G(39, 3, 64, "global", 4, 2, 1, 3, "instance", gpu_ids=[], binarize_generator=True,
+                      bin_generator_before_res=False)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.randn(2, 39, 128, 256, generator=torch.Generator().manual_seed(6))
+    net = net.to(cuda).eval()
+    with torch.no_grad():
+        codes = net(x.to(cuda), mode="get_binary_code").cpu()
+        img = net(x.to(cuda)).cpu()
+        ref_codes = orc.generator_forward(sd, x, 4, 2, binarize=True, codes_only=True)
+    assert codes.shape == (2, 128, 8, 16) and set(codes.unique().tolist()) <= {-1.0, 0.0, 1.0}
+    assert float((codes == ref_codes).float().mean()) >= 0.97
+    # up-path of the oracle on our codes
+    up_sd = dict(sd)
+    with torch.no_grad():
+        t = codes
+        idx = 4 + 3 * 4 + 2 + 1
+        for i in range(4):
+            t = F.relu(F.instance_norm(F.conv_transpose2d(t, sd["model.%d.weight" % idx], sd["model.%d.bias" % idx], stride=2,
+                                                          padding=1, output_padding=1)))
+            idx += 3
+        want = torch.tanh(F.conv2d(F.pad(t, (3, 3, 3, 3), mode="reflect"), sd["model.%d.weight" % (idx + 1)],
+                                   sd["model.%d.bias" % (idx + 1)]))
+    assert float((img - want).abs().mean()) <= 0.02 and orc.psnr(img, want) >= 39.2
+    with pytest.raises(AttributeError):
+        nw.define_G(39, 3, 64, "global", 1, 0, 1, 3, "instance", gpu_ids=[0])(x[:, :, :128, :128].to(cuda), mode="get_binary_code")
+
+
+def test_trainer_get_code_and_eval_rate(cuda):
+    """Binarizing generator behind the ctu trainer API: get_code returns the {0,1} code bits (B, 128*h*w) and
+    get_eval_rate the (Shannon, raw) bits per pixel (pix2pixHD_trainer.py:100-110, pix2pixHD_model.py:466-490)."""
+    import bench
+    trainers = importlib.import_module("jpd-se_b200.ctu.trainers")
+    opt = bench.make_opt()
+    opt.no_generator_binarization, opt.n_blocks_global = False, 1
+    torch.manual_seed(8)
+    trainer = trainers.get_trainer(opt)(opt, "test")
+    label, inst, image = bench.synth_inputs(2, 128, 256, seed=2)
+    x_dict = {"label": label, "instance": inst, "image": image, "path": ["a", "b"]}
+    code = trainer.get_code(x_dict)
+    assert code.shape == (2, 128 * 8 * 16) and set(code.unique().tolist()) <= {0.0, 0.5, 1.0}
+    shannon, actual = trainer.get_eval_rate(x_dict)
+    assert abs(actual - 128 * 8 * 16 / (128 * 256)) < 1e-9
+    assert 0.0 < float(shannon) <= actual + 1e-6
+    img = trainer.get_img(x_dict)
+    assert img.shape == (2, 3, 128, 256) and torch.isfinite(img).all()
+    bits = _ops().sign_to_bits(code * 2 - 1)
+    assert bits.dtype == torch.uint8 and int(bits.max()) <= 1
