@@ -418,9 +418,9 @@ def main():
         line["train"] = train
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sec = cpu_reference_time(1, H, W, steps=3, warmup=1, weights={k: v.cpu() for k, v in netG.state_dict().items()})
+        sec = cpu_reference_time(1, H, W, steps=8, warmup=1, weights={k: v.cpu() for k, v in netG.state_dict().items()})
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": "3 timed forwards of batch 1 at %dx%d (same generator, fp32, torch CPU)" % (W, H)}
+                                "sample": "8 timed forwards of batch 1 at %dx%d (same generator, same synthetic inputs, fp32, torch CPU on all host threads; ~10 s)" % (W, H)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
