@@ -18,7 +18,7 @@ import os
 import torch
 import torch.nn as nn
 
-from ....engine import GeneratorPlan
+from ....engine import GeneratorPlan, make_inference_plan
 from ...._lib import JpdseError
 
 
@@ -170,9 +170,14 @@ class GlobalGenerator(nn.Module):
         key = (batch, height, width, str(device), bool(training))
         plan = self._plans.get(key)
         if plan is None:
-            plan = GeneratorPlan(self.input_nc, self.output_nc, self.ngf, self.n_downsampling, self.n_blocks, batch,
-                                 height, width, device, training=training,
-                                 binarizer_out_channels=self.binarizer_out_channels)
+            if training:
+                plan = GeneratorPlan(self.input_nc, self.output_nc, self.ngf, self.n_downsampling, self.n_blocks, batch,
+                                     height, width, device, training=True,
+                                     binarizer_out_channels=self.binarizer_out_channels)
+            else:
+                plan = make_inference_plan(self.input_nc, self.output_nc, self.ngf, self.n_downsampling, self.n_blocks,
+                                           batch, height, width, device,
+                                           binarizer_out_channels=self.binarizer_out_channels)
             # one live plan per mode: activations at batch 16 are several GB
             self._plans = {k: v for k, v in self._plans.items() if k[4] != bool(training)}
             self._plans[key] = plan

@@ -533,3 +533,28 @@ def test_trainer_get_code_and_eval_rate(cuda):
     assert img.shape == (2, 3, 128, 256) and torch.isfinite(img).all()
     bits = _ops().sign_to_bits(code * 2 - 1)
     assert bits.dtype == torch.uint8 and int(bits.max()) <= 1
+
+
+def test_split_stream_plan_equals_single_stream(cuda, monkeypatch):
+    """Batches >= 8 run as two half-batch plans on two CUDA streams inside one captured graph; the result must be
+    bit-identical to the single-stream plan (InstanceNorm is per-sample), eagerly and replayed."""
+    import bench
+    nw = _networks()
+    torch.manual_seed(12)
+    net = nw.define_G(39, 3, 64, "global", 4, 2, 1, 3, "instance", gpu_ids=[0]).eval()
+    label, inst, image = [t.to(cuda) for t in bench.synth_inputs(8, 128, 256, seed=9)]
+    outs = []
+    for split, use_graph in (("2", True), ("2", False), ("1", True)):
+        monkeypatch.setenv("JPDSE_SPLIT_STREAMS", split)
+        net._plans = {}
+        with torch.no_grad():
+            plan = net.plan_for(8, 128, 256, cuda)
+            assert hasattr(plan, "parts") == (split == "2")
+            plan.use_graph = use_graph
+            a = net.forward_from_maps(label, inst, image, 35).clone()
+            b = net.forward_from_maps(label, inst, image, 35).clone()   # second call: graph replay
+            x = torch.randn(8, 39, 128, 256, generator=torch.Generator().manual_seed(1)).to(cuda)
+            c = net(x).clone()
+        assert torch.equal(a, b)
+        outs.append((a, c))
+    assert all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) for o in outs[1:])

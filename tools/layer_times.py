@@ -7,6 +7,8 @@ import importlib
 import os
 import sys
 
+os.environ["JPDSE_SPLIT_STREAMS"] = "1"  # per-kernel events need the single-stream plan
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
