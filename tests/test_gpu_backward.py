@@ -452,3 +452,29 @@ def test_binarizer_train_mode_forward_and_backward(cuda):
     t_ref.backward(gy)  # straight-through: d(sign)/dt = 1
     assert float((m.conv.weight.grad.cpu() - wr.grad).abs().max()) <= 1e-2 * float(wr.grad.abs().max())
     assert float((xd.grad.cpu() - xr.grad).abs().max()) <= 2.0 ** -6 * float(xr.grad.abs().max())
+
+
+def test_wide_image_forward_backward_vs_oracle(cuda):
+    """A 128x1024 image (strip-shaped: many column strips, few rows) through the row-stationary stem / head, the fused
+    ConvTranspose kernel and their backward forms; forward and head / last-up-layer gradients against the oracle."""
+    from oracle import generator_oracle as orc
+    import bench
+    nw = _networks()
+    torch.manual_seed(31)
+    net = nw.define_G(39, 3, 64, "global", 3, 1, 1, 3, "instance", gpu_ids=[])
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    label, inst, image = bench.synth_inputs(1, 128, 1024, seed=6)
+    x = torch.from_numpy(orc.build_input(label.numpy(), inst.numpy(), image.numpy(), 35))
+    ref = orc.generator_forward(sd, x, 3, 1)
+    (10.0 * (ref - image).abs().mean()).backward()
+    net = net.to(cuda).train()
+    y = net.forward_from_maps(label.to(cuda), inst.to(cuda), image.to(cuda), 35)
+    (10.0 * (y - image.to(cuda)).abs().mean()).backward()
+    err = (y.detach().cpu() - ref.detach()).abs()
+    assert float(err.mean()) <= 0.02 and orc.psnr(y.detach().cpu(), ref.detach()) >= 39.2
+    names = [n for n, _ in net.named_parameters() if n.endswith(".weight")]
+    for n in names[-2:]:  # head and last ConvTranspose: no chaotic depth behind them
+        c = _cos(dict(net.named_parameters())[n].grad.cpu(), sd[n].grad)
+        assert c >= 0.999, (n, c)
+    for n, p in net.named_parameters():
+        assert torch.isfinite(p.grad).all(), n
