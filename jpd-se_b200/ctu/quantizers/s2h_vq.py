@@ -36,6 +36,11 @@ class S2HVQ(nn.Module):
         self._sigma = new_sigma
 
     def _rows(self, x_mtrx):
+        if torch.is_grad_enabled() and (x_mtrx.requires_grad or self._code_book.requires_grad):
+            # the reference's soft quantisation is differentiable through autograd (s2h_vq.py:91-109); these kernels
+            # are forward-only, so refuse instead of silently cutting the graph (no caller in the reference trains it)
+            raise NotImplementedError('jpdse_b200 S2HVQ: forward-only kernels; call under torch.no_grad() '
+                                      '(or detach the input and freeze the code book)')
         return x_mtrx.detach().contiguous().float().view(-1, x_mtrx.size(-1))
 
     def _cb(self):

@@ -396,6 +396,16 @@ def test_s2hvq_golden_and_ties(cuda, golden_dir):
         assert np.array_equal(vq.decode(torch.from_numpy(g["vq_hard"]).to(cuda)).cpu().numpy(), g["vq_decoded"])
 
 
+def test_s2hvq_refuses_to_drop_gradients(cuda):
+    s2h = importlib.import_module("jpd-se_b200.ctu.quantizers.s2h_vq")
+    vq = s2h.S2HVQ(torch.randn(8, 4).to(cuda), sigma=2.0)
+    x = torch.randn(3, 8, device=cuda)
+    with pytest.raises(NotImplementedError):  # code book is a Parameter: the reference would backprop through softmax
+        vq.encode(x, 2, train=True, raw=True)
+    with torch.no_grad():
+        assert vq.encode(x, 2, train=True, raw=True).shape == (3, 2, 8)
+
+
 def test_s2hvq_random_floats_match_up_to_near_ties(cuda):
     ops = _ops()
     g = torch.Generator().manual_seed(12)
