@@ -602,6 +602,7 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
       g->out_w = g->gemm_w = d->in_w;
       g->cpt = d->cin / 64;
       g->ktot = (d->kind == JPDSE_CONV1X1 ? 1 : 9) * d->cin;
+      if (pair_conv_applicable(d)) g->path = kPathPair;  // same packed weights as the single-CTA kernel
       break;
     case JPDSE_CONV3X3_S2:
       if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv s2: cin must be a multiple of 64 (got %d)", d->cin);
@@ -855,6 +856,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     return fail(JPDSE_ERR_INVALID, "conv_forward: pointers must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (g.path == kPathConvtFused) return convt_fused_forward(d, x, w_packed, y, stats, stream);
+  if (g.path == kPathPair) return pair_conv_forward(d, x, w_packed, y, stats, stream);
   if (g.path != kPathIgemm) return rowconv_forward(d, g.path == kPathRowHead, x, w_packed, bias, y, stats, stream);
 
   IgemmParams p;

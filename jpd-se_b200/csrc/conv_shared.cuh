@@ -14,7 +14,8 @@ enum ConvPath {
   kPathIgemm = 0,    // generic per-tap implicit GEMM (conv_igemm.cu)
   kPathRowHead = 1,  // row-stationary 7x7, (kw,cout) polyphase columns, bias+tanh (conv_rowstat.cu)
   kPathRowStem = 2,  // row-stationary 7x7, window-K, 32-channel splits, raw+stats (conv_rowstat.cu)
-  kPathConvtFused = 3  // ConvTranspose with all four output phases per tile and halo-shared A boxes (conv_convt.cu)
+  kPathConvtFused = 3,  // ConvTranspose with all four output phases per tile and halo-shared A boxes (conv_convt.cu)
+  kPathPair = 4         // 3x3 stride-1 conv on a CTA pair, tcgen05 cta_group::2, 256 x 256 tiles (conv_pair.cu)
 };
 
 struct ConvGeom {
@@ -37,6 +38,10 @@ bool convt_fused_applicable(const jpdse_conv_desc* d);
 int convt_fused_pack(const jpdse_conv_desc* d, const float* w, void* w_packed, cudaStream_t stream);
 int convt_fused_forward(const jpdse_conv_desc* d, const void* x, const void* w_packed, void* y, double* stats,
                         cudaStream_t stream);
+
+bool pair_conv_applicable(const jpdse_conv_desc* d);
+int pair_conv_forward(const jpdse_conv_desc* d, const void* x, const void* w_packed, void* y, double* stats,
+                      cudaStream_t stream);
 
 int rowconv_forward(const jpdse_conv_desc* d, bool head, const void* x, const void* w_packed, const float* bias, void* y,
                     double* stats, cudaStream_t stream);

@@ -568,3 +568,31 @@ def test_split_stream_plan_equals_single_stream(cuda, monkeypatch):
         assert torch.equal(a, b)
         outs.append((a, c))
     assert all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][1], o[1]) for o in outs[1:])
+
+
+def test_cta_pair_conv_equals_single_cta_kernel(cuda, monkeypatch):
+    """The res-block conv runs on CTA pairs (tcgen05 cta_group::2, conv_pair.cu) when the problem is large enough; same
+    packed weights, same K order, fp32 accumulate -> bit-identical raw output and matching statistics vs conv_igemm.cu,
+    and within one bf16 ulp of torch."""
+    ops = _ops()
+    from jpdse_b200._lib import CONV3X3_PAD1, EPI_RAW_STATS
+    g = torch.Generator().manual_seed(5)
+    B, H, W, C = 10, 32, 64, 1024   # 160 m-tiles -> 80 pairs x 4 n-tiles = 320 pair tiles (>= 148: pair path), ragged waves
+    x = _bf(torch.randn(B, C, H, W, generator=g))
+    w = _bf(torch.randn(C, C, 3, 3, generator=g) * 0.02)
+    xd = ops.nchw_to_nhwc_bf16(x.to(cuda), pad_reflect=1)
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("JPDSE_PAIR_CONV", flag)
+        cv = ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, B, H, W, 1, C, C, C, cuda)
+        cv.pack(w.to(cuda))
+        y = torch.full((B, H, W, C), float("nan"), dtype=torch.bfloat16, device=cuda)
+        st = torch.zeros(B, C, 2, dtype=torch.float64, device=cuda)
+        cv.forward(xd, y, st)
+        torch.cuda.synchronize()
+        outs.append((y, st))
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.allclose(outs[0][1], outs[1][1], rtol=1e-6, atol=1e-3)
+    ref = F.conv2d(F.pad(x[:2], (1, 1, 1, 1), mode="reflect"), w)
+    got = outs[0][0][:2].float().cpu().permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -7

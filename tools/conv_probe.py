@@ -31,3 +31,18 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 print("%s B%d %dx%d %d->%d flags=%s: %.3f ms, %.1f TFLOP/s" % (kind, B, H, W, cin, cout, os.environ.get("JPDSE_DEBUG_FLAGS", "0"), ms, cv.flops / ms / 1e9))
+if os.environ.get("JPDSE_PROBE_CHECK") and kind == "conv3x3":
+    import torch.nn.functional as F
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    wt = torch.randn(cout, cin, 3, 3, device=dev) * 0.02
+    cv.pack(wt)
+    st.zero_()
+    cv.forward(x, y, st)
+    nb = min(B, 2)
+    ref = F.conv2d(x[:nb].float().permute(0, 3, 1, 2), wt.bfloat16().float())
+    got = y[:nb].float().permute(0, 3, 1, 2)
+    s1 = got.double().sum(dim=(2, 3))
+    print("check: max err %.4g (scale %.3g), stats rel err %.3g, digest %.6f" % (
+        float((got - ref).abs().max()), float(ref.abs().max()), float(((st[:nb, :, 0] - s1).abs() / (s1.abs() + 1)).max()),
+        float(y.float().abs().sum())))
