@@ -424,7 +424,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"kernel": "igemm_kernel<256> (ResnetBlock 3x3 conv 1024->1024)", "bound": "tensor",
+            "roofline": {"kernel": "pair_conv3x3_kernel (ResnetBlock 3x3 conv 1024->1024 on CTA pairs, tcgen05 cta_group::2)", "bound": "tensor",
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
                          "frac_of_burst_peak": achieved / burst, "peak_source": peak_kind + " (bf16_tflops_sustained)",
                          "launch_ms": res_ms, "flops_per_launch": res_flops, "images_per_launch": res_batch,
