@@ -283,8 +283,13 @@ bool pair_conv_applicable(const jpdse_conv_desc* d) {
   if (w <= 0 || (128 % w) || (d->in_w % w) || (d->in_h % (128 / w))) return false;
   const long long m_tiles = static_cast<long long>(d->batch) * (d->in_h / (128 / w)) * (d->in_w / w);
   if (m_tiles & 1) return false;
-  // worth it only when every pair of SMs gets work for several tiles and the k loop hides the epilogue
-  return m_tiles / 2 * (d->cout / 256) >= num_sms() && 9 * (d->cin / 64) >= 72;
+  // worth it only when the pairs of SMs get enough tiles and the k loop hides the epilogue
+  static int min_tiles = -1;
+  if (min_tiles < 0) {
+    const char* t = getenv("JPDSE_PAIR_MIN_TILES");
+    min_tiles = t ? atoi(t) : 96;  // measured: even with batch 3 (96 pair tiles on 74 SM pairs) against the single-CTA kernel, ahead from 4
+  }
+  return m_tiles / 2 * (d->cout / 256) >= min_tiles && 9 * (d->cin / 64) >= 72;
 }
 
 int pair_conv_forward(const jpdse_conv_desc* d, const void* x, const void* w_packed, void* y, double* stats,
