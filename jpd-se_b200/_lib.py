@@ -28,6 +28,9 @@ SIGNATURES = {
     "jpdse_last_error": (ctypes.c_char_p, []),
     "jpdse_build_input": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int,
                                   c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "jpdse_build_input_u8": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, ctypes.POINTER(c_float),
+                                     ctypes.POINTER(c_float), c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                     c_void_p, c_void_p]),
     "jpdse_conv_packed_weight_bytes": (c_size_t, [ctypes.POINTER(ConvDesc)]),
     "jpdse_conv_pack_weights": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p]),
     "jpdse_conv_forward": (c_int, [ctypes.POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -59,13 +59,25 @@ __device__ __forceinline__ bool load_edge(const void* inst, int dtype, size_t im
   }
 }
 
+// image pixel: float32 (already normalised) or uint8 with the loader's normalisation fused in --
+// ToTensor (x / 255) then Normalize ((x - mean) / std), float32, IEEE division (ctu/data/base_dataset.py transforms)
+struct ImgNorm {
+  int u8;
+  float mean[3], std[3];
+};
+__device__ __forceinline__ float load_px(const void* image, const ImgNorm& nm, size_t idx, int c) {
+  if (!nm.u8) return static_cast<const float*>(image)[idx];
+  const float v = static_cast<float>(static_cast<const uint8_t*>(image)[idx]);
+  return __fdiv_rn(__fsub_rn(__fdiv_rn(v, 255.0f), nm.mean[c]), nm.std[c]);
+}
+
 constexpr int kBuildThreads = 256;
 
 // One thread per padded output pixel; rows are staged in shared memory so the NHWC write is a
 // contiguous stream of 16-byte vectors.
 __global__ void __launch_bounds__(kBuildThreads)
 build_input_nhwc_kernel(const void* __restrict__ label, int label_dtype, const void* __restrict__ inst, int inst_dtype,
-                        const float* __restrict__ image, int B, int H, int W, int num_labels, int pad, int c_pad,
+                        const void* __restrict__ image, ImgNorm nm, int B, int H, int W, int num_labels, int pad, int c_pad,
                         __nv_bfloat16* __restrict__ out, int* __restrict__ bad) {
   extern __shared__ uint4 s_rows[];  // [kBuildThreads][c_pad/8]
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
@@ -85,8 +97,8 @@ build_input_nhwc_kernel(const void* __restrict__ label, int label_dtype, const v
       if (lab < 0 && bad != nullptr && ph >= pad && ph < H + pad && pw >= pad && pw < W + pad) atomicAdd(bad, 1);
       const float edge = load_edge(inst, inst_dtype, img_off, h, w, H, W) ? 1.f : 0.f;
       const size_t plane = static_cast<size_t>(H) * W;
-      const float* ip = image + static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(h) * W + w;
-      const float r = ip[0], g = ip[plane], bl = ip[2 * plane];
+      const size_t ip = static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(h) * W + w;
+      const float r = load_px(image, nm, ip, 0), g = load_px(image, nm, ip + plane, 1), bl = load_px(image, nm, ip + 2 * plane, 2);
       for (int v = 0; v < vpp; ++v) {
         uint32_t wds[4];
 #pragma unroll
@@ -121,7 +133,7 @@ build_input_nhwc_kernel(const void* __restrict__ label, int label_dtype, const v
 // Reference layout: float32 NCHW `input_concat` (B, num_labels + 4, H, W); thread per pixel, plane-coalesced.
 __global__ void __launch_bounds__(256)
 build_input_nchw_kernel(const void* __restrict__ label, int label_dtype, const void* __restrict__ inst, int inst_dtype,
-                        const float* __restrict__ image, int B, int H, int W, int num_labels, float* __restrict__ out,
+                        const void* __restrict__ image, ImgNorm nm, int B, int H, int W, int num_labels, float* __restrict__ out,
                         int* __restrict__ bad, int count_bad) {
   const size_t plane = static_cast<size_t>(H) * W;
   const size_t total = static_cast<size_t>(B) * plane;
@@ -137,10 +149,10 @@ build_input_nchw_kernel(const void* __restrict__ label, int label_dtype, const v
     float* o = out + static_cast<size_t>(b) * C * plane + hw;
     for (int ch = 0; ch < num_labels; ++ch) o[ch * plane] = (ch == lab) ? 1.f : 0.f;
     o[num_labels * plane] = edge;
-    const float* ip = image + static_cast<size_t>(b) * 3 * plane + hw;
-    o[(num_labels + 1) * plane] = ip[0];
-    o[(num_labels + 2) * plane] = ip[plane];
-    o[(num_labels + 3) * plane] = ip[2 * plane];
+    const size_t ip = static_cast<size_t>(b) * 3 * plane + hw;
+    o[(num_labels + 1) * plane] = load_px(image, nm, ip, 0);
+    o[(num_labels + 2) * plane] = load_px(image, nm, ip + plane, 1);
+    o[(num_labels + 3) * plane] = load_px(image, nm, ip + 2 * plane, 2);
   }
 }
 
@@ -408,9 +420,9 @@ static int grid_for(size_t work_items, int threads, int per_thread) {
 
 using namespace jpdse;
 
-extern "C" int jpdse_build_input(const void* label, int label_dtype, const void* instance, int inst_dtype,
-                                 const float* image, int batch, int height, int width, int num_labels, void* out_nhwc,
-                                 int pad, int c_pad, float* out_nchw, int* bad_label_count, void* stream_v) {
+static int build_input_impl(const void* label, int label_dtype, const void* instance, int inst_dtype, const void* image,
+                            const ImgNorm& nm, int batch, int height, int width, int num_labels, void* out_nhwc, int pad,
+                            int c_pad, float* out_nchw, int* bad_label_count, void* stream_v) {
   if (label == nullptr || instance == nullptr || image == nullptr) return fail(JPDSE_ERR_INVALID, "build_input: NULL input");
   if (batch <= 0 || height <= 1 || width <= 1 || num_labels <= 0) return fail(JPDSE_ERR_INVALID, "build_input: bad sizes");
   if (label_dtype < 0 || label_dtype > 2 || inst_dtype < 0 || inst_dtype > 3) return fail(JPDSE_ERR_INVALID, "build_input: bad dtype code");
@@ -424,7 +436,7 @@ extern "C" int jpdse_build_input(const void* label, int label_dtype, const void*
     const size_t smem = static_cast<size_t>(kBuildThreads) * c_pad * 2;
     if (smem > 48 * 1024) return fail(JPDSE_ERR_UNSUPPORTED, "build_input: c_pad too large");
     const int grid = grid_for(total, kBuildThreads, 1);
-    build_input_nhwc_kernel<<<grid, kBuildThreads, smem, stream>>>(label, label_dtype, instance, inst_dtype, image, batch,
+    build_input_nhwc_kernel<<<grid, kBuildThreads, smem, stream>>>(label, label_dtype, instance, inst_dtype, image, nm, batch,
                                                                    height, width, num_labels, pad, c_pad,
                                                                    static_cast<__nv_bfloat16*>(out_nhwc), bad_label_count);
     int rc = check_launch("build_input_nhwc_kernel");
@@ -433,12 +445,38 @@ extern "C" int jpdse_build_input(const void* label, int label_dtype, const void*
   if (out_nchw != nullptr) {
     const size_t total = static_cast<size_t>(batch) * height * width;
     const int grid = grid_for(total, 256, 1);
-    build_input_nchw_kernel<<<grid, 256, 0, stream>>>(label, label_dtype, instance, inst_dtype, image, batch, height, width,
+    build_input_nchw_kernel<<<grid, 256, 0, stream>>>(label, label_dtype, instance, inst_dtype, image, nm, batch, height, width,
                                                       num_labels, out_nchw, bad_label_count, out_nhwc == nullptr ? 1 : 0);
     int rc = check_launch("build_input_nchw_kernel");
     if (rc != JPDSE_OK) return rc;
   }
   return JPDSE_OK;
+}
+
+extern "C" int jpdse_build_input(const void* label, int label_dtype, const void* instance, int inst_dtype,
+                                 const float* image, int batch, int height, int width, int num_labels, void* out_nhwc,
+                                 int pad, int c_pad, float* out_nchw, int* bad_label_count, void* stream_v) {
+  ImgNorm nm;
+  nm.u8 = 0;
+  for (int c = 0; c < 3; ++c) nm.mean[c] = 0.f, nm.std[c] = 1.f;
+  return build_input_impl(label, label_dtype, instance, inst_dtype, image, nm, batch, height, width, num_labels, out_nhwc, pad,
+                          c_pad, out_nchw, bad_label_count, stream_v);
+}
+
+extern "C" int jpdse_build_input_u8(const void* label, int label_dtype, const void* instance, int inst_dtype,
+                                    const uint8_t* image_u8, const float* mean, const float* std, int batch, int height,
+                                    int width, int num_labels, void* out_nhwc, int pad, int c_pad, float* out_nchw,
+                                    int* bad_label_count, void* stream_v) {
+  if (mean == nullptr || std == nullptr) return fail(JPDSE_ERR_INVALID, "build_input_u8: NULL mean / std");
+  ImgNorm nm;
+  nm.u8 = 1;
+  for (int c = 0; c < 3; ++c) {
+    nm.mean[c] = mean[c];
+    nm.std[c] = std[c];
+    if (!(std[c] != 0.f)) return fail(JPDSE_ERR_INVALID, "build_input_u8: std must be non-zero");
+  }
+  return build_input_impl(label, label_dtype, instance, inst_dtype, image_u8, nm, batch, height, width, num_labels, out_nhwc,
+                          pad, c_pad, out_nchw, bad_label_count, stream_v);
 }
 
 extern "C" int jpdse_instnorm_apply(const void* raw, const double* stats, const void* residual, void* out, int batch,

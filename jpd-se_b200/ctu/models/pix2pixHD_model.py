@@ -232,8 +232,12 @@ class Pix2PixHDModel(nn.Module):
         if key not in x_dict:
             raise JpdseError("x_dict['compressed_img'] is required with --use_compressed: libbpg is outside this "
                              "path, supply the decoded image tensor")
-        image = x_dict[key].cuda(non_blocking=True).float().contiguous()
-        return self.netG.forward_from_maps(label, inst, image, self.num_labels)
+        image = x_dict[key].cuda(non_blocking=True)
+        if image.dtype != torch.uint8:  # uint8 = the compact loader format: normalised on the device (extension)
+            image = image.float()
+        return self.netG.forward_from_maps(label, inst, image.contiguous(), self.num_labels,
+                                           _opt(opt, 'normalize_mean', (0.5, 0.5, 0.5)),
+                                           _opt(opt, 'normalize_std', (1.0, 1.0, 1.0)))
 
     # ------------------------------------------------------------------ training (pix2pixHD_model.py:451-460, 709-771)
     def _fast_inputs(self, x_dict):

@@ -227,12 +227,14 @@ class GlobalGenerator(nn.Module):
         else:
             raise ValueError('Invalid generator mode: {}'.format(mode))
 
-    def forward_from_maps(self, label, instance, image, num_labels):
-        """Fused preprocess + generator: skips the (B,39,H,W) float tensor of pix2pixHD_model.py:595."""
+    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
+        """Fused preprocess + generator: skips the (B,39,H,W) float tensor of pix2pixHD_model.py:595. A uint8 `image`
+        (raw decoder output) is normalised with (x/255 - mean)/std inside the input-build kernel."""
         self._check_runnable(image)
         B, _, H, W = image.shape
         image = image.detach()
-        return self._run(B, H, W, image.device, lambda plan: plan.forward_from_maps(label, instance, image, num_labels))
+        return self._run(B, H, W, image.device,
+                         lambda plan: plan.forward_from_maps(label, instance, image, num_labels, mean, std))
 
 
 # ================================================================================================== training-only parts

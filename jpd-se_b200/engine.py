@@ -308,16 +308,18 @@ class GeneratorPlan:
             return self._graphed(("nchw",), [inp], self._eager_nchw)
         return self._eager_nchw(inp)
 
-    def forward_from_maps(self, label, instance, image, num_labels):
-        """Fused preprocessing path: label ids + instance ids + image -> generator output."""
+    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
+        """Fused preprocessing path: label ids + instance ids + image -> generator output. `image` is float32 (already
+        normalised) or uint8 (raw decoder output: (x/255 - mean)/std is applied inside the input-build kernel)."""
         if num_labels + 4 != self.input_nc:
             raise JpdseError("num_labels + 4 must equal input_nc")
 
         def eager(lab, ins, img):
-            ops.build_input(lab, ins, img, num_labels, pad=3, c_pad=self.c_in_pad, out_nhwc=self.x0)
+            ops.build_input(lab, ins, img, num_labels, pad=3, c_pad=self.c_in_pad, out_nhwc=self.x0, mean=mean, std=std)
             return self.forward_from_x0()
         if self.use_graph:
-            return self._graphed(("maps", label.dtype, instance.dtype, num_labels), [label, instance, image], eager)
+            key = ("maps", label.dtype, instance.dtype, image.dtype, num_labels, tuple(mean), tuple(std))
+            return self._graphed(key, [label, instance, image], eager)
         return eager(label, instance, image)
 
     # ---- backward
@@ -489,14 +491,15 @@ class SplitGeneratorPlan:
             raise JpdseError("plan built for %s, got %s" % ((self.B, self.input_nc, self.H, self.W), tuple(inp.shape)))
         return self._run(("nchw",), [inp], lambda p, x: p._eager_nchw(x))
 
-    def forward_from_maps(self, label, instance, image, num_labels):
+    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
         if num_labels + 4 != self.input_nc:
             raise JpdseError("num_labels + 4 must equal input_nc")
 
         def fn(p, lab, ins, img):
-            ops.build_input(lab, ins, img, num_labels, pad=3, c_pad=p.c_in_pad, out_nhwc=p.x0)
+            ops.build_input(lab, ins, img, num_labels, pad=3, c_pad=p.c_in_pad, out_nhwc=p.x0, mean=mean, std=std)
             return p.forward_from_x0()
-        return self._run(("maps", label.dtype, instance.dtype, num_labels), [label, instance, image], fn)
+        key = ("maps", label.dtype, instance.dtype, image.dtype, num_labels, tuple(mean), tuple(std))
+        return self._run(key, [label, instance, image], fn)
 
     def binary_code_nchw(self, inp):
         pb = self.B // len(self.parts)

@@ -66,7 +66,7 @@ def _count(n=1):
 
 # ------------------------------------------------------------------------------------------------ input build
 def build_input(label, instance, image, num_labels, pad=3, c_pad=None, nhwc=True, nchw=False, out_nhwc=None,
-                bad_count=None):
+                bad_count=None, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
     """One-hot + edge + concat (+reflect pad). See jpdse_build_input.
 
     Returns (nhwc_or_None, nchw_or_None). `nhwc` is bf16 (B, H+2pad, W+2pad, c_pad) carved from a flat
@@ -75,7 +75,9 @@ def build_input(label, instance, image, num_labels, pad=3, c_pad=None, nhwc=True
     lib = _lib.load()
     _need(label, "label")
     _need(instance, "instance")
-    _need(image, "image", torch.float32)
+    _need(image, "image")
+    if image.dtype not in (torch.float32, torch.uint8):
+        raise JpdseError("image must be float32 (normalised) or uint8 (raw; normalised on the device), got %s" % image.dtype)
     if label.dtype not in _LABEL_DTYPES:
         raise JpdseError("label dtype %s not supported (float32, uint8, int64)" % label.dtype)
     if instance.dtype not in _INST_DTYPES:
@@ -89,9 +91,15 @@ def build_input(label, instance, image, num_labels, pad=3, c_pad=None, nhwc=True
     if nhwc:
         o_nhwc = out_nhwc if out_nhwc is not None else alloc_nhwc(B, H + 2 * pad, W + 2 * pad, c_pad, image.device)
     o_nchw = torch.empty((B, num_labels + 4, H, W), dtype=torch.float32, device=image.device) if nchw else None
-    check(lib.jpdse_build_input(_ptr(label), _LABEL_DTYPES[label.dtype], _ptr(instance), _INST_DTYPES[instance.dtype],
-                                _ptr(image), B, H, W, num_labels, _ptr(o_nhwc), pad, c_pad, _ptr(o_nchw),
-                                _ptr(bad_count), _stream()))
+    if image.dtype == torch.uint8:
+        m3, s3 = (ctypes.c_float * 3)(*[float(v) for v in mean]), (ctypes.c_float * 3)(*[float(v) for v in std])
+        check(lib.jpdse_build_input_u8(_ptr(label), _LABEL_DTYPES[label.dtype], _ptr(instance), _INST_DTYPES[instance.dtype],
+                                       _ptr(image), m3, s3, B, H, W, num_labels, _ptr(o_nhwc), pad, c_pad, _ptr(o_nchw),
+                                       _ptr(bad_count), _stream()))
+    else:
+        check(lib.jpdse_build_input(_ptr(label), _LABEL_DTYPES[label.dtype], _ptr(instance), _INST_DTYPES[instance.dtype],
+                                    _ptr(image), B, H, W, num_labels, _ptr(o_nhwc), pad, c_pad, _ptr(o_nchw),
+                                    _ptr(bad_count), _stream()))
     _count(int(nhwc) + int(nchw))
     return o_nhwc, o_nchw
 

@@ -596,3 +596,35 @@ def test_cta_pair_conv_equals_single_cta_kernel(cuda, monkeypatch):
     ref = F.conv2d(F.pad(x[:2], (1, 1, 1, 1), mode="reflect"), w)
     got = outs[0][0][:2].float().cpu().permute(0, 3, 1, 2)
     assert float((got - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -7
+
+
+def test_compact_uint8_inputs_bit_exact_with_loader_normalisation(cuda):
+    """uint8 label / int16 instance / uint8 RGB go straight to the input-build kernel; the loader's
+    ToTensor + Normalize (x/255, then (x - mean)/std, float32) is fused in and must be bit-exact with torch's."""
+    import bench
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    B, H, W, L = 2, 33, 47, 35
+    lab = torch.randint(0, L, (B, 1, H, W), generator=g)
+    inst = torch.randint(0, 9, (B, 1, H, W), generator=g)
+    u8 = torch.randint(0, 256, (B, 3, H, W), generator=g, dtype=torch.uint8)
+    for mean, std in (((0.5, 0.5, 0.5), (1.0, 1.0, 1.0)), ((0.485, 0.456, 0.406), (0.229, 0.224, 0.225))):
+        m = torch.tensor(mean).view(1, 3, 1, 1)
+        s = torch.tensor(std).view(1, 3, 1, 1)
+        img = (u8.float().div(255) - m) / s  # torchvision ToTensor + Normalize
+        ref = orc.build_input(lab.numpy(), inst.numpy(), img.numpy(), L)
+        nhwc, nchw = ops.build_input(lab.to(torch.uint8).to(cuda), inst.to(torch.int16).to(cuda), u8.to(cuda), L, pad=3, nhwc=True,
+                                     nchw=True, mean=mean, std=std)
+        assert np.array_equal(nchw.cpu().numpy(), ref)
+        assert np.array_equal(nhwc.float().cpu().numpy(), _bf(torch.from_numpy(orc.reflect_pad_nhwc(ref, 3, 40))).numpy())
+    # and through the trainer API
+    trainers = importlib.import_module("jpd-se_b200.ctu.trainers")
+    opt = bench.make_opt()
+    opt.n_blocks_global = 1
+    torch.manual_seed(8)
+    trainer = trainers.get_trainer(opt)(opt, "test")
+    label, inst2, image = bench.synth_inputs(1, 128, 256, seed=2)
+    u = ((image + 0.5) * 255).round().clamp(0, 255).to(torch.uint8)
+    a = trainer.get_img({"label": label, "instance": inst2, "image": u.float().div(255) - 0.5})
+    b = trainer.get_img({"label": label.to(torch.uint8), "instance": inst2.to(torch.int16), "image": u})
+    assert torch.equal(a, b)
