@@ -226,6 +226,26 @@ def train_measure(args, dev, local, rank, world, barrier):
             "note": "generator forward/backward = jpdse_b200 kernels; netD, VGG (random weights offline), losses, Adam = PyTorch"}
 
 
+def cudnn_measure(B, H, W, dev):
+    """The existing Blackwell path for scale: the same GlobalGenerator architecture built from stock torch.nn modules
+    (ATen / cuDNN) on this GPU, bf16 autocast + channels_last, device-resident, CUDA-event timed. Not on our path."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("cudnn_baseline", os.path.join(ROOT, "tools", "cudnn_baseline.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    torch.manual_seed(1234)
+    net = mod.generator().to(dev).eval().to(memory_format=torch.channels_last)
+    x = torch.randn(B, 39, H, W, device=dev).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ms = mod.timed(lambda: net(x), 5)
+    del net, x
+    torch.cuda.empty_cache()
+    return {"value": B / ms * 1e3, "unit": "images/s", "ms_per_step": ms,
+            "what": "same architecture on stock torch.nn modules (ATen/cuDNN), bf16 autocast + channels_last, batch %d, "
+                    "device-resident, this GPU" % B}
+
+
 def workload_config(args):
     return {"workload": "pix2pixHD-BPG QF36 semantic-aware generator inference, batch %d at %dx%d, 35-class label map "
                         "+ instance edges + RGB, random-init weights" % (args.batch, args.width, args.height),
@@ -246,6 +266,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the (extra, non-headline) training-step measurement")
+    ap.add_argument("--no-cudnn-baseline", action="store_true",
+                    help="skip timing the same architecture on stock PyTorch/cuDNN on this GPU (extra, rank 0 at N=1)")
     ap.add_argument("--train-batch", type=int, default=2, help="images per GPU of the training-step measurement")
     ap.add_argument("--layers", action="store_true", help="print a per-kernel-type time breakdown to stderr")
     args = ap.parse_args()
@@ -435,6 +457,11 @@ def main():
                          "whole_forward_tflops": FWD_FLOPS_PER_IMAGE * scale * B / (ms_per_step * 1e-3) / 1e12}}
     if train is not None:
         line["train"] = train
+    if world == 1 and not args.no_cudnn_baseline:
+        try:
+            line["cudnn_baseline"] = cudnn_measure(B, H, W, dev)
+        except Exception as e:  # an extra: never let it take the bench line down
+            line["cudnn_baseline"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sec = cpu_reference_time(1, H, W, steps=8, warmup=1, weights={k: v.cpu() for k, v in netG.state_dict().items()})
