@@ -58,7 +58,7 @@ __device__ __forceinline__ int fold_sources(int i, int n, int pad, int (&q)[3]) 
 }
 
 template <bool kRelu, bool kSkip>
-__global__ void __launch_bounds__(kBwdThreads)
+__global__ void __launch_bounds__(kBwdThreads, 3)
 instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, const __nv_bfloat16* __restrict__ skip,
                                 const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
                                 __nv_bfloat16* __restrict__ dy, double* __restrict__ sums, int H, int W, int C, float eps, int iters) {
@@ -80,30 +80,40 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
   for (int pix0 = blockIdx.x * (ppi * iters); pix0 < npix; pix0 += gridDim.x * (ppi * iters))
+#pragma unroll 2
   for (int it = 0; it < iters; ++it) {
     const int pp = pix0 + it * ppi + psub;
     if (pp >= npix) break;
     const int h = pp / W, w = pp - h * W;
+    // all three streams are issued before anything is consumed; the extra reflect-fold sources (border pixels
+    // only) are the rare path
+    const size_t off = static_cast<size_t>(pp) * vpp + vec;
+    const uint4 xr = __ldg(raw4 + off);
+    uint4 sk = make_uint4(0, 0, 0, 0);
+    if (kSkip) sk = __ldg(skip4 + off);
     float acc[8];
+    unpack8(__ldg(g4 + (static_cast<size_t>(h + gpad) * Wg + (w + gpad)) * vpp + vec), acc);
+    if (gpad > 0) {
+      int qh[3], qw[3];
+      const int nh = fold_sources(h, H, gpad, qh), nw = fold_sources(w, W, gpad, qw);
+      if (nh * nw > 1) {
+        for (int a = 0; a < nh; ++a)
+          for (int c = (a == 0 ? 1 : 0); c < nw; ++c) {
+            float f[8];
+            unpack8(__ldg(g4 + (static_cast<size_t>(qh[a]) * Wg + qw[c]) * vpp + vec), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    int qh[3], qw[3];
-    const int nh = fold_sources(h, H, gpad, qh), nw = fold_sources(w, W, gpad, qw);
-    for (int a = 0; a < nh; ++a)
-      for (int c = 0; c < nw; ++c) {
-        float f[8];
-        unpack8(__ldg(g4 + (static_cast<size_t>(qh[a]) * Wg + qw[c]) * vpp + vec), f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          }
       }
+    }
     if (kSkip) {
       float f[8];
-      unpack8(__ldg(skip4 + static_cast<size_t>(pp) * vpp + vec), f);
+      unpack8(sk, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
     float x[8];
-    unpack8(__ldg(raw4 + static_cast<size_t>(pp) * vpp + vec), x);
+    unpack8(xr, x);
     uint32_t ow[4];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
@@ -148,7 +158,7 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
   }
 }
 
-__global__ void __launch_bounds__(kBwdThreads)
+__global__ void __launch_bounds__(kBwdThreads, 4)
 instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ raw,
                                const double* __restrict__ stats, const double* __restrict__ sums,
                                __nv_bfloat16* __restrict__ dx, int zpad, int H, int W, int C, float eps, int iters) {
