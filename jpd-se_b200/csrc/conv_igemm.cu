@@ -55,6 +55,9 @@ struct IgemmParams {
   // tile grid
   int batch, tiles_h, tiles_w, n_tiles;
   int tile_h, tile_w;  // tile_h * tile_w == 128
+  int gemm_h, gemm_w;  // pixel grid of the GEMM; with `partial` the last tile row / column hangs over its edge
+  int partial;         // 1: the grid is not a whole number of tiles (TMA zero-fills the loads and clips the stores;
+                       //    the epilogue masks the overhanging pixels out of the statistics and per-lane stores)
   // K loop
   int ntaps, chunks_per_tap;
   // A tensor-map addressing
@@ -336,6 +339,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         oh = ow / p.flat_pitch;
         ow -= oh * p.flat_pitch;
         valid = oh < p.out_h && ow < p.out_w;
+      } else if (p.partial) {
+        valid = th * p.tile_h + r < p.gemm_h && tw * p.tile_w + c < p.gemm_w;
       }
       const int n0 = nt * BN;
 
@@ -387,6 +392,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 rowp[(c2 * 4 + j) ^ (m & 7)] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+              if (p.partial && !valid) {  // the TMA store clips this pixel; keep it out of the sums too
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pk[j] = 0u;
+              }
               if (want_stats && !(p.dbg_flags & 1)) chunk_stats(pk, ch);
             }
             if (half == BN / 64 - 1) {  // accumulator fully read: hand it back before the store is even issued
@@ -459,7 +468,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int n = n0 + ch * 16 + j;
-              if (n < p.n_valid) {
+              if (n < p.n_valid && valid) {
                 float x = __uint_as_float(v[j]);
                 float y;
                 if (p.epilogue == JPDSE_EPI_BIAS_TANH_NCHW) {
@@ -662,16 +671,16 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
   return JPDSE_OK;
 }
 
-// M tiling: 128 pixels = tile_h rows x tile_w columns of the GEMM pixel grid.
-static int pick_tile(int gh, int gw, int* th, int* tw) {
-  int w = gw < 128 ? gw : 128;
-  if (w <= 0 || (128 % w) != 0 || (gw % w) != 0)
-    return fail(JPDSE_ERR_UNSUPPORTED, "conv: width %d cannot be tiled into 128-pixel tiles", gw);
-  int h = 128 / w;
-  if (gh % h) return fail(JPDSE_ERR_UNSUPPORTED, "conv: %dx%d pixel grid is not a multiple of the %dx%d tile", gh, gw, h, w);
-  *th = h;
+// M tiling: 128 pixels = tile_h rows x tile_w columns of the GEMM pixel grid; tile_w is 128 or, for narrower grids,
+// the next power of two. Grids that are not a whole number of tiles get overhanging edge tiles (IgemmParams::partial).
+static void pick_tile(int gw, int* th, int* tw) {
+  int w = 128;
+  if (gw < 128) {
+    w = 1;
+    while (w < gw) w <<= 1;
+  }
   *tw = w;
-  return JPDSE_OK;
+  *th = 128 / w;
 }
 
 static long long* g_dbg = nullptr;  // role counters of the LAST igemm launch when enabled (tools/role_times.py)
@@ -872,10 +881,12 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     p.tiles_h = 1;
     p.tiles_w = static_cast<int>((last + 127) / 128);
   } else {
-    rc = pick_tile(g.gemm_h, g.gemm_w, &p.tile_h, &p.tile_w);
-    if (rc != JPDSE_OK) return rc;
-    p.tiles_h = g.gemm_h / p.tile_h;
-    p.tiles_w = g.gemm_w / p.tile_w;
+    pick_tile(g.gemm_w, &p.tile_h, &p.tile_w);
+    p.tiles_h = (g.gemm_h + p.tile_h - 1) / p.tile_h;
+    p.tiles_w = (g.gemm_w + p.tile_w - 1) / p.tile_w;
+    p.gemm_h = g.gemm_h;
+    p.gemm_w = g.gemm_w;
+    p.partial = (g.gemm_h % p.tile_h || g.gemm_w % p.tile_w) ? 1 : 0;
   }
   p.n_tiles = g.rows / g.bn;
   p.chunks_per_tap = g.cpt;

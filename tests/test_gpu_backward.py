@@ -45,6 +45,7 @@ def _nhwc(t, pad=0, c_pad=None, mode="constant"):
     ("convt", 2, 8, 16, 128, 64), ("convt", 1, 32, 64, 256, 128), ("convt", 2, 8, 16, 1024, 512),
     ("stem", 2, 8, 16, 40, 64), ("stem", 1, 64, 128, 40, 64), ("stem", 2, 70, 96, 40, 64),
     ("head", 2, 8, 16, 64, 3), ("head", 1, 64, 128, 64, 3), ("head", 2, 70, 100, 64, 3),
+    ("conv3x3", 2, 6, 10, 64, 64), ("convs2", 2, 12, 40, 64, 128), ("convt", 1, 6, 10, 128, 64), ("conv3x3", 1, 9, 97, 128, 256),
 ])
 def test_conv_wgrad(cuda, case):
     ops = _ops()
@@ -105,7 +106,10 @@ def test_conv_wgrad(cuda, case):
                                   ("convs2", 2, 16, 32, 64, 128), ("convs2", 1, 32, 64, 256, 512),
                                   ("convs2", 1, 6, 256, 64, 128), ("convs2", 2, 10, 512, 128, 256),  # dgrad through the fused-phase ConvT kernel
                                   ("convt", 2, 8, 16, 128, 64), ("convt", 1, 16, 32, 512, 256),
-                                  ("head", 2, 8, 16, 64, 3), ("head", 1, 40, 72, 64, 3)])
+                                  ("head", 2, 8, 16, 64, 3), ("head", 1, 40, 72, 64, 3),
+                                  # pixel grids off the 128-pixel tile grid (overhanging edge tiles)
+                                  ("convs2", 2, 12, 40, 64, 128), ("convs2", 1, 6, 192, 64, 128),
+                                  ("convt", 1, 6, 10, 128, 64), ("convt", 2, 9, 68, 256, 128)])
 def test_conv_dgrad(cuda, case):
     """Gradient w.r.t. the conv input through the same implicit-GEMM kernel (role-swapped kinds)."""
     ops = _ops()
@@ -235,7 +239,7 @@ def _cos(a, b):
     return float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
 
 
-@pytest.mark.parametrize("n_down,n_blocks,B,H,W", [(2, 1, 2, 32, 64), (4, 2, 1, 128, 256)])
+@pytest.mark.parametrize("n_down,n_blocks,B,H,W", [(2, 1, 2, 32, 64), (4, 2, 1, 128, 256), (2, 1, 2, 36, 60)])
 def test_generator_gradients_vs_oracle(cuda, n_down, n_blocks, B, H, W):
     """d(loss)/d(every generator parameter) through the sm_100a backward vs CPU fp32 autograd of the oracle.
 

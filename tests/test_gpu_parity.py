@@ -143,12 +143,20 @@ def _conv_case(ops, cuda, kind_name, B, H, W, cin, cout, cin_real=None, seed=0):
     ("convt", 2, 5, 128, 128, 64), ("convt", 1, 9, 256, 256, 128), ("convt", 2, 3, 128, 64, 64),  # fused-phase kernel (W % 128 == 0, Cout <= 128)
     ("conv7x7", 2, 8, 16, 40, 64, 39), ("conv7x7", 1, 16, 128, 40, 64, 39),
     ("conv7x7", 2, 140, 256, 40, 64, 39),  # row-stationary stem path: 2 strips, a full and a ragged row chunk
+    # pixel grids that are not a whole number of 128-pixel tiles (overhanging edge tiles: TMA zero fill / clipped
+    # stores, masked statistics) -- any H, W the reference accepts
+    ("conv1x1", 1, 5, 7, 64, 64), ("conv3x3", 2, 6, 10, 64, 64), ("conv3x3", 1, 24, 48, 128, 256),
+    ("conv3x3", 1, 5, 192, 64, 128), ("conv3x3", 2, 3, 5, 1024, 1024),
+    ("convs2", 2, 12, 40, 64, 128), ("convs2", 1, 10, 400, 128, 256),
+    ("convt", 2, 6, 10, 128, 64), ("convt", 1, 7, 192, 256, 128), ("convt", 1, 3, 5, 1024, 512),
+    ("conv7x7", 2, 9, 20, 40, 64, 39), ("conv7x7", 1, 6, 200, 40, 64, 39),
 ])
 def test_conv_kinds(cuda, case):
     _conv_case(_ops(), cuda, *case, seed=len(case) + case[2])
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 64), (2, 16, 128), (2, 140, 256)])  # generic path / row path / ragged chunks
+@pytest.mark.parametrize("shape", [(2, 16, 64), (2, 16, 128), (2, 140, 256),  # generic path / row path / ragged chunks
+                                   (2, 9, 20), (1, 6, 100), (1, 5, 200)])       # overhanging tiles / ragged last strip
 def test_head_conv_bias_tanh(cuda, shape):
     ops = _ops()
     from jpdse_b200._lib import CONV7X7_PAD3, EPI_BIAS_TANH_NCHW
@@ -171,10 +179,11 @@ def test_conv_rejects_bad_arguments(cuda):
     from jpdse_b200._lib import CONV3X3_PAD1, EPI_RAW_STATS
     with pytest.raises(jpdse_b200.JpdseError):
         ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, 1, 8, 16, 1, 100, 100, 64, cuda)  # cin not a multiple of 64
-    cv = ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, 1, 6, 10, 1, 64, 64, 64, cuda)  # 6x10 cannot be tiled by 128 pixels
-    x = torch.zeros(1, 8, 12, 64, dtype=torch.bfloat16, device=cuda)
     with pytest.raises(jpdse_b200.JpdseError):
-        cv.forward(x, torch.zeros(1, 6, 10, 64, dtype=torch.bfloat16, device=cuda), torch.zeros(1, 64, 2, dtype=torch.float64, device=cuda))
+        ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, 1, 8, 16, 1, 64, 64, 96, cuda)   # raw+stats output not a multiple of the N tile
+    from jpdse_b200._lib import CONV3X3_S2
+    with pytest.raises(jpdse_b200.JpdseError):
+        ops.Conv(CONV3X3_S2, EPI_RAW_STATS, 1, 7, 16, 0, 64, 64, 64, cuda)     # odd height under a stride-2 conv
 
 
 # ------------------------------------------------------------------------------------------------ InstanceNorm apply
@@ -250,6 +259,24 @@ def test_generator_full_architecture(cuda):
     err = (y_maps - ref).abs()
     assert float(err.mean()) <= 0.02 and float(err.max()) <= 0.15 and orc.psnr(y_maps, ref) >= 39.2
     assert float(y_maps.abs().max()) < 1.0  # tanh range
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 48, 80), (1, 144, 272), (1, 96, 1552)])
+def test_generator_sizes_off_the_tile_grid(cuda, B, H, W):
+    """Image sizes the reference accepts (multiples of 16) whose pixel grids are not whole 128-pixel tiles at some or
+    all of the five resolutions: 3x5, 9x17 and 6x97 bottlenecks."""
+    nw = _networks()
+    torch.manual_seed(77)
+    net = nw.define_G(39, 3, 64, "global", 4, 2, 1, 3, "instance", gpu_ids=[]).eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    x = torch.randn(B, 39, H, W, generator=torch.Generator().manual_seed(H + W))
+    with torch.no_grad():
+        ref = orc.generator_forward(sd, x, 4, 2)
+        emu = orc.generator_forward(sd, x, 4, 2, round_fn=_bf)
+        y = net.to(cuda)(x.to(cuda)).cpu()
+    err = (y - ref).abs()
+    assert float(err.mean()) <= 0.02 and float(err.max()) <= 0.15 and orc.psnr(y, ref) >= 39.2
+    assert float((y - emu).abs().mean()) <= 0.008
 
 
 def test_generator_state_dict_round_trip_and_repack(cuda, tmp_path):
