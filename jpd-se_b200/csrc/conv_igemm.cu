@@ -838,12 +838,76 @@ extern "C" double jpdse_conv_flops(const jpdse_conv_desc* d) {
   return 2.0 * d->batch * static_cast<double>(g.gemm_h) * g.gemm_w * taps * d->cin_real * d->cout;
 }
 
+namespace jpdse {
+
+// Coalesced packers for the layouts that carry 98 % of the generator's weights (a training step re-packs every conv
+// after the optimizer step). The generic kernel above gathers one element per thread at a 36-byte (or, for the
+// data-gradient layout, 36 KiB) stride; these stage a tile in shared memory so both sides move in contiguous runs.
+// Same values bit for bit.
+//   3x3 forward layout  out[n][t][c] = w[n][c][t]                 (CONV3X3_PAD1, CONV3X3_S2)
+template <int kChunk>
+__global__ void __launch_bounds__(kChunk / 2)
+pack3x3_fwd_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cin) {
+  __shared__ __align__(16) float s[kChunk * 9];
+  const int n = blockIdx.x, c0 = blockIdx.y * kChunk;
+  const float4* src = reinterpret_cast<const float4*>(w + (static_cast<size_t>(n) * cin + c0) * 9);
+  for (int i = threadIdx.x; i < kChunk * 9 / 4; i += kChunk / 2) reinterpret_cast<float4*>(s)[i] = __ldg(src + i);
+  __syncthreads();
+  const int c = 2 * threadIdx.x;
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(s[c * 9 + t], s[(c + 1) * 9 + t]);
+    *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(n) * 9 + t) * cin + c0 + c) = h;
+  }
+}
+
+//   3x3 data-gradient layout  out[n][t'][c] = w[c][n][8 - t']     (CONV3X3_FULL: n = forward ci, c = forward co)
+__global__ void __launch_bounds__(256)
+pack3x3_full_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int cdim, int ndim) {
+  constexpr int kRow = 16 * 9 + 1;
+  __shared__ float s[64 * kRow];
+  const int n0 = blockIdx.x * 16, c0 = blockIdx.y * 64;
+  for (int i = threadIdx.x; i < 64 * 36; i += 256) {
+    const int c = i / 36, v = i - c * 36;
+    const float4 f = __ldg(reinterpret_cast<const float4*>(w + (static_cast<size_t>(c0 + c) * ndim + n0) * 9) + v);
+    float* dst = s + c * kRow + v * 4;
+    dst[0] = f.x; dst[1] = f.y; dst[2] = f.z; dst[3] = f.w;
+  }
+  __syncthreads();
+  const int pair = threadIdx.x & 31;
+  for (int r = threadIdx.x >> 5; r < 16 * 9; r += 8) {
+    const int nn = r / 9, t = r - nn * 9;
+    const int k = nn * 9 + 8 - t;
+    const __nv_bfloat162 h = __floats2bfloat162_rn(s[(2 * pair) * kRow + k], s[(2 * pair + 1) * kRow + k]);
+    *reinterpret_cast<__nv_bfloat162*>(out + (static_cast<size_t>(n0 + nn) * 9 + t) * cdim + c0 + 2 * pair) = h;
+  }
+}
+
+}  // namespace jpdse
+
 extern "C" int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w, void* w_packed, void* stream) {
   ConvGeom g;
   int rc = conv_geom(d, &g);
   if (rc != JPDSE_OK) return rc;
   if (w == nullptr || w_packed == nullptr) return fail(JPDSE_ERR_INVALID, "pack_weights: NULL pointer");
   if (g.path == kPathConvtFused) return convt_fused_pack(d, w, w_packed, static_cast<cudaStream_t>(stream));
+  {
+    const char* e = getenv("JPDSE_GENERIC_PACK");  // tests: force the generic gather kernel
+    const bool fast = !(e && e[0] == '1') && g.path != kPathRowHead && g.path != kPathRowStem && d->cin_real == d->cin &&
+                      g.rows == d->cout && d->cin % 64 == 0 && d->cout % 16 == 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (fast && (d->kind == JPDSE_CONV3X3_PAD1 || d->kind == JPDSE_CONV3X3_S2)) {
+      if (d->cin % 256 == 0)
+        pack3x3_fwd_kernel<256><<<dim3(d->cout, d->cin / 256), 128, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_packed), d->cin);
+      else
+        pack3x3_fwd_kernel<64><<<dim3(d->cout, d->cin / 64), 32, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_packed), d->cin);
+      return check_launch("pack3x3_fwd_kernel");
+    }
+    if (fast && d->kind == JPDSE_CONV3X3_FULL) {
+      pack3x3_full_kernel<<<dim3(d->cout / 16, d->cin / 64), 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_packed), d->cin, d->cout);
+      return check_launch("pack3x3_full_kernel");
+    }
+  }
   PackParams q{d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt, g.path};
   const size_t total = static_cast<size_t>(g.rows) * g.ktot;
   int blocks = static_cast<int>((total + 255) / 256);

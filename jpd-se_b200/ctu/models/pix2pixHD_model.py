@@ -127,6 +127,10 @@ class Pix2PixHDModel(nn.Module):
     def create_optimizers(self, opt):
         # pix2pixHD_model.py:247-281: two Adams, same lr / betas
         kw = dict(lr=_opt(opt, 'lr', 0.0002), betas=(_opt(opt, 'beta1', 0.5), _opt(opt, 'beta2', 0.999)))
+        # same update rule; the multi-tensor "fused" implementation makes one pass over the 730 MB of generator
+        # parameters and moments instead of one pass per elementary operation (2.7 -> ~1 ms a step)
+        if self.use_gpu() and os.environ.get('JPDSE_NO_FUSED_ADAM', '0') != '1':
+            kw['fused'] = True
         return torch.optim.Adam(list(self.netG.parameters()), **kw), torch.optim.Adam(list(self.netD.parameters()), **kw)
 
     def use_gpu(self):

@@ -173,6 +173,28 @@ def test_head_conv_bias_tanh(cuda, shape):
     assert float((y.cpu() - ref).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("kind_name,cin,cout", [("pad1", 64, 64), ("pad1", 1024, 1024), ("pad1", 128, 256), ("s2", 64, 128),
+                                                ("s2", 512, 1024), ("full", 64, 64), ("full", 1024, 1024), ("full", 256, 128)])
+def test_coalesced_weight_packers_equal_generic_gather(cuda, monkeypatch, kind_name, cin, cout):
+    """The shared-memory-staged packers of the 3x3 layouts write the same bytes as the one-element-per-thread kernel."""
+    ops = _ops()
+    from jpdse_b200._lib import CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, EPI_RAW, EPI_RAW_STATS
+    kind, pad, epi = {"pad1": (CONV3X3_PAD1, 1, EPI_RAW_STATS), "s2": (CONV3X3_S2, 0, EPI_RAW_STATS),
+                      "full": (CONV3X3_FULL, 2, EPI_RAW)}[kind_name]
+    shape = (cin, cout, 3, 3) if kind_name == "full" else (cout, cin, 3, 3)
+    w = torch.randn(shape, generator=torch.Generator().manual_seed(cin + cout)).to(cuda)
+    cv = ops.Conv(kind, epi, 1, 16, 32, pad, cin, cin, cout, cuda)
+    cv.w_packed.fill_(float("nan"))
+    cv.pack(w)
+    fast = cv.w_packed.clone()
+    monkeypatch.setenv("JPDSE_GENERIC_PACK", "1")
+    cv.w_packed.fill_(float("nan"))
+    cv.pack(w)
+    torch.cuda.synchronize()
+    assert not torch.isnan(fast.float()).any()
+    assert torch.equal(fast.view(torch.int16), cv.w_packed.view(torch.int16))
+
+
 def test_conv_rejects_bad_arguments(cuda):
     import jpdse_b200
     ops = _ops()
