@@ -32,4 +32,18 @@ inline int num_sms() {
   return n;
 }
 
+// One-time per-DEVICE setup (cudaFuncSetAttribute applies to the current device only). The design is one process
+// per GPU, but a process that touches several devices must not inherit "already configured" from the first.
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  int dev = 0;
+  bool first_use() {
+    cudaGetDevice(&dev);
+    return dev < 0 || dev >= 64 || !((mask >> dev) & 1ull);
+  }
+  void done() {
+    if (dev >= 0 && dev < 64) mask |= 1ull << dev;
+  }
+};
+
 }  // namespace jpdse

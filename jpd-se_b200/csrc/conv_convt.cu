@@ -358,11 +358,11 @@ int convt_fused_forward(const jpdse_conv_desc* d, const void* x, const void* w_p
     int rc = make_tmap_bf16(&tc, y, 5, dims, strides, box);
     if (rc != JPDSE_OK) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // the attribute is per device: set it on each device this process uses
+  if (configured.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(convt_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemBytes);
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "cudaFuncSetAttribute(convt smem=%d): %s", kCtSmemBytes, cudaGetErrorString(e));
-    configured = true;
+    configured.done();
   }
   const long long total = static_cast<long long>(p.batch) * p.n_blocks * p.height * p.tiles_w;
   int grid = num_sms();

@@ -690,11 +690,11 @@ template <int BN, int STG>
 static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const IgemmParams& p,
                         cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, STG>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // the attribute is per device: set it on each device this process uses
+  if (configured.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_kernel<BN, STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
-    configured = true;
+    configured.done();
   }
   const int total = p.batch * p.tiles_h * p.tiles_w * p.n_tiles;
   int grid = num_sms();

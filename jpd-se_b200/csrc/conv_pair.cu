@@ -326,11 +326,11 @@ int pair_conv_forward(const jpdse_conv_desc* d, const void* x, const void* w_pac
     int rc = make_tmap_bf16(&tb, w_packed, 2, dims, strides, box);
     if (rc != JPDSE_OK) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // the attribute is per device: set it on each device this process uses
+  if (configured.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(pair_conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPrSmemBytes);
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "cudaFuncSetAttribute(pair smem=%d): %s", kPrSmemBytes, cudaGetErrorString(e));
-    configured = true;
+    configured.done();
   }
   int grid = num_sms() & ~1;
   const long long total = static_cast<long long>(p.batch) * p.tiles_h * p.tiles_w / 2 * p.n_tiles;

@@ -329,11 +329,11 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 template <int KB, bool kHead>
 static int launch_rowconv(const CUtensorMap& ta, const CUtensorMap& tb, const RowConvParams& p, cudaStream_t stream) {
   using Cfg = RowCfg<KB, kHead>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // the attribute is per device: set it on each device this process uses
+  if (configured.first_use()) {
     cudaError_t e = cudaFuncSetAttribute(rowconv_kernel<KB, kHead>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "cudaFuncSetAttribute(rowconv smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
-    configured = true;
+    configured.done();
   }
   const int items = p.batch * p.strips * p.chunks;
   int grid = num_sms();

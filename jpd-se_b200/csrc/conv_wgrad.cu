@@ -612,11 +612,11 @@ extern "C" int jpdse_conv_wgrad(const jpdse_conv_desc* d, const void* x, const v
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "conv_wgrad: memset failed: %s", cudaGetErrorString(e));
   }
   w.p.ws = static_cast<float*>(workspace);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // the attribute is per device: set it on each device this process uses
+  if (configured.first_use()) {
     e = cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "cudaFuncSetAttribute(wgrad smem=%d): %s", kWgSmemBytes, cudaGetErrorString(e));
-    configured = true;
+    configured.done();
   }
   const int items = w.p.n_groups * w.p.m_tiles * w.p.n_tiles * w.p.splits;
   int grid = num_sms();

@@ -677,3 +677,20 @@ def test_compact_uint8_inputs_bit_exact_with_loader_normalisation(cuda):
     a = trainer.get_img({"label": label, "instance": inst2, "image": u.float().div(255) - 0.5})
     b = trainer.get_img({"label": label.to(torch.uint8), "instance": inst2.to(torch.int16), "image": u})
     assert torch.equal(a, b)
+
+
+def test_second_device_in_the_same_process(cuda):
+    """One process per GPU is the design, but a process that moves to another device (`--gpu_ids 1` after a first call
+    on device 0) must work: the kernels' shared-memory attributes are set per device."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nw = _networks()
+    torch.manual_seed(3)
+    net = nw.define_G(39, 3, 64, "global", 2, 1, 1, 3, "instance", gpu_ids=[]).eval()
+    x = torch.randn(1, 39, 32, 64, generator=torch.Generator().manual_seed(1))
+    outs = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev), torch.no_grad():
+            import copy
+            outs.append(copy.deepcopy(net).to("cuda:%d" % dev)(x.to("cuda:%d" % dev)).cpu())
+    assert torch.equal(outs[0], outs[1])
