@@ -50,6 +50,8 @@ struct ConvtParams {
   int cout;
   int want_stats;
   double* stats;
+  int dbg_flags;  // developer experiments (JPDSE_DEBUG_FLAGS, as in conv_igemm.cu): 1 skip statistics | 2 skip the TMA
+                  // stores | 8 hand the accumulator straight back | 16 skip the MMAs | 32 skip the weight loads
 };
 
 __global__ void __launch_bounds__(kCtThreads, 1)
@@ -112,9 +114,9 @@ convt_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           for (int khi = 0; khi < 3; ++khi) {  // filter rows in the order kh = 1, 2 (input row i), 0 (input row i+1)
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * kCtStageBytes;
-            mbar_arrive_expect_tx(&full_bar[stage], kCtABox + kCtBBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], (p.dbg_flags & 32) ? kCtABox : kCtABox + kCtBBytes);
             tma_load_4d(&tm_a, &full_bar[stage], sa, c * 64, tw * 128, i + (khi == 2 ? 1 : 0), b);
-            tma_load_2d(&tm_b, &full_bar[stage], sa + kCtABytes, c * 64, (nblk * 3 + khi) * 192);
+            if (!(p.dbg_flags & 32)) tma_load_2d(&tm_b, &full_bar[stage], sa + kCtABytes, c * 64, (nblk * 3 + khi) * 192);
             if (++stage == kCtStages) {
               stage = 0;
               phase ^= 1;
@@ -147,11 +149,13 @@ convt_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
           const uint64_t a1 = umma_smem_desc_sw128(sa + 128);              // pixels j+1 .. j+128
           const uint64_t b01 = umma_smem_desc_sw128(sa + kCtABytes);       // [W(kh,1) | W(kh,2)]
           const uint64_t b2 = umma_smem_desc_sw128(sa + kCtABytes + 128 * 128);  // W(kh,0)
+          if (!(p.dbg_flags & 16)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            umma_bf16<1>(d_ph, a0 + static_cast<uint64_t>(k * 2), b01 + static_cast<uint64_t>(k * 2), idesc_wide,
-                         (first && k == 0) ? 0u : 1u);
-            umma_bf16<1>(d_ph + 64, a1 + static_cast<uint64_t>(k * 2), b2 + static_cast<uint64_t>(k * 2), idesc_narrow, 1u);
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16<1>(d_ph, a0 + static_cast<uint64_t>(k * 2), b01 + static_cast<uint64_t>(k * 2), idesc_wide,
+                           (first && k == 0) ? 0u : 1u);
+              umma_bf16<1>(d_ph + 64, a1 + static_cast<uint64_t>(k * 2), b2 + static_cast<uint64_t>(k * 2), idesc_narrow, 1u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (s == kstages - 1) umma_commit(&tfull_bar[acc]);
@@ -235,6 +239,13 @@ convt_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         cur_n0 = n0;
       }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
+      if (p.dbg_flags & 8) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc_phase ^= 1;
+        continue;
+      }
 #pragma unroll
       for (int sub = 0; sub < 4; ++sub) {  // sub-tile = (row phase, column phase), 64 columns each
         uint8_t* buf = s_out + (group * 2 + (out_buf & 1)) * (128 * 128);
@@ -255,7 +266,7 @@ convt_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             rowp[(c2 * 4 + j) ^ (m & 7)] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          if (p.want_stats) chunk_stats(pk, c2);
+          if (p.want_stats && !(p.dbg_flags & 1)) chunk_stats(pk, c2);
         }
         if (sub == 3) {
           tc_fence_before();
@@ -264,7 +275,7 @@ convt_fused_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_consta
         }
         fence_proxy_async_smem();
         named_bar_sync(1 + group, 128);
-        if (issuer) {
+        if (issuer && !(p.dbg_flags & 2)) {
           // output view {2*Cout (column phase major), W, 2 (row phase), H, B}
           tma_store_5d(&tm_c, buf, (sub & 1) * p.cout + n0, tw * 128, sub >> 1, i, b);
           tma_store_commit();
@@ -332,6 +343,14 @@ int convt_fused_forward(const jpdse_conv_desc* d, const void* x, const void* w_p
   p.cout = d->cout;
   p.want_stats = d->epilogue == JPDSE_EPI_RAW_STATS ? 1 : 0;
   p.stats = stats;
+  {
+    static int flags = -1;
+    if (flags < 0) {
+      const char* e = getenv("JPDSE_DEBUG_FLAGS");
+      flags = e ? atoi(e) : 0;
+    }
+    p.dbg_flags = flags;
+  }
   const uint64_t C = d->cin, Co = d->cout, H = d->in_h, W = d->in_w, B = d->batch;
   const uint64_t Hp = H + 2 * static_cast<uint64_t>(d->in_pad), Wp = W + 2 * static_cast<uint64_t>(d->in_pad);
   const uint8_t* xin = static_cast<const uint8_t*>(x) + (static_cast<uint64_t>(d->in_pad) * Wp + d->in_pad) * C * 2;
