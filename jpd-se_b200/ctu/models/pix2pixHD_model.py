@@ -33,8 +33,57 @@ def _opt(opt, name, default):
     return getattr(opt, name, default)
 
 
+# The model's command-line surface (pix2pixHD_model.py:22-101): (flag, type or None for store_true, default, choices).
+# Every flag of the reference is accepted so its scripts parse unchanged; the ones outside the accelerated path are
+# rejected in __init__ with NotImplementedError, not silently ignored.
+_FLAGS = (
+    # architecture
+    ('num_D', int, 2, None), ('n_layers_D', int, 3, None), ('ndf', int, 64, None), ('no_lsgan', None, False, None),
+    ('pool_size', int, 0, None), ('no_instance', None, False, None), ('no_label', None, False, None),
+    ('sem_masking', None, False, None), ('binary_mask', None, False, None), ('netE_groups', int, 1, None),
+    ('inst_wise_pool', None, False, None), ('norm', str, 'instance', None), ('use_dropout', None, False, None),
+    # objective
+    ('lambda_feat', float, 10.0, None), ('lambda_distortion', float, 10.0, None), ('anneal_lambda', None, False, None),
+    ('anneal_interval', int, 5000, None), ('anneal_factor', float, 5., None), ('match_raw_feat', None, False, None),
+    ('no_gan_feat_loss', None, False, None), ('no_vgg_loss', None, False, None), ('no_distortion_loss', None, False, None),
+    ('no_g_gan_loss', None, False, None), ('no_d_gan_loss', None, False, None),
+    # data I/O
+    ('data_type', int, 32, [8, 16, 32]), ('fp16', None, False, None), ('local_rank', int, 0, None), ('input_nc', int, 3, None),
+    ('use_compressed', None, False, None), ('ext', str, 'jpg', ['jpg', 'j2k', 'bpg', 'webp']), ('quality', str, '100', None),
+    ('zero_sem', None, False, None), ('zero_ins', None, False, None), ('zero_vis', None, False, None),
+    # model I/O
+    ('checkpoints_dir', str, None, None),
+    # generator
+    ('netG', str, 'global', None), ('ngf', int, 64, None), ('n_downsample_global', int, 4, None),
+    ('n_blocks_global', int, 9, None), ('n_blocks_local', int, 3, None), ('n_local_enhancers', int, 1, None),
+    ('niter_fix_global', int, 0, None),
+    # feature / label encoders (outside the accelerated path)
+    ('no_feat_encoding', None, False, None), ('no_feat', None, False, None), ('feat_num', int, 3, None),
+    ('n_downsample_E', int, 4, None), ('nef', int, 64, None), ('use_netE_output', None, False, None),
+    ('no_label_encoding', None, False, None), ('label_encoder_out_channels', int, 36, None),
+    ('n_downsample_E4label', int, 4, None), ('ne4lf', int, 64, None),
+    ('no_encoder_binarization', None, False, None), ('encoder_binarizer_out_channels', int, 128, None),
+    ('no_label_encoder_binarization', None, False, None), ('label_encoder_binarizer_out_channels', int, 128, None),
+    # generator binarisation
+    ('no_generator_binarization', None, False, None), ('bin_generator_before_res', None, False, None),
+    ('generator_binarizer_out_channels', int, 128, None),
+)
+
+
 class Pix2PixHDModel(nn.Module):
     loss_names = ('G_GAN', 'G_GAN_Feat', 'G_VGG', 'G_Distortion', 'D_real', 'D_fake')  # pix2pixHD_model.py:213
+
+    @staticmethod
+    def modify_commandline_options(parser, train):
+        """pix2pixHD_model.py:22-101: same flags, types, defaults and choices (pinned by tests/golden/model_options.json)."""
+        for name, typ, default, choices in _FLAGS:
+            if typ is None:
+                parser.add_argument('--' + name, action='store_true', default=default)
+            elif choices is not None:
+                parser.add_argument('--' + name, type=typ, default=default, choices=choices)
+            else:
+                parser.add_argument('--' + name, type=typ, default=default)
+        return parser
 
     def __init__(self, opt):
         super(Pix2PixHDModel, self).__init__()

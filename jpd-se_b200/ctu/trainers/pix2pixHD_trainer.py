@@ -36,6 +36,11 @@ class BaseTrainer(nn.Module):
     def load(self):
         pass
 
+    def log_loss_values(self, loss_dict):
+        # base_trainer.py:80-88 writes tensorflow summaries; train.py:121-123 only calls it under --tf_log, which the
+        # constructor above already refuses
+        raise NotImplementedError('jpdse_b200: log_loss_values needs --tf_log (tensorflow summaries), outside the accelerated path')
+
 
 class Pix2PixHDTrainer(BaseTrainer):
     def __init__(self, opt, mode='train'):

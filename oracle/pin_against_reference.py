@@ -189,6 +189,20 @@ def main():
     assert qorc.rounded_identity(np.array([1.5, 1.4, 1.6], dtype=np.float32)).tolist() == [2.0, 1.0, 2.0]
     print("quantisers: oracle == reference (bit-exact); golden written")
 
+    # ---------------------------------------------------------------- command-line surface of the model plugin
+    # (ctu/models/pix2pixHD_model.py:22-101, reached through ctu.models.get_option_setter from base_parser.py:142-144)
+    import argparse
+    import json
+    table = {}
+    for is_train in (True, False):
+        ap = p2p.Pix2PixHDModel.modify_commandline_options(argparse.ArgumentParser(), is_train)
+        table["train" if is_train else "test"] = sorted(
+            [a.dest, type(a).__name__, None if a.type is None else a.type.__name__, a.default,
+             None if a.choices is None else list(a.choices)] for a in ap._actions if a.dest != "help")
+    with open(os.path.join(GOLDEN, "model_options.json"), "w") as f:
+        json.dump(table, f, indent=0, sort_keys=True)
+    print("model options: %d flags; golden written" % len(table["train"]))
+
 
 if __name__ == "__main__":
     main()

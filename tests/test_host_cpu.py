@@ -125,3 +125,28 @@ def test_s2hvq_mirror_argument_errors():
         vq.encode(torch.zeros(3, 8), code_len=2)  # center size 4 != code book's 2
     with pytest.raises(AssertionError):
         s2h.S2HVQ(torch.zeros(4, 2), sigma=0.0)
+
+
+def test_model_lookup_and_option_setter_match_the_reference_table(golden_dir):
+    """ctu/models/__init__.py:10-43 + pix2pixHD_model.py:22-101: `--model pix2pixHD` resolves to our class, and its
+    static option setter declares exactly the reference's flags (dest, action, type, default, choices) -- the table in
+    tests/golden/model_options.json was dumped from the reference by oracle/pin_against_reference.py."""
+    import json
+    models = importlib.import_module("jpd-se_b200.ctu.models")
+    cls = models.find_model_using_name("pix2pixHD")
+    assert cls.__name__ == "Pix2PixHDModel" and issubclass(cls, torch.nn.Module)
+    assert models.get_option_setter("pix2pixHD") is cls.modify_commandline_options
+    with pytest.raises(ModuleNotFoundError):
+        models.find_model_using_name("toderici2017")
+    golden = json.load(open(os.path.join(golden_dir, "model_options.json")))
+    for mode, is_train in (("train", True), ("test", False)):
+        ap = cls.modify_commandline_options(argparse.ArgumentParser(), is_train)
+        ours = sorted([a.dest, type(a).__name__, None if a.type is None else a.type.__name__, a.default,
+                       None if a.choices is None else list(a.choices)] for a in ap._actions if a.dest != "help")
+        assert ours == golden[mode]
+    # the shipped training script's model flags (scripts/pix2pixHD_bpg_train.sh) parse
+    ap = cls.modify_commandline_options(argparse.ArgumentParser(), True)
+    ns, rest = ap.parse_known_args("--no_label_encoding --no_feat_encoding --no_generator_binarization --use_compressed "
+                                   "--quality 36 --ext bpg --checkpoints_dir ckpt --no_vgg_loss --dataset cityscapes".split())
+    assert ns.no_label_encoding and ns.no_generator_binarization and ns.ext == "bpg" and ns.quality == "36"
+    assert rest == ["--dataset", "cityscapes"] and ns.n_downsample_global == 4 and ns.n_blocks_global == 9
