@@ -20,3 +20,12 @@ def test_oracle_is_bit_identical_to_reference(tmp_path):
     assert "preprocess: oracle == reference" in r.stdout
     assert "generator: oracle == reference" in r.stdout
     assert "quantisers: oracle == reference" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "ctu")), reason="reference tree not mounted here")
+def test_install_into_reference_builds_our_generator_behind_the_reference_trainer():
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "reference_install_check.py"), REF, ROOT], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "loaded the reference checkpoint" in r.stdout
