@@ -20,6 +20,7 @@
 // warp 8 TMA producer, warp 9 TMEM owner + MMA issuer.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -46,6 +47,9 @@ struct RowConvParams {
   void* out;
   double* stats;
   const float* bias;
+  int mc;         // 1: the two channel-split CTAs of a strip form a cluster and share every A box by TMA multicast
+  int dbg_flags;  // developer experiments (JPDSE_DEBUG_FLAGS, as in conv_igemm.cu): 1 skip statistics | 2 skip the output
+                  // stores | 8 hand the accumulator straight back | 16 skip the MMAs
 };
 
 template <int KB, bool kHead>
@@ -56,7 +60,7 @@ struct RowCfg {
   static constexpr int kSmemBytes = 1024 + kBBytes + kStages * kRowATile + kScratchFloats * 4 + 512;
 };
 
-template <int KB, bool kHead>
+template <int KB, bool kHead, bool kMc>
 __global__ void __launch_bounds__(kRowThreads, 1)
 rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                const __grid_constant__ RowConvParams p) {
@@ -83,7 +87,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     tma_prefetch_desc(&tm_b);
     for (int i = 0; i < Cfg::kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], kMc ? 2 : 1);  // multicast: a slot is free once BOTH CTAs' MMAs have read it
     }
     for (int i = 0; i < kRowSlots; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -98,6 +102,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (kMc) cluster_sync_all();  // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -115,6 +120,7 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         tma_load_2d(&tm_b, bfull_bar, s_b + kb * 7 * kRowBTile, 0, (split * KB + kb) * 7 * kRowN);
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t it = 0;  // running A box number
       for (int item = cta; item < items; item += ctas) {
         const int chunk = item % p.chunks;
         const int strip = (item / p.chunks) % p.strips;
@@ -130,10 +136,13 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int i = 0; i < rows + 6; ++i) {
           if (split == 0 && i + kAhead < rows + 6)
             for (int kb = 0; kb < KB; ++kb) tma_prefetch_4d(&tm_a, kb * 64, iw0, r0 + i + kAhead, b);
-          for (int kb = 0; kb < KB; ++kb) {
+          for (int kb = 0; kb < KB; ++kb, ++it) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], kRowATile);
-            tma_load_4d(&tm_a, &full_bar[stage], s_a + stage * kRowATile, kb * 64, iw0, r0 + i, b);
+            if (!kMc)
+              tma_load_4d(&tm_a, &full_bar[stage], s_a + stage * kRowATile, kb * 64, iw0, r0 + i, b);
+            else if ((it & 1u) == static_cast<uint32_t>(split))  // the pair walks the same boxes: each loads every other one
+              tma_load_4d_mc(&tm_a, &full_bar[stage], s_a + stage * kRowATile, kb * 64, iw0, r0 + i, b, 0x3);
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1;
@@ -188,24 +197,38 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           const uint32_t d_z = tmem_base + ((n0 + static_cast<uint32_t>(i)) & (kRowSlots - 1)) * kRowN;
           const uint64_t b_z = static_cast<uint64_t>((6 * kRowBTile) >> 4);
           constexpr uint32_t id_z = umma_idesc_bf16(128, kRowN);
-          for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) {  // fully unrolled: the kb == 0 / last-block cases below fold at compile time
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             const uint64_t adesc = umma_smem_desc_sw128(smem_u32(s_a + stage * kRowATile));
             const uint64_t bdesc = b_desc0 + static_cast<uint64_t>((kb * 7 * kRowBTile) >> 4);
+            if (p.dbg_flags & 16) {
+              if (kMc) umma_commit_mc(&empty_bar[stage], 0x3);
+              else umma_commit(&empty_bar[stage]);
+              if (++stage == Cfg::kStages) {
+                stage = 0;
+                phase ^= 1;
+              }
+              continue;
+            }
             if (kb == 0) {
               if (len_a0 > 0) umma_bf16<1>(d_a, adesc, bdesc + b_a, id_a0, 1u);
               if (len_b0 > 0) umma_bf16<1>(d_b, adesc, bdesc + b_b0, id_b0, 1u);
               if (starts) umma_bf16<1>(d_z, adesc, bdesc + b_z, id_z, 0u);
             }
+            // stem: the window under a filter row has 7 * 40 = 280 elements; the last k-block (256..319) only carries
+            // 24 of them, so its upper two K = 16 steps meet nothing but zero weights
+            const int ksteps = (!kHead && kb == KB - 1) ? 2 : 4;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              if (kb == 0 && k == 0) continue;
+              if ((kb == 0 && k == 0) || k >= ksteps) continue;
               umma_bf16<1>(d_a, adesc + static_cast<uint64_t>(k * 2), bdesc + b_a + static_cast<uint64_t>(k * 2), id_a, 1u);
               if (len_b > 0)
                 umma_bf16<1>(d_b, adesc + static_cast<uint64_t>(k * 2), bdesc + b_b + static_cast<uint64_t>(k * 2), id_b, 1u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (kMc) umma_commit_mc(&empty_bar[stage], 0x3);
+            else umma_commit(&empty_bar[stage]);
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1;
@@ -238,6 +261,12 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int slot = n & (kRowSlots - 1);
         mbar_wait_parked(&tfull_bar[slot], (n / kRowSlots) & 1);
         tc_fence_after();
+        if (p.dbg_flags & 8) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[slot]);
+          continue;
+        }
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + slot * kRowN, v);
         tmem_ld_wait();
@@ -278,8 +307,11 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             pk[t] = *reinterpret_cast<uint32_t*>(&h);
           }
           uint4* dst = reinterpret_cast<uint4*>(orow);
+          if (!(p.dbg_flags & 2)) {
 #pragma unroll
-          for (int t = 0; t < 4; ++t) dst[t] = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+            for (int t = 0; t < 4; ++t) dst[t] = make_uint4(pk[4 * t], pk[4 * t + 1], pk[4 * t + 2], pk[4 * t + 3]);
+          }
+          if (p.dbg_flags & 1) continue;
           // column sums through a per-warp 32x16-word shared transpose: lane l owns column pair (l & 15) over
           // rows 16*(l >> 4) .. +15 (see conv_igemm.cu)
           uint32_t* s_t = reinterpret_cast<uint32_t*>(s_scr) + warp * (32 * 17);
@@ -320,18 +352,19 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (kMc) cluster_sync_all();  // no CTA leaves while the peer may still arrive on its barriers
   if (warp == kRowMmaWarp) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, kRowSlots * kRowN);
   }
 }
 
-template <int KB, bool kHead>
+template <int KB, bool kHead, bool kMc>
 static int launch_rowconv(const CUtensorMap& ta, const CUtensorMap& tb, const RowConvParams& p, cudaStream_t stream) {
   using Cfg = RowCfg<KB, kHead>;
   static DeviceOnce configured;  // the attribute is per device: set it on each device this process uses
   if (configured.first_use()) {
-    cudaError_t e = cudaFuncSetAttribute(rowconv_kernel<KB, kHead>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(rowconv_kernel<KB, kHead, kMc>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "cudaFuncSetAttribute(rowconv smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
     configured.done();
   }
@@ -343,7 +376,24 @@ static int launch_rowconv(const CUtensorMap& ta, const CUtensorMap& tb, const Ro
     grid -= grid % p.n_splits;
     if (grid > items * p.n_splits) grid = items * p.n_splits;
   }
-  rowconv_kernel<KB, kHead><<<grid, kRowThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  if (kMc) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kRowThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, rowconv_kernel<KB, kHead, kMc>, ta, tb, p);
+    if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "rowconv cluster launch: %s", cudaGetErrorString(e));
+    return check_launch("rowconv_kernel");
+  }
+  rowconv_kernel<KB, kHead, kMc><<<grid, kRowThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   return check_launch("rowconv_kernel");
 }
 
@@ -359,6 +409,14 @@ int rowconv_forward(const jpdse_conv_desc* d, bool head, const void* x, const vo
   p.out = y;
   p.stats = stats;
   p.bias = bias;
+  {
+    static int flags = -1;
+    if (flags < 0) {
+      const char* e = getenv("JPDSE_DEBUG_FLAGS");
+      flags = e ? atoi(e) : 0;
+    }
+    p.dbg_flags = flags;
+  }
   p.chunk_rows = d->in_h < 128 ? d->in_h : 128;
   p.chunks = (d->in_h + p.chunk_rows - 1) / p.chunk_rows;
   const uint64_t C = static_cast<uint64_t>(d->cin), B = static_cast<uint64_t>(d->batch);
@@ -385,9 +443,13 @@ int rowconv_forward(const jpdse_conv_desc* d, bool head, const void* x, const vo
     uint32_t bb[2] = {64, 7 * kRowN};
     rc = make_tmap_bf16(&tb, w_packed, 2, bd, bs, bb);
     if (rc != JPDSE_OK) return rc;
-    return launch_rowconv<1, true>(ta, tb, p, stream);
+    return launch_rowconv<1, true, false>(ta, tb, p, stream);
   }
   p.n_splits = d->cout / kRowN;
+  {
+    const char* e = getenv("JPDSE_STEM_MULTICAST");  // "0": every CTA loads its own copy of the A boxes
+    p.mc = (p.n_splits == 2 && !(e && e[0] == '0')) ? 1 : 0;
+  }
   p.strip_valid = 128;
   p.strip_step = 128;
   p.strips = d->in_w / 128;
@@ -399,7 +461,7 @@ int rowconv_forward(const jpdse_conv_desc* d, bool head, const void* x, const vo
   uint32_t bb[2] = {64, 7 * kRowN};
   rc = make_tmap_bf16(&tb, w_packed, 2, bd, bs, bb);
   if (rc != JPDSE_OK) return rc;
-  return launch_rowconv<5, false>(ta, tb, p, stream);
+  return p.mc ? launch_rowconv<5, false, true>(ta, tb, p, stream) : launch_rowconv<5, false, false>(ta, tb, p, stream);
 }
 
 }  // namespace jpdse

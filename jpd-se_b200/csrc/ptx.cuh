@@ -184,6 +184,16 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, in
                "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// Multicast flavour: the box lands at the same shared-memory offset in every CTA of the cluster named in `cta_mask`,
+// and each destination CTA's barrier (same offset) receives the transaction bytes.
+__device__ __forceinline__ void tma_load_4d_mc(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                               int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, "
+      "%5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
 // 2-CTA flavour: both CTAs of the pair issue it; `bar_addr` already has the peer bit cleared so the
 // transaction bytes land on the leader CTA's barrier.
 __device__ __forceinline__ void tma_load_2d_cg2(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1) {
@@ -266,6 +276,14 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// single-CTA MMAs, multicast arrive: the barrier at this smem offset in every CTA named in `cta_mask` gets one arrival
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
 }
 // 2-CTA commit: arrives on the barrier at this smem offset in every CTA named in `cta_mask`.
 __device__ __forceinline__ void umma_commit_cg2_mc(uint64_t* bar, uint16_t cta_mask) {

@@ -1,5 +1,5 @@
 """Times one forward conv shape (for experiments / ncu).  python tools/conv_probe.py kind B H W cin cout [iters]
-kind in conv3x3|convs2|convt"""
+kind in conv3x3|convs2|convt|stem (7x7, cin = 40 stored / 39 real)"""
 import os
 import sys
 
@@ -7,14 +7,16 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 import jpdse_b200  # noqa: E402,F401
 from jpdse_b200 import ops  # noqa: E402
-from jpdse_b200._lib import CONV3X3_PAD1, CONV3X3_S2, CONVT3X3_S2, EPI_RAW_STATS  # noqa: E402
+from jpdse_b200._lib import CONV3X3_PAD1, CONV3X3_S2, CONV7X7_PAD3, CONVT3X3_S2, EPI_RAW_STATS  # noqa: E402
 
 kind, B, H, W, cin, cout = sys.argv[1], *(int(a) for a in sys.argv[2:7])
 iters = int(sys.argv[7]) if len(sys.argv) > 7 else 10
 dev = torch.device("cuda")
-k, pad = {"conv3x3": (CONV3X3_PAD1, 1), "convs2": (CONV3X3_S2, 0), "convt": (CONVT3X3_S2, 0)}[kind]
-cv = ops.Conv(k, EPI_RAW_STATS, B, H, W, pad, cin, cin, cout, dev)
-cv.pack(torch.randn((cin, cout, 3, 3) if kind == "convt" else (cout, cin, 3, 3), device=dev) * 0.02)
+k, pad = {"conv3x3": (CONV3X3_PAD1, 1), "convs2": (CONV3X3_S2, 0), "convt": (CONVT3X3_S2, 0), "stem": (CONV7X7_PAD3, 3)}[kind]
+cin_real = cin - 1 if kind == "stem" else cin
+cv = ops.Conv(k, EPI_RAW_STATS, B, H, W, pad, cin, cin_real, cout, dev)
+ks = 7 if kind == "stem" else 3
+cv.pack(torch.randn((cin, cout, 3, 3) if kind == "convt" else (cout, cin_real, ks, ks), device=dev) * 0.02)
 x = ops.alloc_nhwc(B, H + 2 * pad, W + 2 * pad, cin, dev)
 x.normal_()
 oh, ow = cv.out_hw
