@@ -3,18 +3,19 @@
 dropped); ``get_option_setter`` hands its static ``modify_commandline_options`` to the parser (base_parser.py:142-144)."""
 import importlib
 
-import torch
+from torch import nn
 
 
 def find_model_using_name(model_name):
-    module = importlib.import_module(__name__ + '.' + model_name + '_model')
-    target = model_name.replace('_', '') + 'model'
-    for name, cls in module.__dict__.items():
-        if name.lower() == target.lower() and isinstance(cls, type) and issubclass(cls, torch.nn.Module):
-            return cls
-    # the reference prints this and calls exit(0); a library should not end the process, so raise instead
-    raise ValueError('In %s_model.py, there should be a subclass of torch.nn.Module with class name that matches %s in '
-                     'lowercase.' % (model_name, target))
+    wanted = (model_name.replace('_', '') + 'model').lower()
+    namespace = vars(importlib.import_module('%s.%s_model' % (__name__, model_name)))
+    hits = [obj for key, obj in namespace.items()
+            if key.lower() == wanted and isinstance(obj, type) and issubclass(obj, nn.Module)]
+    if not hits:
+        # the reference prints this and calls exit(0); a library should not end the process, so raise instead
+        raise ValueError('In %s_model.py, there should be a subclass of torch.nn.Module with class name that matches %s '
+                         'in lowercase.' % (model_name, wanted))
+    return hits[-1]
 
 
 def get_option_setter(model_name):
@@ -22,6 +23,6 @@ def get_option_setter(model_name):
 
 
 def create_model(opt):
-    instance = find_model_using_name(opt.model)(opt)
-    print('model [%s] was created' % type(instance).__name__)
-    return instance
+    model = find_model_using_name(opt.model)(opt)
+    print('model [%s] was created' % type(model).__name__)
+    return model

@@ -18,22 +18,15 @@ class S2HVQ(nn.Module):
         self._code_book = nn.Parameter(code_book)
         self._sigma = sigma
 
-    @property
-    def center_size(self):
-        return self._center_size
+    # read-only views of the constructor arguments, and sigma with the reference's positivity check (s2h_vq.py:39-63)
+    center_size = property(lambda self: self._center_size)
+    code_book = property(lambda self: self._code_book)
 
-    @property
-    def code_book(self):
-        return self._code_book
+    def _set_sigma(self, value):
+        assert value > 0, "sigma must be greater than 0, got {}".format(value)
+        self._sigma = value
 
-    @property
-    def sigma(self):
-        return self._sigma
-
-    @sigma.setter
-    def sigma(self, new_sigma):
-        assert new_sigma > 0, "sigma must be greater than 0, got {}".format(new_sigma)
-        self._sigma = new_sigma
+    sigma = property(lambda self: self._sigma, _set_sigma)
 
     def _rows(self, x_mtrx):
         if torch.is_grad_enabled() and (x_mtrx.requires_grad or self._code_book.requires_grad):

@@ -1,13 +1,13 @@
-"""``get_trainer`` with the reference's lookup rule (ctu/trainers/__init__.py:5-20)."""
+"""``get_trainer`` with the reference's lookup rule (ctu/trainers/__init__.py:5-20): ``--model NAME`` imports
+``<this package>.NAME_trainer`` and returns the class called ``NAMEtrainer`` (case-insensitive, underscores dropped)."""
 import importlib
 
 
 def get_trainer(opt):
-    name = opt.model
-    module = importlib.import_module(__name__ + '.' + name + '_trainer')
-    target = name.replace('_', '') + 'trainer'
-    for cls_name, cls in module.__dict__.items():
-        if cls_name.lower() == target.lower() and isinstance(cls, type):
-            return cls
-    raise ValueError('In {}_trainer.py, there should be a trainer class named {} (case-insensitive).'.format(
-        name, target))
+    wanted = (opt.model.replace('_', '') + 'trainer').lower()
+    namespace = vars(importlib.import_module('%s.%s_trainer' % (__name__, opt.model)))
+    hits = [obj for key, obj in namespace.items() if key.lower() == wanted and isinstance(obj, type)]
+    if not hits:
+        raise ValueError('In {}_trainer.py, there should be a trainer class named {} (case-insensitive).'.format(
+            opt.model, wanted))
+    return hits[-1]
