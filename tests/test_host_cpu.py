@@ -150,3 +150,24 @@ def test_model_lookup_and_option_setter_match_the_reference_table(golden_dir):
                                    "--quality 36 --ext bpg --checkpoints_dir ckpt --no_vgg_loss --dataset cityscapes".split())
     assert ns.no_label_encoding and ns.no_generator_binarization and ns.ext == "bpg" and ns.quality == "36"
     assert rest == ["--dataset", "cityscapes"] and ns.n_downsample_global == 4 and ns.n_blocks_global == 9
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys on
+    rank 0, nothing on the other ranks."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+           "--height", "64", "--width", "128"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["steps"] == 1 and d["warmup"] == 0 and "workload" in d["config"]
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
