@@ -144,7 +144,12 @@ class GeneratorPlan:
             self.g_buf = [torch.zeros(act_elems + 2048, dtype=torch.bfloat16, device=device) for _ in range(2)]
             self.dy_buf = [torch.zeros(raw_elems, dtype=torch.bfloat16, device=device) for _ in range(3)]
             dx_elems = max(raw_elems, B * (self.hb + 4) * (self.wb + 4) * self.cb)
-            self.dx_buf = torch.zeros(dx_elems + 2048, dtype=torch.bfloat16, device=device)
+            # two dx buffers: the weight gradient of layer k (own stream, below) still reads dx_k while the main
+            # stream writes dx_{k-1}
+            self.dx_buf = [torch.zeros(dx_elems + 2048, dtype=torch.bfloat16, device=device) for _ in range(2)]
+            self.overlap_wgrad = os.environ.get("JPDSE_WGRAD_STREAM", "1") != "0"
+            self._wgrad_stream = torch.cuda.Stream(device=device)
+            self._wgrad_ws = None  # float32 scratch of the weight-gradient kernels on that stream
             self.d_pre = torch.zeros(B * (H + 12) * (W + 12) * 8 + 2048, dtype=torch.bfloat16, device=device)
         self.layers = []
         self.generation = 0
@@ -354,23 +359,55 @@ class GeneratorPlan:
             if on_grad is not None:
                 on_grad(key, t)
 
+        # Weight gradients run on their own stream: they depend only on dx_k and the saved forward activation, nothing
+        # downstream depends on them, and the main chain (data gradient -> InstanceNorm backward -> ...) leaves SMs idle
+        # at every wave tail (152 data-gradient tiles on 148 SMs at batch 2). The main stream only waits for them
+        # before it overwrites a dx buffer they read, and at the end.
+        main = torch.cuda.current_stream(dev)
+        side = self._wgrad_stream if self.overlap_wgrad else None
+        if self._wgrad_ws is None:
+            need = max([self.head.wgrad_workspace_bytes(6)] +
+                       [L.conv.wgrad_workspace_bytes(2 if L.conv.kind == CONV3X3_PAD1 else 0) for L in self.layers])
+            self._wgrad_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dev)
+        ws = self._wgrad_ws
+
+        def weight_grad(fn):
+            """Enqueue fn (wgrad + emit) behind everything the main stream has issued so far; returns the event the
+            main stream must wait on before it overwrites fn's inputs (None when not overlapping)."""
+            if side is None:
+                fn()
+                return None
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            with torch.cuda.stream(side), ops.stream_cached():
+                fn()
+                done = torch.cuda.Event()
+                done.record(side)
+            return done
+
         self.bwd_sums.zero_()
         ops._count()
         # ---- head: tanh', bias, wgrad, dgrad
         d_pre = self._view(self.d_pre, B, H + 12, W + 12, 8)
         dbias = new(self.head_name + ".bias", (self.output_nc,)).zero_()
         ops.tanh_backward_nchw(grad_out, self.out, d_pre, dbias)
-        dw = new(self.head_name + ".weight", weight_shapes[self.head_name])
-        self.head.wgrad(self.head_in, d_pre, 6, dw)
-        emit(self.head_name + ".bias", dbias)
-        emit(self.head_name + ".weight", dw)
+        dw_head = new(self.head_name + ".weight", weight_shapes[self.head_name])
+
+        def head_grads():
+            self.head.wgrad(self.head_in, d_pre, 6, dw_head, workspace=ws)
+            emit(self.head_name + ".bias", dbias)
+            emit(self.head_name + ".weight", dw_head)
+
+        weight_grad(head_grads)
         gi = 0
         g = self._view(self.g_buf[gi], B, H + 6, W + 6, self.ngf)
         self.dgrads[self.head_name].forward(d_pre, g)
         g_pad = 3
         skip, skip_idx = None, None  # second gradient of the current layer's output (ResnetBlock skip connection)
         pending_idx = None           # dy buffer holding dL/dx_{k+1} until the walk reaches the producer of x_k
-        for si in range(len(self.layers) - 1, -1, -1):
+        dx_free = [None, None]       # per dx buffer: event of the weight gradient that last read it
+        for step, si in enumerate(range(len(self.layers) - 1, -1, -1)):
             L = self.layers[si]
             h, w, c = L.h, L.w, L.c
             if not L.consumer_reads_border:
@@ -380,11 +417,18 @@ class GeneratorPlan:
             sums = self._stats(si, c, self.bwd_sums)
             ops.instnorm_backward_reduce(g, g_pad, skip, L.raw, L.stats, dy, sums, B, h, w, c, L.relu)
             z = 2 if L.conv.kind == CONV3X3_PAD1 else 0
-            dx = self._view(self.dx_buf, B, h + 2 * z, w + 2 * z, c)
+            slot = step & 1
+            if dx_free[slot] is not None:
+                main.wait_event(dx_free[slot])
+            dx = self._view(self.dx_buf[slot], B, h + 2 * z, w + 2 * z, c)
             ops.instnorm_backward_apply(dy, L.raw, L.stats, sums, dx, z, B, h, w, c)
             dw = new(L.name + ".weight", weight_shapes[L.name])
-            L.conv.wgrad(L.x_in, dx, z, dw)
-            emit(L.name + ".weight", dw)
+
+            def layer_grad(L=L, dx=dx, z=z, dw=dw):
+                L.conv.wgrad(L.x_in, dx, z, dw, workspace=ws)
+                emit(L.name + ".weight", dw)
+
+            dx_free[slot] = weight_grad(layer_grad)
             if si == 0:
                 break  # the stem's input (labels + decoded image) needs no gradient
             gi ^= 1
@@ -401,6 +445,8 @@ class GeneratorPlan:
                 # conv_block.1: the layer below produced the block input x_k, gradient = fold(g) + dL/dx_{k+1}
                 skip_idx, pending_idx = pending_idx, None
                 skip = self._view(self.dy_buf[skip_idx], B, h, w, c)
+        if side is not None:
+            main.wait_stream(side)
         return grads
 
 

@@ -147,15 +147,25 @@ class Conv:
         _count(self.launches)
         return y
 
-    def wgrad(self, x, dy, dy_pad, dw, accumulate=False):
-        """dw (float32, torch weight layout) = / += weight gradient of THIS (forward) conv. See jpdse_conv_wgrad."""
+    def wgrad_workspace_bytes(self, dy_pad):
+        nbytes = self.lib.jpdse_conv_wgrad_workspace_bytes(ctypes.byref(self.desc), dy_pad)
+        if nbytes == 0:
+            raise JpdseError("conv_wgrad rejected: %s" % self.lib.jpdse_last_error().decode())
+        return nbytes
+
+    def wgrad(self, x, dy, dy_pad, dw, accumulate=False, workspace=None):
+        """dw (float32, torch weight layout) = / += weight gradient of THIS (forward) conv. See jpdse_conv_wgrad.
+        `workspace`: a float32 scratch tensor of at least wgrad_workspace_bytes(dy_pad) owned by the caller (needed when
+        weight gradients run on their own stream); default: the per-device scratch buffer shared by one stream."""
         _need(x, "x", torch.bfloat16)
         _need(dy, "dy", torch.bfloat16)
         _need(dw, "dw", torch.float32)
         nbytes = self.lib.jpdse_conv_wgrad_workspace_bytes(ctypes.byref(self.desc), dy_pad)
         if nbytes == 0:
             raise JpdseError("conv_wgrad rejected: %s" % self.lib.jpdse_last_error().decode())
-        ws = _workspace(nbytes, x.device)
+        ws = workspace if workspace is not None else _workspace(nbytes, x.device)
+        if ws.numel() * 4 < nbytes:
+            raise JpdseError("conv_wgrad: workspace of %d bytes, %d needed" % (ws.numel() * 4, nbytes))
         check(self.lib.jpdse_conv_wgrad(ctypes.byref(self.desc), _ptr(x), _ptr(dy), dy_pad, _ptr(dw), int(bool(accumulate)),
                                         _ptr(ws), ws.numel() * 4, _stream()))
         _count(2)

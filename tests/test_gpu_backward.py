@@ -482,3 +482,33 @@ def test_wide_image_forward_backward_vs_oracle(cuda):
         assert c >= 0.999, (n, c)
     for n, p in net.named_parameters():
         assert torch.isfinite(p.grad).all(), n
+
+
+def test_weight_gradients_on_their_own_stream_equal_the_sequential_backward(cuda, monkeypatch):
+    """engine.GeneratorPlan.backward runs the weight-gradient kernels on a side stream (they only depend on dx_k and a
+    saved activation); with JPDSE_WGRAD_STREAM=0 they stay in line. Same kernels, same operands: the gradients must
+    agree to the split-K atomics' reordering noise, three backward passes in a row (buffer reuse across calls)."""
+    import copy
+    nw = _networks()
+    torch.manual_seed(5)
+    net_a = nw.define_G(39, 3, 64, "global", 4, 2, 1, 3, "instance", gpu_ids=[])
+    net_b = copy.deepcopy(net_a)
+    gen = torch.Generator().manual_seed(3)
+    xs = [torch.randn(2, 39, 128, 256, generator=gen).to(cuda) for _ in range(3)]
+    grads = []
+    for net, flag in ((net_a, "1"), (net_b, "0")):
+        monkeypatch.setenv("JPDSE_WGRAD_STREAM", flag)
+        net = net.to(cuda).train()
+        per_pass = []
+        for x in xs:
+            for p in net.parameters():
+                p.grad = None
+            y = net(x)
+            (y * y).mean().backward()
+            per_pass.append({n: p.grad.clone() for n, p in net.named_parameters()})
+        torch.cuda.synchronize()
+        grads.append(per_pass)
+    for pa, pb in zip(*grads):
+        for n in pa:
+            scale = float(pb[n].abs().max()) + 1e-12
+            assert float((pa[n] - pb[n]).abs().max()) <= 1e-5 * scale, n
