@@ -43,6 +43,18 @@ def synth_inputs(batch, height, width, seed=1234, qf=36):
     return label.float(), inst.int(), deg.clamp_(-0.5, 0.5)
 
 
+def synth_inputs_compact(batch, height, width, seed=1234, qf=36):
+    """The same synthetic workload in the COMPACT loader format: uint8 class ids, int16 instance ids,
+    uint8 RGB of the degraded image (what a BPG/PNG decoder hands over); 3.1 MB per 1024x512 image instead of 10.5 MB.
+    Also returns the float32 image the loader's ToTensor + Normalize(.5, 1.) would make of those bytes -- the tensor the
+    reference's x_dict['image'] carries (ctu/data/ctu_dataset.py:73-133)."""
+    import torch
+    label, inst, deg = synth_inputs(batch, height, width, seed, qf)
+    img_u8 = torch.round((deg + 0.5) * 255.0).clamp_(0, 255).to(torch.uint8)
+    img_f32 = img_u8.float() / 255.0 - 0.5          # ToTensor then Normalize(mean .5, std 1.): exact in float32
+    return label.to(torch.uint8), inst.to(torch.int16), img_u8, img_f32
+
+
 def make_opt():
     return argparse.Namespace(model="pix2pixHD", gpu_ids=[0], is_train=False, num_labels=35,
                               contain_dontcare_label=False, no_label=False, no_instance=False, no_feat=False,
@@ -113,45 +125,74 @@ def load_peaks():
     return 1400.0, 1590.0, "fallback"
 
 
-def cpu_reference_time(batch, height, width, steps, warmup, weights=None):
-    """Times the CPU restatement of the reference forward (oracle/) on all host threads. Returns s/step."""
+def _reference_arm():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_arm", os.path.join(ROOT, "tools", "reference_arm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def cpu_reference_run(label, inst, image, steps, warmup, weights=None):
+    """Times the reference's CPU path for ONE batch of inputs on all host threads; returns (s/step, output, kind).
+
+    kind "reference": the UNMODIFIED reference installed in baseline/_ref (tools/install_reference.sh), through its own
+    public API -- parser -> get_trainer(opt)(opt, 'test') -> trainer.get_img(x_dict) (one-hot scatter_, get_edges, cat,
+    GlobalGenerator on ATen/oneDNN). kind "port": the oracle restatement, only when baseline/_ref is absent.
+    `weights`: generator state dict to load (reference keys); None = reference define_G under seed 1234."""
     import torch
-    from oracle import generator_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
+    ra = _reference_arm()
+    times, out = [], None
+    if ra.available():
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):  # the reference prints banners; stdout carries ONE JSON line
+            trainer, _opt = ra.build_test_trainer(state_dict=weights)
+        x_dict = {"label": label.float(), "instance": inst.int(), "image": image.float(), "path": ["synthetic"] * label.shape[0]}
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            out = trainer.get_img({k: (v.clone() if hasattr(v, "clone") else v) for k, v in x_dict.items()})
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+        return sum(times) / len(times), out, "reference"
+    from oracle import generator_oracle as orc
     if weights is None:
         import jpdse_b200  # noqa: F401
         import importlib
         nw = importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
         torch.manual_seed(1234)
         weights = nw.define_G(39, 3, 64, "global", 4, 9, 1, 3, "instance", gpu_ids=[]).state_dict()
-    label, inst, image = synth_inputs(batch, height, width)
-    times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            x = torch.from_numpy(orc.build_input(label.numpy(), inst.numpy(), image.numpy(), 35))
-            orc.generator_forward(weights, x, 4, 9)
+            x = torch.from_numpy(orc.build_input(label.float().numpy(), inst.int().numpy(), image.float().numpy(), 35))
+            out = orc.generator_forward(weights, x, 4, 9)
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return sum(times) / len(times)
+    return sum(times) / len(times), out, "port"
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port; the Python reference cannot travel to the box)."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, one image of the
+    workload per step (bounded sample), same metric / config keys as our arm. Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     sample_b = 1  # bounded sample: one image per step
-    sec = cpu_reference_time(sample_b, args.height, args.width, args.steps, args.warmup)
+    _l, _i, _u8, img = synth_inputs_compact(args.batch, args.height, args.width, seed=1234)
+    label, inst = _l[:sample_b], _i[:sample_b]
+    sec, _out, kind = cpu_reference_run(label, inst, img[:sample_b], args.steps, args.warmup)
     v = sample_b / sec
+    what = ("unmodified reference (baseline/_ref) via parser -> get_trainer -> Pix2PixHDTrainer.get_img" if kind == "reference"
+            else "oracle port of the reference path (baseline/_ref not installed)")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args),
-            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "batch 1 of the %dx%d workload per step, fp32, torch CPU (oneDNN), %d threads"
-                                       % (args.width, args.height, cores)},
+            "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": kind,
+                             "sample": "image 0 of the batch-%d %dx%d workload per step (batch 1), fp32, torch CPU "
+                                       "(oneDNN), %d threads; %s" % (args.batch, args.width, args.height, cores, what)},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -178,6 +219,8 @@ def train_measure(args, dev, local, rank, world, barrier):
     import torch
     import torch.distributed as dist
     tr = importlib.import_module("jpd-se_b200.ctu.trainers.pix2pixHD_trainer")
+    # no pretrained VGG19 checkpoint on an offline box: explicit opt-in to random VGG weights (same FLOPs, recorded below)
+    os.environ.setdefault("JPDSE_VGG_RANDOM", "1")
     opt = make_opt()
     opt.gpu_ids, opt.is_train, opt.quiet = [local], True, True
     torch.manual_seed(1234)
@@ -223,7 +266,8 @@ def train_measure(args, dev, local, rank, world, barrier):
             "generator_fwd_bwd_tflops_per_gpu": g_flops / (g_ms * 1e-3) / 1e12,
             "trainer_step_ms": step_ms, "trainer_step_images_per_s": world * B / (step_ms * 1e-3),
             "allreduce": "none (1 GPU)" if world == 1 else "730 MB fp32 generator gradients, bucketed, overlapped with backward (NCCL)",
-            "note": "generator forward/backward = jpdse_b200 kernels; netD, VGG (random weights offline), losses, Adam = PyTorch"}
+            "vgg_weights": "random (JPDSE_VGG_RANDOM=1: the pretrained checkpoint is not available offline; same FLOPs)",
+            "note": "generator forward/backward = jpdse_b200 kernels; netD, VGG, losses, Adam = PyTorch"}
 
 
 def cudnn_measure(B, H, W, dev):
@@ -250,9 +294,170 @@ def workload_config(args):
     return {"workload": "pix2pixHD-BPG QF36 semantic-aware generator inference, batch %d at %dx%d, 35-class label map "
                         "+ instance edges + RGB, random-init weights" % (args.batch, args.width, args.height),
             "batch_per_gpu": args.batch, "height": args.height, "width": args.width,
+            "inputs": "compact loader format: uint8 class ids, int16 instance ids, uint8 RGB (normalised on the device)",
             "execution": "two half-batch plans on two CUDA streams, one captured CUDA graph per step (JPDSE_SPLIT_STREAMS=1 "
                          "for a single stream)" if args.batch >= 8 and args.batch % 2 == 0 else "single stream, one CUDA graph per step",
             "l2": "inputs+activations per step are GBs >> 126 MB L2 (no flush needed)"}
+
+
+def _max_over_ranks(ms, world, dev):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def device_resident(plan, inputs, steps, warmup, barrier, sampler=None):
+    """Device-resident loop: inputs already in HBM, K forwards bracketed by barrier + synchronize, CUDA-event timed."""
+    import torch
+    from jpdse_b200 import ops
+    d_label, d_inst, d_image = inputs
+    for _ in range(warmup):
+        plan.forward_from_maps(d_label, d_inst, d_image, 35)
+    barrier()
+    ops.launch_count = 0
+    if sampler:
+        sampler.begin()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(steps):
+        plan.forward_from_maps(d_label, d_inst, d_image, 35)
+    end.record()
+    barrier()
+    if sampler:
+        sampler.end()
+    return start.elapsed_time(end), ops.launch_count
+
+
+def e2e_measure(trainer, host, B, H, W, steps, barrier, dev):
+    """End to end through the ctu API. Every step: H2D of that step's pinned host inputs, trainer.get_img(x_dict) (the
+    call test.py makes, ctu/trainers/pix2pixHD_trainer.py:113-116), D2H of the output image. Copies run on their own
+    streams with double-buffered device inputs, so step i+1's upload and step i-1's download overlap step i's kernels
+    -- all of them inside the timed region. Returns (ms total, h2d bytes/step, d2h bytes/step)."""
+    import torch
+    pin = {k: v.pin_memory() for k, v in host.items()}
+    host_out = [torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in pin.items()} for _ in range(2)]
+    h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    in_ready = [torch.cuda.Event() for _ in range(2)]
+    in_free = [torch.cuda.Event() for _ in range(2)]
+    out_done = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        s = i % 2
+        with torch.cuda.stream(h2d_stream):
+            h2d_stream.wait_event(in_free[s])
+            for k, v in pin.items():
+                dev_in[s][k].copy_(v, non_blocking=True)
+            in_ready[s].record(h2d_stream)
+
+    def loop(n):
+        for s in range(2):
+            in_free[s].record(main)
+        upload(0)
+        for i in range(n):
+            s = i % 2
+            if i + 1 < n:
+                upload(i + 1)
+            main.wait_event(in_ready[s])
+            out = trainer.get_img(dict(dev_in[s], path=["synthetic"] * B))
+            in_free[s].record(main)
+            done = torch.cuda.Event()
+            done.record(main)
+            out.record_stream(d2h_stream)
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(done)
+                host_out[s].copy_(out, non_blocking=True)
+                out_done[s].record(d2h_stream)
+        for s in range(2):
+            main.wait_event(out_done[s])
+
+    with torch.no_grad():
+        loop(2)
+        barrier()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        loop(steps)
+        e2.record()
+        barrier()
+    trainer.model.check_labels()
+    h2d = sum(v.numel() * v.element_size() for v in pin.values())
+    d2h = host_out[0].numel() * host_out[0].element_size()
+    return s2.elapsed_time(e2), h2d, d2h, host_out[(steps - 1) % 2]
+
+
+def bandwidth_measure(dev, hbm_peak):
+    """Achieved HBM GB/s of the memory-bound kernels of the path (north_star's evidence clause), each timed alone with
+    CUDA events over buffers larger than the 126 MB L2 (unless noted), algorithmic bytes / time, vs the measured copy
+    peak (MEASURED_PEAKS.json hbm_gbs)."""
+    import torch
+    from jpdse_b200 import ops
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    rows = []
+
+    def add(name, nbytes, fn, note=None):
+        ms = timed(fn)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        r = {"kernel": name, "bytes": int(nbytes), "ms": ms, "gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
+        if note:
+            r["note"] = note
+        rows.append(r)
+
+    B, H, W = 16, 512, 1024
+    px = B * H * W
+    lab8, ins16, img8, imgf = synth_inputs_compact(B, H, W)
+    x0 = ops.alloc_nhwc(B, H + 6, W + 6, 40, dev)
+    out_b = B * (H + 6) * (W + 6) * 80
+    lf, ii, fi = lab8.float().to(dev), ins16.int().to(dev), imgf.to(dev)
+    add("build_input_nhwc_kernel (float32 ids + int32 instance + float32 image -> padded NHWC bf16 x40)", px * 20 + out_b,
+        lambda: ops.build_input(lf, ii, fi, 35, pad=3, c_pad=40, out_nhwc=x0))
+    l8, i16, u8 = lab8.to(dev), ins16.to(dev), img8.to(dev)
+    add("build_input_nhwc_kernel (compact: uint8 ids + int16 instance + uint8 RGB)", px * 6 + out_b,
+        lambda: ops.build_input(l8, i16, u8, 35, pad=3, c_pad=40, out_nhwc=x0))
+    del lf, ii, fi, l8, i16, u8, x0
+    for (b, h, w, c, pad, relu, res, note) in ((8, 512, 1024, 64, 3, True, False, None), (8, 256, 512, 128, 0, True, False, None),
+                                               (8, 64, 128, 512, 0, True, False, None),
+                                               (8, 32, 64, 1024, 1, False, True, "67 MB in + 2 x 38 MB: partly L2-resident, as in the real pipeline")):
+        raw = torch.randn(b, h, w, c, device=dev).bfloat16()
+        st = torch.zeros(b, c, 2, dtype=torch.float64, device=dev)
+        st[:, :, 1] = float(h * w)
+        out = ops.alloc_nhwc(b, h + 2 * pad, w + 2 * pad, c, dev)
+        resid = ops.alloc_nhwc(b, h + 2 * pad, w + 2 * pad, c, dev) if res else None
+        nbytes = b * h * w * c * 2 + b * (h + 2 * pad) * (w + 2 * pad) * c * 2 * (2 if res else 1)
+        add("instnorm_apply_kernel c%d %dx%d pad %d%s%s" % (c, w, h, pad, " +relu" if relu else "", " +residual" if res else ""),
+            nbytes, lambda: ops.instnorm_apply(raw, st, out, b, h, w, c, pad, relu, residual=resid), note)
+        del raw, st, out, resid
+    xq = torch.randn(1 << 26, device=dev)
+    add("quant_elementwise_kernel round (RoundedIdentity fwd)", xq.numel() * 8, lambda: ops.round_f32(xq))
+    add("quant_elementwise_kernel sign (DifferentiableSign eval)", xq.numel() * 8, lambda: ops.sign_f32(xq))
+    add("sign_to_bits_kernel", xq.numel() * 5, lambda: ops.sign_to_bits(xq))
+    rows_n, csz, ncen = 1 << 23, 8, 16
+    xv = xq[: rows_n * csz].view(rows_n, csz)
+    cb = torch.randn(ncen, csz, device=dev)
+    add("s2hvq_encode (index only, %d centers x %d)" % (ncen, csz), rows_n * (csz * 4 + 8),
+        lambda: ops.s2hvq_encode(xv, cb, 1.0, want_index=True))
+    add("s2hvq_encode (hard one-hot out)", rows_n * (csz * 4 + ncen * 4), lambda: ops.s2hvq_encode(xv, cb, 1.0, want_one_hot=True))
+    img = xq[: 16 * 3 * 512 * 1024].view(16, 3, 512, 1024)
+    add("tensor2im_u8_kernel", img.numel() * 5, lambda: ops.tensor2im_u8(img))
+    del xq
+    torch.cuda.empty_cache()
+    return rows
 
 
 def main():
@@ -268,8 +473,10 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the (extra, non-headline) training-step measurement")
     ap.add_argument("--no-cudnn-baseline", action="store_true",
                     help="skip timing the same architecture on stock PyTorch/cuDNN on this GPU (extra, rank 0 at N=1)")
+    ap.add_argument("--no-fullres", action="store_true", help="skip the 2048x1024 batch-4 measurement (BASELINE configs[2])")
+    ap.add_argument("--no-bandwidth", action="store_true", help="skip the memory-bound kernels' GB/s table (rank 0 at N=1)")
     ap.add_argument("--train-batch", type=int, default=2, help="images per GPU of the training-step measurement")
-    ap.add_argument("--layers", action="store_true", help="print a per-kernel-type time breakdown to stderr")
+    ap.add_argument("--fullres-batch", type=int, default=4, help="images per GPU of the 2048x1024 measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -277,7 +484,6 @@ def main():
     import torch
     import jpdse_b200  # noqa: F401  (raises if libjpdse_b200.so is missing)
     import importlib
-    from jpdse_b200 import ops
     trainers = importlib.import_module("jpd-se_b200.ctu.trainers")
 
     rank = int(os.environ.get("RANK", "0"))
@@ -297,8 +503,9 @@ def main():
     trainer = trainers.get_trainer(opt)(opt, "test")
     netG = trainer.model.netG
     B, H, W = args.batch, args.height, args.width
-    label, inst, image = synth_inputs(B, H, W, seed=1234 + rank)
-    d_label, d_inst, d_image = label.to(dev), inst.to(dev), image.to(dev)
+    # the image shards of this rank (image-sharded inference: rank r owns every world-th batch; per-rank seeds)
+    lab8, ins16, img8, img_f32 = synth_inputs_compact(B, H, W, seed=1234 + rank)
+    d_in = (lab8.to(dev), ins16.to(dev), img8.to(dev))
     plan = netG.plan_for(B, H, W, dev)  # batch >= 8: two half-batch plans on two streams, captured into one CUDA graph
 
     def barrier():
@@ -309,22 +516,9 @@ def main():
     # ---------------------------------------------------------------- device-resident throughput (the timed region)
     with torch.no_grad():
         sampler = ClockSampler(local) if rank == 0 else None
-        for _ in range(args.warmup):
-            plan.forward_from_maps(d_label, d_inst, d_image, 35)
-        barrier()
-        ops.launch_count = 0
-        if sampler:
-            sampler.begin()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        for _ in range(args.steps):
-            plan.forward_from_maps(d_label, d_inst, d_image, 35)
-        end.record()
-        barrier()
-        if sampler:
-            sampler.end()
-        launches = ops.launch_count
+        elapsed_ms, launches = device_resident(plan, d_in, args.steps, args.warmup, barrier, sampler)
         clocks = sampler.summary() if sampler else None
+        out_dev0 = plan.out[0].detach().cpu() if rank == 0 else None  # image 0 of the timed batch, for the parity object
 
         # ------------------------------------------------------------ roofline kernel: same K steps, instrumented
         # CUDA events around every res-block conv launch need the launches to be eager and un-overlapped, so this pass
@@ -352,7 +546,7 @@ def main():
         for cv in res_convs:
             cv.forward = timed(cv)
         for _ in range(args.steps):
-            plan.forward_from_maps(d_label, d_inst, d_image, 35)
+            plan.forward_from_maps(*d_in, 35)
         barrier()
         for cv in res_convs:
             cv.forward = orig_forward[id(cv)]
@@ -360,77 +554,44 @@ def main():
         if hasattr(plan, "parallel"):
             plan.parallel = saved[1]
     res_batch = parts[0].B
-    elapsed_ms = start.elapsed_time(end)
     res_ms = sum(a.elapsed_time(b) for a, b in res_events) / max(len(res_events), 1)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
+    elapsed_ms = _max_over_ranks(elapsed_ms, world, dev)
     ms_per_step = elapsed_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
 
-    # ---------------------------------------------------------------- end to end through the ctu API
-    # Every step: H2D of that step's pinned host inputs, trainer.get_img(x_dict) (the call test.py makes), D2H of the
-    # output image. Copies run on their own streams with double-buffered device inputs, so step i+1's upload and
-    # step i-1's download overlap step i's kernels -- all of them inside the timed region.
-    pin = {k: v.pin_memory() for k, v in (("label", label), ("instance", inst), ("image", image))}
-    host_out = [torch.empty((B, 3, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
-    dev_in = [{k: torch.empty_like(v, device=dev) for k, v in pin.items()} for _ in range(2)]
-    h2d_stream, d2h_stream = torch.cuda.Stream(), torch.cuda.Stream()
-    main = torch.cuda.current_stream()
-    in_ready = [torch.cuda.Event() for _ in range(2)]
-    in_free = [torch.cuda.Event() for _ in range(2)]
-    out_done = [torch.cuda.Event() for _ in range(2)]
-
-    def upload(i):
-        s = i % 2
-        with torch.cuda.stream(h2d_stream):
-            h2d_stream.wait_event(in_free[s])
-            for k, v in pin.items():
-                dev_in[s][k].copy_(v, non_blocking=True)
-            in_ready[s].record(h2d_stream)
-
-    def e2e_loop(n):
-        for s in range(2):
-            in_free[s].record(main)
-        upload(0)
-        for i in range(n):
-            s = i % 2
-            if i + 1 < n:
-                upload(i + 1)
-            main.wait_event(in_ready[s])
-            out = trainer.get_img(dict(dev_in[s], path=["synthetic"] * B))
-            in_free[s].record(main)
-            done = torch.cuda.Event()
-            done.record(main)
-            out.record_stream(d2h_stream)
-            with torch.cuda.stream(d2h_stream):
-                d2h_stream.wait_event(done)
-                host_out[s].copy_(out, non_blocking=True)
-                out_done[s].record(d2h_stream)
-        for s in range(2):
-            main.wait_event(out_done[s])
-
-    with torch.no_grad():
-        e2e_loop(2)
-        barrier()
-        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s2.record()
-        e2e_loop(args.steps)
-        e2.record()
-        barrier()
-    e2e_ms = s2.elapsed_time(e2)
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    # ---------------------------------------------------------------- end to end through the ctu API (compact inputs)
+    host = {"label": lab8, "instance": ins16, "image": img8}
+    e2e_ms, h2d, d2h, e2e_out = e2e_measure(trainer, host, B, H, W, args.steps, barrier, dev)
+    e2e_ms = _max_over_ranks(e2e_ms, world, dev)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
-    h2d = sum(v.numel() * v.element_size() for v in pin.values())
-    d2h = host_out[0].numel() * host_out[0].element_size()
+    e2e_equal = bool(rank == 0 and torch.equal(e2e_out[0], out_dev0))
+
+    # ---------------------------------------------------------------- 2048x1024 (BASELINE.json configs[2]; extra)
+    fullres = None
+    if not args.no_fullres and (H, W) == (512, 1024):
+        fb, fh, fw = args.fullres_batch, 2 * H, 2 * W
+        fl, fi, fu, _ff = synth_inputs_compact(fb, fh, fw, seed=4242 + rank)
+        fplan = netG.plan_for(fb, fh, fw, dev)
+        fsteps = max(3, min(args.steps, 10))
+        with torch.no_grad():
+            f_ms, _ = device_resident(fplan, (fl.to(dev), fi.to(dev), fu.to(dev)), fsteps, 2, barrier)
+        f_ms = _max_over_ranks(f_ms, world, dev) / fsteps
+        fe_ms, fh2d, fd2h, _ = e2e_measure(trainer, {"label": fl, "instance": fi, "image": fu}, fb, fh, fw, fsteps, barrier, dev)
+        fe_ms = _max_over_ranks(fe_ms, world, dev)
+        fullres = {"workload": "batch %d per GPU at %dx%d, image-sharded over %d GPU(s), compact inputs" % (fb, fw, fh, world),
+                   "value": world * fb / (f_ms * 1e-3), "unit": "images/s", "ms_per_step": f_ms, "steps": fsteps,
+                   "e2e": {"value": world * fb * fsteps / (fe_ms * 1e-3), "unit": "images/s",
+                           "h2d_bytes_per_step": fh2d, "d2h_bytes_per_step": fd2h},
+                   "whole_forward_tflops_per_gpu": 4 * FWD_FLOPS_PER_IMAGE * fb / (f_ms * 1e-3) / 1e12}
+        del fplan
+        netG._plans = {}
+        torch.cuda.empty_cache()
 
     # ---------------------------------------------------------------- training step (BASELINE.json configs[3]; extra)
     train = None
     if not args.no_train:
+        netG._plans = {}
+        torch.cuda.empty_cache()
         train = train_measure(args, dev, local, rank, world, barrier)
 
     if rank != 0:
@@ -444,7 +605,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args),
-            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "output_equals_device_resident_run": e2e_equal},
             "gpu_launches": launches, "clocks": clocks,
             "roofline": {"kernel": "pair_conv3x3_kernel (ResnetBlock 3x3 conv 1024->1024 on CTA pairs, tcgen05 cta_group::2)", "bound": "tensor",
                          "achieved": achieved, "peak": sustained, "unit": "TFLOP/s", "frac": achieved / sustained,
@@ -455,8 +617,21 @@ def main():
                                    "CUDA graph on two streams)" % (len(res_events), args.steps),
                          "traffic": ncu_traffic(res_batch, H, W),
                          "whole_forward_tflops": FWD_FLOPS_PER_IMAGE * scale * B / (ms_per_step * 1e-3) / 1e12}}
+    if fullres is not None:
+        line["fullres"] = fullres
     if train is not None:
         line["train"] = train
+    if world == 1 and not args.no_bandwidth:
+        try:
+            hbm = 6559.4
+            pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            if os.path.exists(pk):
+                with open(pk) as f:
+                    hbm = json.load(f).get("hbm_gbs", hbm)
+            line["bandwidth_kernels"] = {"peak_gbs": hbm, "peak_source": peak_kind + " (hbm_gbs, copy)",
+                                         "rows": bandwidth_measure(dev, hbm)}
+        except Exception as e:
+            line["bandwidth_kernels"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     if world == 1 and not args.no_cudnn_baseline:
         try:
             line["cudnn_baseline"] = cudnn_measure(B, H, W, dev)
@@ -464,9 +639,20 @@ def main():
             line["cudnn_baseline"] = {"unavailable": "%s: %s" % (type(e).__name__, e)}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sec = cpu_reference_time(1, H, W, steps=8, warmup=1, weights={k: v.cpu() for k, v in netG.state_dict().items()})
-        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "images/s", "cores": cores, "kind": "port",
-                                "sample": "8 timed forwards of batch 1 at %dx%d (same generator, same synthetic inputs, fp32, torch CPU on all host threads; ~10 s)" % (W, H)}
+        weights = {k: v.detach().cpu() for k, v in netG.state_dict().items()}
+        sec, ref_out, kind = cpu_reference_run(lab8[:1], ins16[:1], img_f32[:1], steps=8, warmup=1, weights=weights)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "images/s", "cores": cores, "kind": kind,
+                                "sample": "8 timed forwards of image 0 of the timed batch (batch 1 at %dx%d, same weights, fp32, "
+                                          "torch CPU on all host threads; ~10 s) through %s" % (
+                                              W, H, "the unmodified reference's trainer.get_img (baseline/_ref)" if kind == "reference"
+                                              else "the oracle port")}
+        # parity of the TIMED run: image 0 of the batch the timed region produced vs the reference's fp32 CPU output
+        from oracle import generator_oracle as orc
+        err = (out_dev0 - ref_out[0].cpu()).abs()
+        line["parity"] = {"against": kind + " fp32 CPU output for image 0 of the timed batch",
+                          "max_abs": float(err.max()), "mean_abs": float(err.mean()), "psnr_db": orc.psnr(out_dev0, ref_out[0].cpu()),
+                          "gate": "mean_abs <= 0.02, max_abs <= 0.15, psnr >= 39.2 dB (tests/test_gpu_parity.py)",
+                          "within_gate": bool(err.mean() <= 0.02 and err.max() <= 0.15 and orc.psnr(out_dev0, ref_out[0].cpu()) >= 39.2)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -288,9 +288,54 @@ class Pix2PixHDModel(nn.Module):
         image = x_dict[key].cuda(non_blocking=True)
         if image.dtype != torch.uint8:  # uint8 = the compact loader format: normalised on the device (extension)
             image = image.float()
-        return self.netG.forward_from_maps(label, inst, image.contiguous(), self.num_labels,
-                                           _opt(opt, 'normalize_mean', (0.5, 0.5, 0.5)),
-                                           _opt(opt, 'normalize_std', (1.0, 1.0, 1.0)))
+        self._poll_bad_labels()
+        out = self.netG.forward_from_maps(label, inst, image.contiguous(), self.num_labels,
+                                          _opt(opt, 'normalize_mean', (0.5, 0.5, 0.5)),
+                                          _opt(opt, 'normalize_std', (1.0, 1.0, 1.0)), bad_count=self._bad_counter(image.device))
+        self._post_bad_labels()
+        return out
+
+    # ------------------------------------------------------------------ out-of-range class ids (scatter_ raises, :381-382)
+    # The reference's one-hot scatter_ raises on an id outside [0, num_labels) (e.g. Cityscapes id 255 -> 35,
+    # ctu/data/ctu_dataset.py:105). The fused input-build kernel counts those pixels in a device counter instead; the
+    # fast path copies it to pinned host memory behind every call and raises LAZILY -- at the next call whose copy has
+    # landed, or in check_labels() -- so no step pays a host sync for it.
+    def _bad_counter(self, device):
+        st = getattr(self, '_bad_state', None)
+        if st is None or st['dev'].device != device:
+            st = {'dev': torch.zeros(1, dtype=torch.int32, device=device),
+                  'host': torch.zeros(1, dtype=torch.int32).pin_memory(), 'event': None}
+            self._bad_state = st
+        return st['dev']
+
+    def _post_bad_labels(self):
+        st = self._bad_state
+        st['host'].copy_(st['dev'], non_blocking=True)
+        st['event'] = torch.cuda.Event()
+        st['event'].record(torch.cuda.current_stream(st['dev'].device))
+
+    def _raise_bad_labels(self, n):
+        st = self._bad_state
+        st['dev'].zero_()
+        st['host'].zero_()
+        st['event'] = None
+        raise RuntimeError('index out of range in label map (%d pixels outside [0,%d) in an earlier batch; the '
+                           'reference\'s scatter_ raises on these)' % (n, self.num_labels))
+
+    def _poll_bad_labels(self):
+        st = getattr(self, '_bad_state', None)
+        if st is not None and st['event'] is not None and st['event'].query():
+            n = int(st['host'][0])
+            if n:
+                self._raise_bad_labels(n)
+
+    def check_labels(self):
+        """Synchronising form of the lazy check: raises if any batch since the last check had an out-of-range id."""
+        st = getattr(self, '_bad_state', None)
+        if st is not None:
+            n = int(st['dev'].item())
+            if n:
+                self._raise_bad_labels(n)
 
     # ------------------------------------------------------------------ training (pix2pixHD_model.py:451-460, 709-771)
     def _fast_inputs(self, x_dict):
@@ -317,7 +362,9 @@ class Pix2PixHDModel(nn.Module):
         if plain:
             label, inst, real_image = self._fast_inputs(x_dict)
             # one input-build launch gives the reference's input_label (for netD), a second one the stem operand
-            bad = torch.zeros(1, dtype=torch.int32, device=real_image.device)
+            # out-of-range ids are counted on the device; Pix2PixHDTrainer.step checks the counter behind its own
+            # .item() sync (check_labels), so the training step pays no extra synchronisation
+            bad = self._bad_counter(real_image.device)
             _, nchw = ops.build_input(label, inst, real_image, self.num_labels, nhwc=False, nchw=True, bad_count=bad)
             input_label = nchw[:, :self.num_labels + 1]
             fake_image = self.netG.forward_from_maps(label, inst, real_image, self.num_labels)

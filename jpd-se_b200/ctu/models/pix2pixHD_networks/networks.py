@@ -82,9 +82,10 @@ class _GeneratorFunction(torch.autograd.Function):
         reducer = module.grad_reducer
         if reducer is not None:
             reducer.begin([(n, p) for n, p in named])
-        grads = plan.backward(grad_out.contiguous().float(), shapes,
-                              on_grad=None if reducer is None else reducer.ready,
-                              alloc=None if reducer is None else reducer.alloc)
+        with torch.cuda.device(plan.device):
+            grads = plan.backward(grad_out.contiguous().float(), shapes,
+                                  on_grad=None if reducer is None else reducer.ready,
+                                  alloc=None if reducer is None else reducer.alloc)
         out = []
         for n, p in named:
             g = grads.get(n)
@@ -96,6 +97,8 @@ class _GeneratorFunction(torch.autograd.Function):
             out.append(g if p.requires_grad else None)
         if reducer is not None:
             reducer.finish()
+            if reducer.copy_out:  # accumulating into an existing .grad: never hand out views of the flat buffer
+                out = [None if g is None else g.clone() for g in out]
         return (None, None, None) + tuple(out)
 
 
@@ -206,10 +209,13 @@ class GlobalGenerator(nn.Module):
 
     def _run(self, batch, height, width, device, run):
         """Run `run(plan)`; with gradients enabled the call becomes one autograd node over all parameters."""
-        if not self._wants_grad():
-            return run(self.plan_for(batch, height, width, device)).clone()
-        plan = self.plan_for(batch, height, width, device, training=True)
-        return _GeneratorFunction.apply(self, plan, run, *self.parameters())
+        # define_G(..., gpu_ids=[k]) puts the net on cuda:k whatever the current device is (networks.py:52-53): launch on
+        # the tensors' device, like the reference's .cuda(gpu_ids[0]) path does
+        with torch.cuda.device(device):
+            if not self._wants_grad():
+                return run(self.plan_for(batch, height, width, device)).clone()
+            plan = self.plan_for(batch, height, width, device, training=True)
+            return _GeneratorFunction.apply(self, plan, run, *self.parameters())
 
     def forward(self, input, mode='get_continuous_img'):
         if mode == 'get_continuous_img':
@@ -222,19 +228,22 @@ class GlobalGenerator(nn.Module):
                 raise AttributeError('Generator: no binarizer found')
             self._check_runnable(input)
             B, _, H, W = input.shape
-            plan = self.plan_for(B, H, W, input.device)
-            return plan.binary_code_nchw(input.detach().contiguous().float()).clone()
+            with torch.cuda.device(input.device):
+                plan = self.plan_for(B, H, W, input.device)
+                return plan.binary_code_nchw(input.detach().contiguous().float()).clone()
         else:
             raise ValueError('Invalid generator mode: {}'.format(mode))
 
-    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
+    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0),
+                          bad_count=None):
         """Fused preprocess + generator: skips the (B,39,H,W) float tensor of pix2pixHD_model.py:595. A uint8 `image`
-        (raw decoder output) is normalised with (x/255 - mean)/std inside the input-build kernel."""
+        (raw decoder output) is normalised with (x/255 - mean)/std inside the input-build kernel. `bad_count`: optional
+        int32 device counter of class ids outside [0, num_labels) (scatter_ raises on those in the reference)."""
         self._check_runnable(image)
         B, _, H, W = image.shape
         image = image.detach()
         return self._run(B, H, W, image.device,
-                         lambda plan: plan.forward_from_maps(label, instance, image, num_labels, mean, std))
+                         lambda plan: plan.forward_from_maps(label, instance, image, num_labels, mean, std, bad_count))
 
 
 # ================================================================================================== training-only parts
@@ -353,17 +362,23 @@ class Vgg19(nn.Module):
     def __init__(self, requires_grad=False):
         super(Vgg19, self).__init__()
         from torchvision import models
-        # the reference calls models.vgg19(pretrained=True) (networks.py:477), which downloads on first use; offline
-        # boxes only have it if the checkpoint is already in the torch hub cache -- otherwise random weights keep the
-        # step runnable (the loss is still a fixed random-feature distance)
+        # The reference calls models.vgg19(pretrained=True) (networks.py:477), which downloads on first use. Offline the
+        # checkpoint must already be in the torch hub cache: silently training against a random-feature G_VGG loss
+        # (weighted by lambda_feat = 10) would diverge from the reference, so a missing checkpoint RAISES. Random
+        # weights are an explicit opt-in for benchmarks and tests (JPDSE_VGG_RANDOM=1; bench.py records it).
         wts = models.VGG19_Weights.IMAGENET1K_V1
         cached = os.path.join(torch.hub.get_dir(), 'checkpoints', os.path.basename(wts.url))
+        self.pretrained = True
         if os.path.isfile(cached) or os.environ.get('JPDSE_ALLOW_DOWNLOAD'):
             feats = models.vgg19(weights=wts).features
-        else:
-            import sys
-            print('jpdse_b200: pretrained VGG19 not in %s; using random weights' % os.path.dirname(cached), file=sys.stderr)
+        elif os.environ.get('JPDSE_VGG_RANDOM', '0') == '1':
+            self.pretrained = False
             feats = models.vgg19(weights=None).features
+        else:
+            raise JpdseError('jpdse_b200: the pretrained VGG19 checkpoint %s is not in the torch hub cache and this box '
+                             'is offline; the reference trains against vgg19(pretrained=True) (networks.py:477). Put the '
+                             'file there, or set JPDSE_VGG_RANDOM=1 to run with random VGG weights (benchmarks / tests '
+                             'only)' % cached)
         lo = 0
         for k, hi in enumerate(self.CUTS):
             seq = nn.Sequential()

@@ -102,12 +102,16 @@ class Pix2PixHDTrainer(BaseTrainer):
         self.steps_taken += 1
         if _opt(opt, 'anneal_lambda', False) and not (self.steps_taken % _opt(opt, 'anneal_interval', 5000)):
             self.lambda_distortion_weight *= _opt(opt, 'anneal_factor', 5.)
-        return loss_dict['G_Distortion'].item()
+        value = loss_dict['G_Distortion'].item()
+        self.model.check_labels()  # the device is already synchronised by .item(): raise like the reference's scatter_
+        return value
 
     def get_eval_loss(self, x_dict):
         self.eval()
         with torch.no_grad():
-            return self.model(x_dict, self.opt, mode='get_eval_loss').item()
+            value = self.model(x_dict, self.opt, mode='get_eval_loss').item()
+        self.model.check_labels()
+        return value
 
     def get_img(self, x_dict):
         # pix2pixHD_trainer.py:113-116
@@ -153,5 +157,16 @@ class Pix2PixHDTrainer(BaseTrainer):
             self.best_val_loss = states['best_val_loss']
             self.optimizer_G.load_state_dict(states['optimizer_G_state_dict'])
             self.optimizer_D.load_state_dict(states['optimizer_D_state_dict'])
-            if 'lambda_distortion_weight' in states:
-                self.lambda_distortion_weight = states['lambda_distortion_weight']
+            # pix2pixHD_trainer.py:158-175: schedulers under --schedule_lr, lambda weight under --anneal_lambda, both
+            # tolerant of checkpoints written without them
+            if _opt(self.opt, 'schedule_lr', False):
+                try:
+                    self.scheduler_G.load_state_dict(states['scheduler_G_state_dict'])
+                    self.scheduler_D.load_state_dict(states['scheduler_D_state_dict'])
+                except KeyError:
+                    print('Found no saved learning rate schedulers. New ones will be constructed...')
+            if _opt(self.opt, 'anneal_lambda', False):
+                try:
+                    self.lambda_distortion_weight = states['lambda_distortion_weight']
+                except KeyError:
+                    print('Found no saved lambda_distortion_weight. Resetting this weight to 1...')

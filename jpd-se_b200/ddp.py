@@ -31,6 +31,7 @@ class GradReducer:
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.flat = None
         self.stream = None
+        self.copy_out = False  # set by begin(): gradients must leave as copies (an earlier .grad exists)
         self.reset_stats()
 
     def reset_stats(self):
@@ -43,6 +44,21 @@ class GradReducer:
     def begin(self, named_params):
         total = sum((p.numel() + 3) // 4 * 4 for _, p in named_params if p.requires_grad)
         ref = next(p for _, p in named_params)
+        # Gradient accumulation: autograd's AccumulateGrad keeps the tensors `alloc` hands out WITHOUT copying, so after
+        # one backward every p.grad is a view of `flat`. A second backward without zero_grad(set_to_none=True) would
+        # overwrite those views in place and then add the same memory to itself (2*g2 instead of g1+g2). When a
+        # gradient is already present, detach it from `flat` first and hand this backward's gradients out as copies.
+        self.copy_out = False
+        if self.flat is not None:
+            lo = self.flat.data_ptr()
+            hi = lo + self.flat.numel() * 4
+            for _, p in named_params:
+                if p.grad is not None:
+                    self.copy_out = True
+                    if lo <= p.grad.data_ptr() < hi:
+                        p.grad = p.grad.clone()
+        elif any(p.grad is not None for _, p in named_params):
+            self.copy_out = True
         if self.flat is None or self.flat.numel() < total or self.flat.device != ref.device:
             self.flat = torch.empty(total, dtype=torch.float32, device=ref.device)
         if ref.is_cuda and self.stream is None:

@@ -153,6 +153,10 @@ class GeneratorPlan:
             self.d_pre = torch.zeros(B * (H + 12) * (W + 12) * 8 + 2048, dtype=torch.bfloat16, device=device)
         self.layers = []
         self.generation = 0
+        # tests: a dict here makes backward() keep copies of every layer's incoming / outgoing gradient (the rotating
+        # gradient buffers are overwritten as the walk proceeds), keyed by layer name -- used by the teacher-forced
+        # whole-network gradient check
+        self.capture = None
         self._codes_only = False  # mode='get_binary_code': stop behind the Binarizer
         # CUDA-graph replay of the inference forward (63 launches are host-bound below batch ~4: 2.5 -> ~1.2 ms at
         # batch 1); JPDSE_NO_GRAPH=1 or plan.use_graph = False runs every launch eagerly
@@ -313,17 +317,22 @@ class GeneratorPlan:
             return self._graphed(("nchw",), [inp], self._eager_nchw)
         return self._eager_nchw(inp)
 
-    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
+    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0),
+                          bad_count=None):
         """Fused preprocessing path: label ids + instance ids + image -> generator output. `image` is float32 (already
-        normalised) or uint8 (raw decoder output: (x/255 - mean)/std is applied inside the input-build kernel)."""
+        normalised) or uint8 (raw decoder output: (x/255 - mean)/std is applied inside the input-build kernel).
+        `bad_count`: optional persistent int32 device counter bumped for every class id outside [0, num_labels) (the
+        reference's scatter_ raises on those, pix2pixHD_model.py:381-382); the caller checks it lazily."""
         if num_labels + 4 != self.input_nc:
             raise JpdseError("num_labels + 4 must equal input_nc")
 
         def eager(lab, ins, img):
-            ops.build_input(lab, ins, img, num_labels, pad=3, c_pad=self.c_in_pad, out_nhwc=self.x0, mean=mean, std=std)
+            ops.build_input(lab, ins, img, num_labels, pad=3, c_pad=self.c_in_pad, out_nhwc=self.x0, mean=mean, std=std,
+                            bad_count=bad_count)
             return self.forward_from_x0()
         if self.use_graph:
-            key = ("maps", label.dtype, instance.dtype, image.dtype, num_labels, tuple(mean), tuple(std))
+            key = ("maps", label.dtype, instance.dtype, image.dtype, num_labels, tuple(mean), tuple(std),
+                   None if bad_count is None else bad_count.data_ptr())
             return self._graphed(key, [label, instance, image], eager)
         return eager(label, instance, image)
 
@@ -403,6 +412,8 @@ class GeneratorPlan:
         gi = 0
         g = self._view(self.g_buf[gi], B, H + 6, W + 6, self.ngf)
         self.dgrads[self.head_name].forward(d_pre, g)
+        if self.capture is not None:
+            self.capture[self.head_name] = {"g_in": g.clone()}
         g_pad = 3
         skip, skip_idx = None, None  # second gradient of the current layer's output (ResnetBlock skip connection)
         pending_idx = None           # dy buffer holding dL/dx_{k+1} until the walk reaches the producer of x_k
@@ -415,6 +426,8 @@ class GeneratorPlan:
             dy_idx = [i for i in range(3) if i != skip_idx and i != pending_idx][0]
             dy = self._view(self.dy_buf[dy_idx], B, h, w, c)
             sums = self._stats(si, c, self.bwd_sums)
+            if self.capture is not None:
+                self.capture[L.name] = {"g": g.clone(), "g_pad": g_pad, "skip": None if skip is None else skip.clone()}
             ops.instnorm_backward_reduce(g, g_pad, skip, L.raw, L.stats, dy, sums, B, h, w, c, L.relu)
             z = 2 if L.conv.kind == CONV3X3_PAD1 else 0
             slot = step & 1
@@ -435,6 +448,8 @@ class GeneratorPlan:
             oh, ow = L.dgrad.out_hw
             g = self._view(self.g_buf[gi], B, oh, ow, L.dgrad.cout)
             L.dgrad.forward(dx, g)
+            if self.capture is not None:
+                self.capture[L.name]["g_in"] = g.clone()  # gradient w.r.t. this layer's input as the conv saw it
             g_pad = self.layers[si - 1].out_pad
             skip, skip_idx = None, None
             if L.residual:
@@ -537,14 +552,17 @@ class SplitGeneratorPlan:
             raise JpdseError("plan built for %s, got %s" % ((self.B, self.input_nc, self.H, self.W), tuple(inp.shape)))
         return self._run(("nchw",), [inp], lambda p, x: p._eager_nchw(x))
 
-    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
+    def forward_from_maps(self, label, instance, image, num_labels, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0),
+                          bad_count=None):
         if num_labels + 4 != self.input_nc:
             raise JpdseError("num_labels + 4 must equal input_nc")
 
         def fn(p, lab, ins, img):
-            ops.build_input(lab, ins, img, num_labels, pad=3, c_pad=p.c_in_pad, out_nhwc=p.x0, mean=mean, std=std)
+            ops.build_input(lab, ins, img, num_labels, pad=3, c_pad=p.c_in_pad, out_nhwc=p.x0, mean=mean, std=std,
+                            bad_count=bad_count)
             return p.forward_from_x0()
-        key = ("maps", label.dtype, instance.dtype, image.dtype, num_labels, tuple(mean), tuple(std))
+        key = ("maps", label.dtype, instance.dtype, image.dtype, num_labels, tuple(mean), tuple(std),
+               None if bad_count is None else bad_count.data_ptr())
         return self._run(key, [label, instance, image], fn)
 
     def binary_code_nchw(self, inp):

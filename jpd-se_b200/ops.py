@@ -20,6 +20,7 @@ launch_count = 0
 
 
 _cached_stream = None
+_cached_dev = None
 
 
 def _stream():
@@ -34,14 +35,15 @@ class stream_cached:
     the sequence inside the block must stay on the stream that was current on entry."""
 
     def __enter__(self):
-        global _cached_stream
-        self.prev = _cached_stream
+        global _cached_stream, _cached_dev
+        self.prev = (_cached_stream, _cached_dev)
+        _cached_dev = torch.cuda.current_device()
         _cached_stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         return self
 
     def __exit__(self, *exc):
-        global _cached_stream
-        _cached_stream = self.prev
+        global _cached_stream, _cached_dev
+        _cached_stream, _cached_dev = self.prev
         return False
 
 
@@ -52,6 +54,11 @@ def _ptr(t):
 def _need(t, name, dtype=None):
     if not isinstance(t, torch.Tensor) or not t.is_cuda:
         raise JpdseError("%s must be a CUDA tensor (jpdse_b200 has no CPU path)" % name)
+    # the launch goes to the CURRENT device's current stream: a tensor of another GPU would be a foreign pointer there
+    cur = _cached_dev if _cached_dev is not None else torch.cuda.current_device()
+    if t.device.index != cur:
+        raise JpdseError("%s lives on cuda:%d but the current device is cuda:%d; run the call under "
+                         "torch.cuda.device(%d)" % (name, t.device.index, cur, t.device.index))
     if not t.is_contiguous():
         raise JpdseError("%s must be contiguous" % name)
     if dtype is not None and t.dtype != dtype:

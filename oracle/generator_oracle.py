@@ -155,3 +155,16 @@ def tensor2im_uint8(x, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
     a = np.transpose(a, (1, 2, 0))
     a = (a * np.asarray(std) + np.asarray(mean)) * 255.0
     return np.clip(a, 0, 255).astype(np.uint8)
+
+
+def eval_distortion(recon, real, mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0), mode="l1"):
+    """Pix2PixHDModel.get_eval_loss, ctu/models/pix2pixHD_model.py:636-641: both (B,3,H,W) images go through tensor2im
+    (uint8 truncation), back to float, then nn.L1Loss / nn.MSELoss (mean). Restated as the EXACT integer sum of
+    |a-b| (or (a-b)^2) over the bytes divided once by the element count, rounded to float32 -- what the device kernel
+    (jpdse_distortion_u8) computes. The reference's float32 mean accumulates in floating point, so it can differ from
+    this exact value in the last bits on large images; pin_against_reference.py measures that gap (<= 2 float32 ulp
+    at the pinned sizes, 0 where every partial sum stays below 2^24)."""
+    a = np.stack([tensor2im_uint8(x, mean, std) for x in recon]).astype(np.int64)
+    b = np.stack([tensor2im_uint8(x, mean, std) for x in real]).astype(np.int64)
+    d = np.abs(a - b) if mode == "l1" else (a - b) ** 2
+    return np.float32(np.float64(int(d.sum())) / np.float64(d.size))

@@ -124,6 +124,33 @@ def main():
     G.eval()
     print("generator backward: oracle autograd == reference autograd (bit-exact); golden gradient checksums written")
 
+    # ---------------------------------------------------------------- eval-metric path
+    # tensor2im (ctu/utils/misc.py:64-95) and the distortion get_eval_loss takes on its bytes (pix2pixHD_model.py:636-641)
+    from ctu.utils import misc
+    eopt = types.SimpleNamespace(normalize_mean=[0.5, 0.5, 0.5], normalize_std=[1.0, 1.0, 1.0])
+    for (eb, eh, ew) in ((2, 24, 40), (1, 256, 512)):
+        ra = (torch.rand(eb, 3, eh, ew, generator=g) - 0.5) * 1.2   # some values outside [-0.5, 0.5]: the clip matters
+        rb = (ra + torch.randn(eb, 3, eh, ew, generator=g) * 0.05)
+        ra[0, :, 0, :4] = torch.tensor([-0.5, 0.5, 0.49999997, 1.0 / 255 - 0.5])  # exact byte boundaries
+        ia, ib = misc.tensor2im(ra, eopt), misc.tensor2im(rb, eopt)
+        oa = np.stack([orc.tensor2im_uint8(x_, eopt.normalize_mean, eopt.normalize_std) for x_ in ra])
+        ob = np.stack([orc.tensor2im_uint8(x_, eopt.normalize_mean, eopt.normalize_std) for x_ in rb])
+        assert ia.dtype == np.uint8 and np.array_equal(ia, oa) and np.array_equal(ib, ob), "oracle tensor2im != reference"
+        ta = torch.tensor(ia.transpose(0, 3, 1, 2)).to(torch.float)
+        tb = torch.tensor(ib.transpose(0, 3, 1, 2)).to(torch.float)
+        for mode, crit in (("l1", torch.nn.L1Loss()), ("mse", torch.nn.MSELoss())):
+            ref_loss = np.float32(crit(ta, tb).item())
+            got_loss = orc.eval_distortion(ra, rb, eopt.normalize_mean, eopt.normalize_std, mode)
+            ulp = abs(int(ref_loss.view(np.int32)) - int(got_loss.view(np.int32)))
+            assert ulp <= 2, "eval %s loss: oracle %r vs reference %r (%d ulp)" % (mode, got_loss, ref_loss, ulp)
+            print("eval-loss %s at %dx%dx%d: reference %.9g, exact-integer oracle %.9g (%d float32 ulp)" % (
+                mode, eb, eh, ew, ref_loss, got_loss, ulp))
+        if eb == 2:
+            np.savez_compressed(os.path.join(GOLDEN, "eval_metric.npz"), a=ra.numpy(), b=rb.numpy(), a_u8=ia, b_u8=ib,
+                                l1=np.float32(torch.nn.L1Loss()(ta, tb).item()),
+                                mse=np.float32(torch.nn.MSELoss()(ta, tb).item()))
+    print("eval metric: oracle tensor2im == reference (bit-exact bytes); L1 / MSE within 2 float32 ulp; golden written")
+
     # ---------------------------------------------------------------- training-step networks of the mirror
     torch.manual_seed(7)
     Dr = networks.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[])

@@ -85,3 +85,42 @@ def test_grad_reducer_single_process_is_a_noop_allocator():
         assert torch.equal(g, torch.full_like(g, float(i + 1)))
         assert g.data_ptr() % 16 == 0
     assert red.launched[-1][1] == red._offset
+
+
+def test_grad_reducer_second_backward_without_set_to_none_accumulates():
+    """autograd keeps the reducer's views as p.grad; a second backward (gradient accumulation, or
+    zero_grad(set_to_none=False)) must neither overwrite those views nor add the flat buffer to itself."""
+    ddp = importlib.import_module("jpd-se_b200.ddp")
+    red = ddp.GradReducer(bucket_bytes=1 << 20)
+    params = [(n, torch.nn.Parameter(torch.zeros(s))) for n, s in SHAPES]
+
+    def backward(scale):
+        red.begin(params)
+        outs = []
+        for i, (name, shape) in enumerate(SHAPES):
+            t = red.alloc(name, shape)
+            t.copy_(torch.full(shape, float(i + 1) * scale))
+            red.ready(name, t)
+            outs.append(t)
+        red.finish()
+        if red.copy_out:  # what _GeneratorFunction.backward does
+            outs = [t.clone() for t in outs]
+        for (_, p), g in zip(params, outs):  # AccumulateGrad: steal when empty, add in place otherwise
+            if p.grad is None:
+                p.grad = g
+            else:
+                p.grad += g
+
+    backward(1.0)
+    assert not red.copy_out
+    assert all(p.grad.data_ptr() >= red.flat.data_ptr() for _, p in params)  # first backward: zero-copy views
+    backward(10.0)
+    assert red.copy_out
+    lo, hi = red.flat.data_ptr(), red.flat.data_ptr() + red.flat.numel() * 4
+    for i, (_, p) in enumerate(params):
+        assert not (lo <= p.grad.data_ptr() < hi)
+        assert torch.equal(p.grad, torch.full_like(p, 11.0 * (i + 1)))
+    for _, p in params:
+        p.grad = None
+    backward(2.0)
+    assert not red.copy_out

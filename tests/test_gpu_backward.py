@@ -308,6 +308,89 @@ def test_generator_gradients_vs_oracle(cuda, n_down, n_blocks, B, H, W):
     print("worst cosine: %.5f (bf16 oracle) %.5f (fp32 reference)" % (worst16, worst32))
 
 
+@pytest.mark.parametrize("n_down,n_blocks,B,H,W", [(2, 1, 2, 32, 64), (4, 2, 1, 128, 256), (4, 9, 1, 64, 128)])
+def test_generator_gradients_teacher_forced(cuda, n_down, n_blocks, B, H, W):
+    """Whole-network gradient check at SURVEY.md 8c's stated tolerance (cosine >= 0.999 per tensor).
+
+    The end-to-end comparison above cannot reach 0.999 with ANY bf16 forward (rounding flips ReLU masks / shifts
+    InstanceNorm statistics and the difference is amplified layer by layer), so a few-percent scaling bug in one
+    layer's data gradient could hide inside its calibrated gate. Here every layer is checked IN CONTEXT instead: the
+    checker is CPU fp32 autograd of the reference's ops for that layer (ReflectionPad2d / Conv2d / ConvTranspose2d /
+    InstanceNorm2d / ReLU / Tanh, networks.py:198-305) evaluated on OUR saved input activation and raw conv output of
+    the real training forward, fed OUR incoming gradient of the real backward; its weight gradient and its gradient
+    w.r.t. the layer input must match what the kernels produced. Errors cannot accumulate across layers, so the gate
+    is tight: cosine >= 0.999 and norm ratio within 2 % for every weight gradient and every inter-layer gradient."""
+    from jpdse_b200._lib import CONV3X3_PAD1, CONV3X3_S2, CONV7X7_PAD3, CONVT3X3_S2
+    nw = _networks()
+    torch.manual_seed(99)
+    net = nw.define_G(39, 3, 64, "global", n_down, n_blocks, 1, 3, "instance", gpu_ids=[0]).train()
+    gen = torch.Generator().manual_seed(17)
+    x = torch.randn(B, 39, H, W, generator=gen).to(cuda)
+    target = (torch.rand(B, 3, H, W, generator=gen) - 0.5).to(cuda)
+    y = net(x)
+    grad_out = []
+    y.register_hook(lambda g_: grad_out.append(g_.detach().clone()))
+    plan = net.plan_for(B, H, W, x.device, training=True)
+    plan.capture = {}
+    (10.0 * (y - target).abs().mean() + (y * y).mean()).backward()
+    torch.cuda.synchronize()
+    cap, layers = plan.capture, list(plan.layers)
+    plan.capture = None
+    params = dict(net.named_parameters())
+
+    def nchw(t):
+        return t.detach().float().permute(0, 3, 1, 2).cpu().contiguous()
+
+    def check(name, got, ref, what):
+        c = _cos(got, ref)
+        ratio = float(got.double().norm() / (ref.double().norm() + 1e-30))
+        assert c >= 0.999 and 0.98 <= ratio <= 1.02, "%s %s: cosine %.6f, norm ratio %.4f" % (name, what, c, ratio)
+        return c
+
+    worst = 1.0
+    for si, L in enumerate(layers):
+        rec = cap[L.name]
+        X = nchw(L.x_in).requires_grad_(True)
+        Wt = params[L.name + ".weight"].detach().cpu().clone().requires_grad_(True)
+        kind, ip = L.conv.kind, L.conv.desc.in_pad
+        if kind == CONV7X7_PAD3:
+            conv = F.conv2d(X[:, :39], Wt)
+        elif kind == CONV3X3_PAD1:
+            conv = F.conv2d(X, Wt)
+        else:
+            Xi = X[:, :, ip:X.shape[2] - ip, ip:X.shape[3] - ip] if ip else X
+            conv = F.conv2d(Xi, Wt, stride=2, padding=1) if kind == CONV3X3_S2 else \
+                F.conv_transpose2d(Xi, Wt, stride=2, padding=1, output_padding=1)
+        raw = nchw(L.raw)
+        assert float((conv.detach() - raw).abs().max()) <= 2.0 ** -7 * float(raw.abs().max()) + 1e-6  # same forward
+        yv = conv + (raw - conv).detach()  # masks / statistics from OUR stored raw output, gradient through the conv
+        z = F.instance_norm(yv, eps=1e-5)
+        if L.relu:
+            z = F.relu(z)
+        gp = rec["g_pad"]
+        G = nchw(rec["g"])
+        full = F.pad(z, (gp, gp, gp, gp), mode="reflect") if gp else z
+        obj = (full * G).sum()
+        if rec["skip"] is not None:
+            obj = obj + (z * nchw(rec["skip"])).sum()
+        obj.backward()
+        worst = min(worst, check(L.name, params[L.name + ".weight"].grad.cpu(), Wt.grad, "weight gradient"))
+        if si > 0:
+            ref_in = X.grad[:, :, ip:X.shape[2] - ip, ip:X.shape[3] - ip] if (ip and kind != CONV3X3_PAD1) else X.grad
+            worst = min(worst, check(L.name, nchw(rec["g_in"]), ref_in, "input gradient"))
+    # head: ReflectionPad2d(3) was materialised by the producer; Conv2d(64, 3, 7) + bias + Tanh
+    hn = plan.head_name
+    X = nchw(plan.head_in).requires_grad_(True)
+    Wt = params[hn + ".weight"].detach().cpu().clone().requires_grad_(True)
+    bt = params[hn + ".bias"].detach().cpu().clone().requires_grad_(True)
+    out = torch.tanh(F.conv2d(X, Wt, bt))
+    (out * grad_out[0].cpu()).sum().backward()
+    worst = min(worst, check(hn, params[hn + ".weight"].grad.cpu(), Wt.grad, "weight gradient"))
+    worst = min(worst, check(hn, params[hn + ".bias"].grad.cpu(), bt.grad, "bias gradient"))
+    worst = min(worst, check(hn, nchw(cap[hn]["g_in"]), X.grad, "input gradient"))
+    print("teacher-forced worst cosine over %d layers: %.6f" % (len(layers) + 1, worst))
+
+
 def test_generator_backward_guards(cuda):
     import jpdse_b200
     nw = _networks()
@@ -323,12 +406,13 @@ def test_generator_backward_guards(cuda):
         assert not net(x).requires_grad
 
 
-def test_trainer_step_runs_and_learns(cuda, tmp_path):
+def test_trainer_step_runs_and_learns(cuda, tmp_path, monkeypatch):
     """Pix2PixHDTrainer.step (ctu/trainers/pix2pixHD_trainer.py:42-85) end to end: losses finite, all parameters of G
     and D move, and a few steps on one batch reduce the distortion."""
     import importlib
     import bench
     tr = importlib.import_module("jpd-se_b200.ctu.trainers.pix2pixHD_trainer")
+    monkeypatch.setenv("JPDSE_VGG_RANDOM", "1")  # no pretrained VGG19 checkpoint offline: explicit opt-in to random weights
     opt = bench.make_opt()
     opt.is_train, opt.n_downsample_global, opt.n_blocks_global = True, 2, 2
     opt.no_vgg_loss, opt.quiet, opt.save_dir, opt.checkpoints_dir = False, True, str(tmp_path), str(tmp_path)

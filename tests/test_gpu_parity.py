@@ -283,6 +283,34 @@ def test_generator_full_architecture(cuda):
     assert float(y_maps.abs().max()) < 1.0  # tanh range
 
 
+@pytest.mark.parametrize("H,W", [(512, 1024), (1024, 2048)])
+def test_generator_vs_oracle_at_baseline_sizes(cuda, H, W):
+    """BASELINE.json configs[1] / configs[2] image sizes (1024x512 and 2048x1024), full 4-down / 9-block generator with
+    the bench's weights (seed 1234) and synthetic inputs, batch 1: the sm_100a path against the fp32 CPU oracle
+    (oracle/generator_oracle.py, pinned bit-identical to the reference) under the stated bf16 gate. The image is also
+    run as image 1 of a batch of 2 (the batch the timed plans run is a multiple of this; InstanceNorm is per sample) and
+    must come out bit-identical, which carries the oracle check over to every image slot of a batch."""
+    import bench
+    nw = _networks()
+    torch.manual_seed(1234)
+    net = nw.define_G(39, 3, 64, "global", 4, 9, 1, 3, "instance", gpu_ids=[]).eval()
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    label, inst, image = bench.synth_inputs(2, H, W, seed=1234)
+    x = torch.from_numpy(orc.build_input(label[1:].numpy(), inst[1:].numpy(), image[1:].numpy(), 35))
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        ref = orc.generator_forward(sd, x, 4, 9)
+        net = net.to(cuda)
+        one = net.forward_from_maps(label[1:].to(cuda), inst[1:].to(cuda), image[1:].to(cuda), 35).cpu()
+        two = net.forward_from_maps(label.to(cuda), inst.to(cuda), image.to(cuda), 35).cpu()
+    assert torch.equal(two[1:], one)
+    err = (one - ref).abs()
+    p = orc.psnr(one, ref)
+    print("%dx%d vs fp32 oracle: max abs %.4f mean abs %.5f psnr %.2f dB" % (W, H, float(err.max()), float(err.mean()), p))
+    assert float(err.mean()) <= 0.02 and float(err.max()) <= 0.15 and p >= 39.2
+    assert float(one.abs().max()) < 1.0
+
+
 @pytest.mark.parametrize("B,H,W", [(2, 48, 80), (1, 144, 272), (1, 96, 1552)])
 def test_generator_sizes_off_the_tile_grid(cuda, B, H, W):
     """Image sizes the reference accepts (multiples of 16) whose pixel grids are not whole 128-pixel tiles at some or
@@ -491,6 +519,18 @@ def test_tensor2im_and_distortion_bit_exact(cuda):
             want = np.abs(d).mean() if mode == "l1" else (d * d).mean()
             val = float(ops.distortion_u8(a.to(cuda), b.to(cuda), mode, mean, std))
             assert val == want, (mode, val, want)
+
+
+def test_eval_metric_matches_reference_golden(cuda, golden_dir):
+    """The reference's own numbers (tests/golden/eval_metric.npz, written by oracle/pin_against_reference.py from
+    ctu.utils.misc.tensor2im + nn.L1Loss / nn.MSELoss): device bytes bit-exact, losses equal as float32."""
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "eval_metric.npz"))
+    a, b = torch.from_numpy(g["a"]).to(cuda), torch.from_numpy(g["b"]).to(cuda)
+    assert np.array_equal(ops.tensor2im_u8(a).cpu().numpy(), g["a_u8"])
+    assert np.array_equal(ops.tensor2im_u8(b).cpu().numpy(), g["b_u8"])
+    assert np.float32(float(ops.distortion_u8(a, b, "l1"))) == g["l1"]
+    assert np.float32(float(ops.distortion_u8(a, b, "mse"))) == g["mse"]
 
 
 def test_cuda_graph_replay_equals_eager_launches(cuda):

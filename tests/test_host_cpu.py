@@ -166,8 +166,35 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the unmodified reference from baseline/_ref when it is installed (tools/install_reference.sh), else the oracle port
+    want_kind = "reference" if os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "ctu", "__init__.py")) else "port"
+    assert d["cpu_baseline"]["kind"] == want_kind and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["steps"] == 1 and d["warmup"] == 0 and "workload" in d["config"]
     r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "ctu", "__init__.py")),
+                    reason="reference not installed in baseline/_ref (tools/install_reference.sh)")
+def test_installed_reference_trainer_equals_oracle_bit_for_bit():
+    """The reference arm of bench.py: the UNMODIFIED reference (baseline/_ref) driven through its own parser ->
+    get_trainer -> Pix2PixHDTrainer.get_img must give the oracle's output bit for bit on CPU (same torch ops)."""
+    import subprocess
+    import sys
+    code = (
+        "import sys, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import bench, reference_arm as ra\n"
+        "from oracle import generator_oracle as orc\n"
+        "t, opt = ra.build_test_trainer(extra=['--n_blocks_global', '2', '--n_downsample_global', '3'])\n"
+        "l8, i16, u8, img = bench.synth_inputs_compact(2, 64, 128)\n"
+        "y = t.get_img({'label': l8.float(), 'instance': i16.int(), 'image': img.clone(), 'path': ['a', 'b']})\n"
+        "x = torch.from_numpy(orc.build_input(l8.float().numpy(), i16.int().numpy(), img.numpy(), 35))\n"
+        "with torch.no_grad():\n"
+        "    ref = orc.generator_forward(t.model.netG.state_dict(), x, 3, 2)\n"
+        "assert type(t.model.netG).__module__ == 'ctu.models.pix2pixHD_networks.networks'\n"
+        "assert torch.equal(y, ref), float((y - ref).abs().max())\n"
+        "print('REFERENCE_EQUALS_ORACLE')\n" % (ROOT, os.path.join(ROOT, "tools")))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert r.returncode == 0 and "REFERENCE_EQUALS_ORACLE" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]

@@ -116,3 +116,14 @@ def test_s2hvq_golden(golden_dir):
 
 def test_code_bits():
     assert qorc.code_bits(np.array([-1.0, 1.0, 0.0], dtype=np.float32)).tolist() == [0, 1, 0]
+
+
+def test_eval_metric_golden(golden_dir):
+    """tensor2im bytes and the eval L1 / MSE of the reference (ctu/utils/misc.py:64-95, pix2pixHD_model.py:636-641),
+    stored by oracle/pin_against_reference.py from the imported reference."""
+    g = np.load(os.path.join(golden_dir, "eval_metric.npz"))
+    a, b = torch.from_numpy(g["a"]), torch.from_numpy(g["b"])
+    assert np.array_equal(np.stack([orc.tensor2im_uint8(t) for t in a]), g["a_u8"])
+    assert np.array_equal(np.stack([orc.tensor2im_uint8(t) for t in b]), g["b_u8"])
+    assert orc.eval_distortion(a, b, mode="l1") == g["l1"]   # sums below 2^24: the reference's float32 mean is exact
+    assert orc.eval_distortion(a, b, mode="mse") == g["mse"]

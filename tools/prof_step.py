@@ -1,3 +1,5 @@
+import os
+os.environ.setdefault("JPDSE_VGG_RANDOM", "1")  # offline box: no pretrained VGG19 checkpoint
 import importlib, sys, os, torch
 sys.path.insert(0, '/root/repo')
 import jpdse_b200, bench

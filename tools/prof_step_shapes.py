@@ -1,3 +1,5 @@
+import os
+os.environ.setdefault("JPDSE_VGG_RANDOM", "1")  # offline box: no pretrained VGG19 checkpoint
 """Developer probe: which tensor shapes the PyTorch-side copies / adds of a trainer.step come from."""
 import importlib, sys, os, torch
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))

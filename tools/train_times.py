@@ -5,6 +5,7 @@
 import argparse
 import importlib
 import os
+os.environ.setdefault("JPDSE_VGG_RANDOM", "1")  # offline box: no pretrained VGG19 checkpoint
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
