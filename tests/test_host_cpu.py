@@ -198,3 +198,18 @@ def test_installed_reference_trainer_equals_oracle_bit_for_bit():
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
     assert r.returncode == 0 and "REFERENCE_EQUALS_ORACLE" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+def test_vgg_refuses_silent_random_weights(monkeypatch):
+    """without the pretrained checkpoint in the hub cache Vgg19 must raise, unless JPDSE_VGG_RANDOM=1."""
+    nw = importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
+    cached = os.path.join(torch.hub.get_dir(), "checkpoints", "vgg19-dcbb9e9d.pth")
+    if os.path.isfile(cached):
+        pytest.skip("pretrained VGG19 present")
+    monkeypatch.delenv("JPDSE_VGG_RANDOM", raising=False)
+    monkeypatch.delenv("JPDSE_ALLOW_DOWNLOAD", raising=False)
+    import jpdse_b200
+    with pytest.raises(jpdse_b200.JpdseError):
+        nw.Vgg19()
+    monkeypatch.setenv("JPDSE_VGG_RANDOM", "1")
+    assert nw.Vgg19().pretrained is False
