@@ -83,13 +83,25 @@ enum jpdse_conv_kind {
   /* (B,H+4,W+4,Cin) -> y (B,H+2,W+2,Cout) = gradient w.r.t. the PADDED forward input. The weight    */
   /* handed to jpdse_conv_pack_weights is the FORWARD conv's (Cin_this = Cout_fwd, Cout_this = Cin_fwd) */
   JPDSE_CONV3X3_FULL = 5,
-  JPDSE_CONV7X7_FULL = 6    /* x (B,H+12,W+12,Cin) with Cin*2 bytes a multiple of 16 and 7*Cin <= 64 */
+  JPDSE_CONV7X7_FULL = 6,   /* x (B,H+12,W+12,Cin) with Cin*2 bytes a multiple of 16 and 7*Cin <= 64 */
+  /* PatchGAN discriminator convs (networks.py:430-449: kernel 4, zero padding 2). x is stored with a ZERO border  */
+  /* of 2 (in_pad must be 2): (B,H+4,W+4,Cin); any H, W (the discriminator runs on 257x513, 129x257, 65x129 ...).  */
+  JPDSE_CONV4X4_S2 = 7,       /* stride 2: out (B, H/2+1, W/2+1, Cout)                                              */
+  JPDSE_CONV4X4_S1 = 8,       /* stride 1: out (B, H+1, W+1, Cout)                                                  */
+  /* their data gradients. x = gradient w.r.t. the conv OUTPUT, zero border 2: (B,h+4,w+4,Cin = Cout_fwd), in_h/in_w */
+  /* = h, w; y = gradient w.r.t. the forward INPUT, dense (B,out_h,out_w,Cout = Cin_fwd). The weight handed to       */
+  /* jpdse_conv_pack_weights is the FORWARD conv's (Cout_fwd, Cin_fwd_real, 4, 4); cin_real = Cout_fwd real channels. */
+  JPDSE_CONV4X4_S2_DGRAD = 9, /* four output-phase GEMMs; out_h/out_w (forward input size: 2h-2 or 2h-1) are required */
+  JPDSE_CONV4X4_S1_FULL = 10  /* out (B, h-1, w-1, Cout)                                                            */
 };
 enum jpdse_conv_epilogue {
   JPDSE_EPI_RAW_STATS = 0,      /* y = bf16 NHWC raw conv output, stats += (sum, sumsq) per (b,c)    */
   JPDSE_EPI_BIAS_TANH_NCHW = 1, /* y = float32 NCHW tanh(conv + bias)            (networks.py:246)   */
   JPDSE_EPI_SIGN_NCHW = 2,      /* y = float32 NCHW sign(tanh(conv))             (binarize.py:51-54) */
-  JPDSE_EPI_RAW = 3             /* y = bf16 NHWC, no statistics (gradients)                           */
+  JPDSE_EPI_RAW = 3,            /* y = bf16 NHWC, no statistics (gradients)                           */
+  JPDSE_EPI_BIAS_ACT = 4,       /* y = bf16 NHWC LeakyReLU_slope(conv + bias) (slope 0 = ReLU): PatchGAN layer 0 */
+                                /* (networks.py:430) and the VGG19 convs (:474-504)                    */
+  JPDSE_EPI_BIAS_NCHW = 5       /* y = float32 NCHW conv + bias: the PatchGAN's 1-channel output conv (:447) */
 };
 typedef struct jpdse_conv_desc {
   int kind;      /* enum jpdse_conv_kind */
@@ -101,6 +113,13 @@ typedef struct jpdse_conv_desc {
   int cin;        /* input channels as stored (multiple of 64, or 40 for the stem) */
   int cin_real;   /* channels of the torch weight (<= cin); extra stored channels multiply zero weights */
   int cout;       /* output channels */
+  /* ---- ABI version 2 */
+  int out_pad;    /* bf16 NHWC epilogues: y is (B, out_h+2*out_pad, out_w+2*out_pad, cout) and only its interior is  */
+                  /* written (the border belongs to the caller: zero for the next zero-padded conv)                 */
+  int out_h, out_w; /* explicit output size, only read by JPDSE_CONV4X4_S2_DGRAD (0 elsewhere)                      */
+  float slope;    /* JPDSE_EPI_BIAS_ACT: negative slope of the LeakyReLU (0.2 PatchGAN, 0 = ReLU)                     */
+  int cout_real;  /* data-gradient kinds 9 / 10: input channels of the FORWARD weight (<= cout; 0 = cout); output     */
+                  /* channels beyond it are written as zeros                                                       */
 } jpdse_conv_desc;
 
 /* Bytes of the packed (bf16, K-major, tap-blocked) weight buffer for this conv. 0 on error. */
@@ -154,6 +173,10 @@ int jpdse_instnorm_backward_reduce(const void* g, int g_pad, const void* skip, c
 int jpdse_instnorm_backward_apply(const void* dy, const void* raw, const double* stats,
                                   const double* sums, void* dx, int dx_pad, int batch, int height,
                                   int width, int channels, float eps, void* stream);
+/* Same with a LeakyReLU(slope) mask instead of ReLU (PatchGAN, networks.py:436-445): dy = (xhat > 0 ? 1 : slope) * (...). */
+int jpdse_instnorm_backward_reduce_act(const void* g, int g_pad, const void* skip, const void* raw,
+                                       const double* stats, void* dy, double* sums, int batch, int height,
+                                       int width, int channels, int relu, float slope, float eps, void* stream);
 /* Head: nn.Tanh backward (networks.py:246). grad_out / out: float32 NCHW (B,channels<=8,H,W);
  * d_pre: bf16 (B,H+12,W+12,8) = grad_out * (1 - out^2), zero border 6, channels >= `channels` zero;
  * dbias: float32 (channels) += sum over (B,H,W) of d_pre (zeroed by the caller). */
@@ -174,6 +197,47 @@ int jpdse_tanh_backward_nchw(const float* grad_out, const float* out, void* d_pr
 int jpdse_instnorm_apply(const void* raw, const double* stats, const void* residual, void* out,
                          int batch, int height, int width, int channels, int pad, int relu,
                          float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * PatchGAN discriminator + feature losses of the training step:
+ * MultiscaleDiscriminator / NLayerDiscriminator (networks.py:371-471), discriminate (pix2pixHD_model.py:451-460),
+ * feature matching (:746-753), VGGLoss / Vgg19 (networks.py:124-139, 474-504). The convolutions are jpdse_conv_forward /
+ * jpdse_conv_wgrad with the JPDSE_CONV4X4_* kinds (VGG: JPDSE_CONV3X3_PAD1 on zero-bordered tensors, JPDSE_EPI_BIAS_ACT).
+ *
+ * d_input: out (B, Ho+2*out_pad, Wo+2*out_pad, c_pad) bf16, interior = cat(a, b) over channels (a: float32 (B,ca,H,W),
+ *   b: float32 (B,cb,H,W) or NULL) -- the reference's torch.cat((input_label, image), dim=1) -- channels >= ca+cb zero;
+ *   pool = 1 first applies nn.AvgPool2d(3, stride=2, padding=1, count_include_pad=False) (networks.py:387): Ho = (H-1)/2+1.
+ *   The border is NOT written (the caller keeps it zero).
+ * d_input_backward: out float32 (B,c,H,W) = g0[..., c0:c0+c] + AvgPool backward of g1[..., c0:c0+c]; g0 dense bf16
+ *   (B,H,W,c_stored) = gradient w.r.t. the full-resolution input, g1 dense (B,(H-1)/2+1,(W-1)/2+1,c_stored) or NULL.
+ */
+int jpdse_d_input(const float* a, int ca, const float* b, int cb, void* out, int batch, int height, int width,
+                  int c_pad, int pool, int out_pad, void* stream);
+int jpdse_d_input_backward(const void* g0, const void* g1, float* out, int batch, int height, int width,
+                           int c_stored, int c0, int c, void* stream);
+/* InstanceNorm2d apply + LeakyReLU(slope): out (B,H+2*out_pad,W+2*out_pad,C) bf16 with a ZERO border (written). */
+int jpdse_instnorm_apply_act(const void* raw, const double* stats, void* out, int batch, int height, int width,
+                             int channels, int out_pad, float slope, float eps, void* stream);
+/* Backward through y = LeakyReLU_slope(conv + bias) (no norm): d_pre = (g + skip) * (f > 0 ? 1 : slope).
+ *   g, skip (optional): dense bf16 (B,H,W,C); f: the stored activation (B,H+2*f_pad,W+2*f_pad,C);
+ *   d_pre: bf16 (B,H+2*out_pad,W+2*out_pad,C), zero border written; dbias (optional): float32 (C) += sum of d_pre. */
+int jpdse_act_backward(const void* g, const void* skip, const void* f, void* d_pre, float* dbias, int batch,
+                       int height, int width, int channels, int f_pad, int out_pad, float slope, void* stream);
+/* nn.L1Loss numerator between two bf16 tensors of one stored shape: *sum += sum |a - b| over n_elements (borders and pad
+ * channels are zero in both). Backward: out dense bf16 (B,H,W,C) = sign(a - b) * (*scale_dev) * scale_host, a / b stored
+ * with a border of `pad` (scale_dev: optional device scalar, e.g. the upstream gradient). */
+int jpdse_l1_pair(const void* a, const void* b, size_t n_elements, double* sum, void* stream);
+int jpdse_l1_pair_backward(const void* a, const void* b, void* out, const float* scale_dev, float scale_host,
+                           int batch, int height, int width, int channels, int pad, void* stream);
+/* nn.MaxPool2d(2, 2) (torchvision VGG19): x (B,H+2*in_pad,W+2*in_pad,C) -> y (B,H/2+2*out_pad,W/2+2*out_pad,C), zero border
+ * written. Backward: dx dense (B,H,W,C) = g (dense (B,H/2,W/2,C)) at the first maximum of each window, else 0. */
+int jpdse_maxpool2x2(const void* x, void* y, int batch, int height, int width, int channels, int in_pad,
+                     int out_pad, void* stream);
+int jpdse_maxpool2x2_backward(const void* x, const void* g, void* dx, int batch, int height, int width,
+                              int channels, int in_pad, void* stream);
+/* Stored bf16 (B,H+2*pad,W+2*pad,c_stored) -> float32 NCHW (B,channels,H,W) (feature maps handed back to PyTorch). */
+int jpdse_nhwc_pad_to_nchw_f32(const void* x, float* y, int batch, int channels, int height, int width, int pad,
+                               int c_stored, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout helpers used at the boundary (reference tensors are NCHW float32).

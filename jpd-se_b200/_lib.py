@@ -15,12 +15,16 @@ c_void_p, c_int, c_float, c_size_t, c_double = (
 class ConvDesc(ctypes.Structure):
     """struct jpdse_conv_desc"""
     _fields_ = [("kind", c_int), ("epilogue", c_int), ("batch", c_int), ("in_h", c_int), ("in_w", c_int),
-                ("in_pad", c_int), ("cin", c_int), ("cin_real", c_int), ("cout", c_int)]
+                ("in_pad", c_int), ("cin", c_int), ("cin_real", c_int), ("cout", c_int),
+                # ABI version 2
+                ("out_pad", c_int), ("out_h", c_int), ("out_w", c_int), ("slope", c_float), ("cout_real", c_int)]
 
 
 # enum jpdse_conv_kind / jpdse_conv_epilogue
-CONV3X3_PAD1, CONV3X3_S2, CONVT3X3_S2, CONV7X7_PAD3, CONV1X1, CONV3X3_FULL, CONV7X7_FULL = range(7)
-EPI_RAW_STATS, EPI_BIAS_TANH_NCHW, EPI_SIGN_NCHW, EPI_RAW = range(4)
+(CONV3X3_PAD1, CONV3X3_S2, CONVT3X3_S2, CONV7X7_PAD3, CONV1X1, CONV3X3_FULL, CONV7X7_FULL, CONV4X4_S2, CONV4X4_S1,
+ CONV4X4_S2_DGRAD, CONV4X4_S1_FULL) = range(11)
+EPI_RAW_STATS, EPI_BIAS_TANH_NCHW, EPI_SIGN_NCHW, EPI_RAW, EPI_BIAS_ACT, EPI_BIAS_NCHW = range(6)
+ABI_VERSION = 2
 
 # symbol -> (restype, argtypes); also the list the CPU test checks against the header
 SIGNATURES = {
@@ -64,6 +68,20 @@ SIGNATURES = {
     "jpdse_distortion_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                     ctypes.POINTER(c_double), ctypes.POINTER(c_double), c_void_p]),
     "jpdse_s2hvq_decode": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "jpdse_instnorm_backward_reduce_act": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "jpdse_d_input": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "jpdse_d_input_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "jpdse_instnorm_apply_act": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
+                                         c_void_p]),
+    "jpdse_act_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
+                                   c_float, c_void_p]),
+    "jpdse_l1_pair": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "jpdse_l1_pair_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_int, c_int, c_int,
+                                       c_void_p]),
+    "jpdse_maxpool2x2": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "jpdse_maxpool2x2_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "jpdse_nhwc_pad_to_nchw_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
 }
 
 _lib = None

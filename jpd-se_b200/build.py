@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libjpdse_b200.so")
 STAMP = os.path.join(HERE, "build", "stamp.txt")
-SOURCES = ["api.cu", "conv_igemm.cu", "conv_rowstat.cu", "bandwidth_kernels.cu", "conv_wgrad.cu", "backward_kernels.cu", "conv_convt.cu", "conv_pair.cu"]
+SOURCES = ["api.cu", "conv_igemm.cu", "conv_rowstat.cu", "bandwidth_kernels.cu", "conv_wgrad.cu", "backward_kernels.cu", "conv_convt.cu", "conv_pair.cu", "discriminator_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",

@@ -61,7 +61,8 @@ template <bool kRelu, bool kSkip>
 __global__ void __launch_bounds__(kBwdThreads, 3)
 instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, const __nv_bfloat16* __restrict__ skip,
                                 const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
-                                __nv_bfloat16* __restrict__ dy, double* __restrict__ sums, int H, int W, int C, float eps, int iters) {
+                                __nv_bfloat16* __restrict__ dy, double* __restrict__ sums, int H, int W, int C, float eps, int iters,
+                                float slope) {
   __shared__ float s_red[kBwdThreads][17];
   const int vpp = C >> 3;
   const int ppi = kBwdThreads / vpp;
@@ -119,9 +120,9 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
     for (int j = 0; j < 8; j += 2) {
       const float xh0 = (x[j] - mean[j]) * rstd[j], xh1 = (x[j + 1] - mean[j + 1]) * rstd[j + 1];
       float d0 = acc[j], d1 = acc[j + 1];
-      if (kRelu) {
-        d0 = xh0 > 0.f ? d0 : 0.f;
-        d1 = xh1 > 0.f ? d1 : 0.f;
+      if (kRelu) {  // ReLU (slope 0: exact zeros) or LeakyReLU(slope) mask
+        d0 = xh0 > 0.f ? d0 : (slope == 0.f ? 0.f : slope * d0);
+        d1 = xh1 > 0.f ? d1 : (slope == 0.f ? 0.f : slope * d1);
       }
       const uint32_t pk = bwd_pack_bf16x2(d0, d1);
       ow[j >> 1] = pk;
@@ -274,9 +275,20 @@ static int check_channels(int channels, const char* what) {
 
 using namespace jpdse;
 
+extern "C" int jpdse_instnorm_backward_reduce_act(const void* g, int g_pad, const void* skip, const void* raw, const double* stats,
+                                                  void* dy, double* sums, int batch, int height, int width, int channels, int relu,
+                                                  float slope, float eps, void* stream_v);
+
 extern "C" int jpdse_instnorm_backward_reduce(const void* g, int g_pad, const void* skip, const void* raw, const double* stats,
                                               void* dy, double* sums, int batch, int height, int width, int channels, int relu,
                                               float eps, void* stream_v) {
+  return jpdse_instnorm_backward_reduce_act(g, g_pad, skip, raw, stats, dy, sums, batch, height, width, channels, relu, 0.f, eps,
+                                            stream_v);
+}
+
+extern "C" int jpdse_instnorm_backward_reduce_act(const void* g, int g_pad, const void* skip, const void* raw, const double* stats,
+                                                  void* dy, double* sums, int batch, int height, int width, int channels, int relu,
+                                                  float slope, float eps, void* stream_v) {
   if (g == nullptr || raw == nullptr || stats == nullptr || dy == nullptr || sums == nullptr)
     return fail(JPDSE_ERR_INVALID, "instnorm_backward_reduce: NULL pointer");
   if (batch <= 0 || height <= 0 || width <= 0) return fail(JPDSE_ERR_INVALID, "instnorm_backward_reduce: bad sizes");
@@ -304,13 +316,13 @@ extern "C" int jpdse_instnorm_backward_reduce(const void* g, int g_pad, const vo
   const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(raw);
   __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(dy);
   if (relu && skip)
-    instnorm_backward_reduce_kernel<true, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters);
+    instnorm_backward_reduce_kernel<true, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters, slope);
   else if (relu)
-    instnorm_backward_reduce_kernel<true, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters);
+    instnorm_backward_reduce_kernel<true, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters, slope);
   else if (skip)
-    instnorm_backward_reduce_kernel<false, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters);
+    instnorm_backward_reduce_kernel<false, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters, slope);
   else
-    instnorm_backward_reduce_kernel<false, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters);
+    instnorm_backward_reduce_kernel<false, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters, slope);
   return check_launch("instnorm_backward_reduce_kernel");
 }
 

@@ -39,7 +39,7 @@ constexpr int kTileM = 128;         // output pixels per tile (UMMA M)
 constexpr int kBlockK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kUmmaK = 16;          // K of one tcgen05.mma for 16-bit inputs
 constexpr int kABytes = kTileM * kBlockK * 2;
-constexpr int kMaxTaps = 9;
+constexpr int kMaxTaps = 16;        // 4x4 PatchGAN convs
 constexpr int kThreads = 320;       // two epilogue warpgroups (one per TMEM accumulator) + 2 control warps
 // The control warps get the HIGHEST warp ids: the sub-partition arbiter favours high ids, and the single TMA /
 // MMA threads are the critical path of the low-K convs.
@@ -73,6 +73,10 @@ struct IgemmParams {
   int epilogue;
   int tma_store;   // 1: bf16 NHWC output leaves through shared memory + TMA store (tm_c), BN in {64, 128}
   int c_rank;      // 4: {c, w, h, b}; 5: {2c (col parity major), w, row parity, h, b} (ConvTranspose phases)
+  int out_pad;     // bf16 NHWC epilogues: border of the OUTPUT tensor that is skipped over (zero, owned by the caller)
+  int check_out;   // 1: rows whose output coordinate falls outside out_h x out_w are neither stored nor counted
+                   //    (data gradient of the 4x4 stride-2 conv onto an odd-sized input)
+  float slope;     // JPDSE_EPI_BIAS_ACT: LeakyReLU negative slope (0 = ReLU)
   void* out;
   double* stats;
   const float* bias;
@@ -101,6 +105,16 @@ struct IgemmCfg {
 };
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// JPDSE_EPI_BIAS_ACT on one 32-column accumulator chunk: v = LeakyReLU_slope(v + bias) (every lane reads the same 32
+// biases: broadcast loads out of L1)
+__device__ __forceinline__ void bias_act32(uint32_t (&v)[32], const float* __restrict__ bias, float slope) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const float x = __uint_as_float(v[j]) + __ldg(bias + j);
+    v[j] = __float_as_uint(x > 0.f ? x : slope * x);
+  }
+}
 
 template <int BN, int STG>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -342,6 +356,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       } else if (p.partial) {
         valid = th * p.tile_h + r < p.gemm_h && tw * p.tile_w + c < p.gemm_w;
       }
+      if (p.check_out) valid = valid && oh < p.out_h && ow < p.out_w;
       const int n0 = nt * BN;
 
       const long long tw2 = p.dbg ? clock64() : 0;
@@ -381,6 +396,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
               uint32_t v[32];
               tmem_ld_32x32b_x32(taddr + ch * 32, v);
               tmem_ld_wait();
+              if (p.epilogue == JPDSE_EPI_BIAS_ACT) bias_act32(v, p.bias + n0 + ch * 32, p.slope);
               uint32_t pk[16];
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -416,7 +432,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
             ++out_buf;
           }
         }
-      } else if (p.epilogue == JPDSE_EPI_RAW_STATS || p.epilogue == JPDSE_EPI_RAW) {
+      } else if (p.epilogue == JPDSE_EPI_RAW_STATS || p.epilogue == JPDSE_EPI_RAW || p.epilogue == JPDSE_EPI_BIAS_ACT) {
         const bool want_stats = p.epilogue == JPDSE_EPI_RAW_STATS;
         if (want_stats && (b != cur_b || n0 != cur_n0)) {
           flush();
@@ -424,13 +440,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           cur_n0 = n0;
         }
         __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) +
-                              ((static_cast<size_t>(b) * p.out_h + oh) * p.out_w + ow) * p.ldc + n0;
+                              ((static_cast<size_t>(b) * (p.out_h + 2 * p.out_pad) + oh + p.out_pad) * (p.out_w + 2 * p.out_pad) +
+                               ow + p.out_pad) * p.ldc + n0;
         if constexpr (BN >= 32) {
 #pragma unroll
           for (int ch = 0; ch < kChunks; ++ch) {
             uint32_t v[32];
             tmem_ld_32x32b_x32(taddr + ch * 32, v);
             tmem_ld_wait();
+            if (p.epilogue == JPDSE_EPI_BIAS_ACT) bias_act32(v, p.bias + n0 + ch * 32, p.slope);
             uint32_t pk[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -473,6 +491,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
                 float y;
                 if (p.epilogue == JPDSE_EPI_BIAS_TANH_NCHW) {
                   y = tanhf(x + p.bias[n]);
+                } else if (p.epilogue == JPDSE_EPI_BIAS_NCHW) {
+                  y = x + p.bias[n];
                 } else {
                   // torch.sign(torch.tanh(x)) == (x > 0) - (x < 0): tanh keeps the sign of every
                   // non-zero float (denormals included) and torch.sign maps NaN and -0 to 0
@@ -611,7 +631,8 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
       g->out_w = g->gemm_w = d->in_w;
       g->cpt = d->cin / 64;
       g->ktot = (d->kind == JPDSE_CONV1X1 ? 1 : 9) * d->cin;
-      if (pair_conv_applicable(d)) g->path = kPathPair;  // same packed weights as the single-CTA kernel
+      if (pair_conv_applicable(d) && d->out_pad == 0 && d->epilogue != JPDSE_EPI_BIAS_ACT)
+        g->path = kPathPair;  // same packed weights as the single-CTA kernel
       break;
     case JPDSE_CONV3X3_S2:
       if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv s2: cin must be a multiple of 64 (got %d)", d->cin);
@@ -630,6 +651,37 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
       g->cpt = d->cin / 64;
       g->ktot = 9 * d->cin;
       if (convt_fused_applicable(d)) g->path = kPathConvtFused;
+      break;
+    case JPDSE_CONV4X4_S2:
+    case JPDSE_CONV4X4_S1:
+      if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv4x4: cin must be a multiple of 64 (got %d)", d->cin);
+      if (d->in_pad != 2) return fail(JPDSE_ERR_INVALID, "CONV4X4 kinds need in_pad == 2 (the conv's zero padding)");
+      g->out_h = g->gemm_h = d->kind == JPDSE_CONV4X4_S2 ? d->in_h / 2 + 1 : d->in_h + 1;
+      g->out_w = g->gemm_w = d->kind == JPDSE_CONV4X4_S2 ? d->in_w / 2 + 1 : d->in_w + 1;
+      g->cpt = d->kind == JPDSE_CONV4X4_S2 ? 2 * d->cin / 64 : d->cin / 64;  // stride 2: one tap = a column PAIR
+      g->ktot = 16 * d->cin;
+      break;
+    case JPDSE_CONV4X4_S2_DGRAD:
+      if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv4x4 dgrad: cin must be a multiple of 64 (got %d)", d->cin);
+      if (d->in_pad != 2) return fail(JPDSE_ERR_INVALID, "CONV4X4_S2_DGRAD needs in_pad == 2");
+      if (d->out_h <= 0 || d->out_w <= 0 || d->out_h / 2 + 1 != d->in_h || d->out_w / 2 + 1 != d->in_w)
+        return fail(JPDSE_ERR_INVALID, "CONV4X4_S2_DGRAD: out_h/out_w (%d x %d) are not a forward input size of a %d x %d output",
+                    d->out_h, d->out_w, d->in_h, d->in_w);
+      g->out_h = d->out_h;
+      g->out_w = d->out_w;
+      g->gemm_h = (d->out_h + 1) / 2;
+      g->gemm_w = (d->out_w + 1) / 2;
+      g->cpt = d->cin / 64;
+      g->ktot = 16 * d->cin;  // four phase blocks of 4 taps
+      break;
+    case JPDSE_CONV4X4_S1_FULL:
+      if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv4x4 full: cin must be a multiple of 64 (got %d)", d->cin);
+      if (d->in_pad != 2) return fail(JPDSE_ERR_INVALID, "CONV4X4_S1_FULL needs in_pad == 2");
+      if (d->in_h < 2 || d->in_w < 2) return fail(JPDSE_ERR_INVALID, "CONV4X4_S1_FULL: gradient smaller than 2x2");
+      g->out_h = g->gemm_h = d->in_h - 1;
+      g->out_w = g->gemm_w = d->in_w - 1;
+      g->cpt = d->cin / 64;
+      g->ktot = 16 * d->cin;
       break;
     case JPDSE_CONV7X7_PAD3:
       if ((d->cin * 2) % 16) return fail(JPDSE_ERR_UNSUPPORTED, "conv7x7: cin*2 bytes must be a multiple of 16");
@@ -656,14 +708,17 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
   // the tile count doubles (an N = 128 MMA costs about half an N = 256 one, so a lone tile also finishes sooner).
   // (A wave-quantisation-aware choice for the flat data-gradient kinds was tried and lost: N = 128 doubles the unique
   // A traffic and falls back to per-lane stores there.)
-  if (g->bn == 256 && g->path == kPathIgemm && d->kind != JPDSE_CONV3X3_FULL) {
+  if (g->bn == 256 && g->path == kPathIgemm && d->kind != JPDSE_CONV3X3_FULL && d->kind != JPDSE_CONV4X4_S1_FULL) {
     const long long m_tiles = (static_cast<long long>(d->batch) * g->gemm_h * g->gemm_w + 127) / 128;
     if (m_tiles * (g->rows / 256) * 4 < static_cast<long long>(num_sms()) * 3) g->bn = 128;
   }
-  if (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW) {
+  if (d->out_pad < 0) return fail(JPDSE_ERR_INVALID, "conv desc: out_pad < 0");
+  if (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW || d->epilogue == JPDSE_EPI_BIAS_ACT) {
     if (d->cout % g->bn || g->bn < 32)
-      return fail(JPDSE_ERR_UNSUPPORTED, "raw+stats epilogue needs cout %% %d == 0 (got %d)", g->bn, d->cout);
-  } else if (d->epilogue == JPDSE_EPI_BIAS_TANH_NCHW || d->epilogue == JPDSE_EPI_SIGN_NCHW) {
+      return fail(JPDSE_ERR_UNSUPPORTED, "bf16 NHWC epilogues need cout %% %d == 0 (got %d)", g->bn, d->cout);
+    if (d->out_pad && g->path != kPathIgemm)
+      return fail(JPDSE_ERR_UNSUPPORTED, "out_pad is only supported by the generic implicit-GEMM path");
+  } else if (d->epilogue == JPDSE_EPI_BIAS_TANH_NCHW || d->epilogue == JPDSE_EPI_SIGN_NCHW || d->epilogue == JPDSE_EPI_BIAS_NCHW) {
     if (g->bn > 128) return fail(JPDSE_ERR_UNSUPPORTED, "NCHW epilogues support cout <= 128 (got %d)", d->cout);
   } else {
     return fail(JPDSE_ERR_INVALID, "conv desc: unknown epilogue %d", d->epilogue);
@@ -717,7 +772,7 @@ static int launch_igemm_bn(int bn, const CUtensorMap& ta, const CUtensorMap& tb,
 
 // ------------------------------------------------------------------------------------------ weight packing
 struct PackParams {
-  int kind, cin, cin_real, cout, rows, ktot, cpt, path;
+  int kind, cin, cin_real, cout, rows, ktot, cpt, path, cout_real;
 };
 
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, PackParams q) {
@@ -789,6 +844,25 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
           val = w[((static_cast<size_t>(n) * q.cin_real + c) * 7 + kh) * 7 + kw];
       } else if (q.kind == JPDSE_CONV1X1) {
         if (n < q.cout && k < q.cin_real) val = w[static_cast<size_t>(n) * q.cin_real + k];
+      } else if (q.kind == JPDSE_CONV4X4_S2 || q.kind == JPDSE_CONV4X4_S1) {
+        // [n][t = kh*4+kw][c]; the stride-2 kernel walks it as (kh, column pair) taps of 2*cin contiguous elements
+        const int t = k / q.cin, c = k % q.cin;
+        if (n < q.cout && c < q.cin_real) val = w[(static_cast<size_t>(n) * q.cin_real + c) * 16 + t];
+      } else if (q.kind == JPDSE_CONV4X4_S1_FULL) {
+        // W'[n = ci_fwd][t' = kh'*4+kw'][c = co_fwd] = W_fwd[co_fwd][ci_fwd][3-kh'][3-kw'], W_fwd is (cin_real, cout_real, 4, 4)
+        const int t = k / q.cin, c = k % q.cin;
+        const int kh = 3 - t / 4, kw = 3 - t % 4;
+        if (n < q.cout_real && c < q.cin_real) val = w[((static_cast<size_t>(c) * q.cout_real + n) * 4 + kh) * 4 + kw];
+      } else if (q.kind == JPDSE_CONV4X4_S2_DGRAD) {
+        // four phase blocks (r, s), each rows x (4 taps x cin): tap t = i*2+j -> W_fwd[co][ci][2i+r][2j+s]
+        const size_t blk = static_cast<size_t>(q.rows) * 4 * q.cin;
+        const int ph = static_cast<int>(i / blk);
+        const size_t rem = i % blk;
+        const int nn = static_cast<int>(rem / (4 * q.cin));
+        const int kk = static_cast<int>(rem % (4 * q.cin));
+        const int t = kk / q.cin, c = kk % q.cin;
+        const int kh = 2 * (t >> 1) + (ph >> 1), kw = 2 * (t & 1) + (ph & 1);
+        if (nn < q.cout_real && c < q.cin_real) val = w[((static_cast<size_t>(c) * q.cout_real + nn) * 4 + kh) * 4 + kw];
       } else {
         const int t = k / q.cin, c = k % q.cin;
         if (n < q.cout && c < q.cin_real) val = w[(static_cast<size_t>(n) * q.cin_real + c) * 9 + t];
@@ -827,15 +901,20 @@ extern "C" size_t jpdse_conv_packed_weight_bytes(const jpdse_conv_desc* d) {
 extern "C" int jpdse_conv_launch_count(const jpdse_conv_desc* d) {
   ConvGeom g;
   if (conv_geom(d, &g) != JPDSE_OK) return 0;
+  if (d->kind == JPDSE_CONV4X4_S2_DGRAD) return 4;
   return (d->kind == JPDSE_CONVT3X3_S2 && g.path == kPathIgemm) ? 4 : 1;  // generic ConvTranspose = one launch per phase
 }
 
 extern "C" double jpdse_conv_flops(const jpdse_conv_desc* d) {
   ConvGeom g;
   if (conv_geom(d, &g) != JPDSE_OK) return 0.0;
-  const int taps = d->kind == JPDSE_CONV7X7_PAD3 ? 49 : (d->kind == JPDSE_CONV1X1 ? 1 : 9);
+  int taps = d->kind == JPDSE_CONV7X7_PAD3 ? 49 : (d->kind == JPDSE_CONV1X1 ? 1 : 9);
+  if (d->kind == JPDSE_CONV4X4_S2 || d->kind == JPDSE_CONV4X4_S1 || d->kind == JPDSE_CONV4X4_S1_FULL) taps = 16;
+  const int co = (d->cout_real > 0 && d->cout_real <= d->cout) ? d->cout_real : d->cout;
+  if (d->kind == JPDSE_CONV4X4_S2_DGRAD)  // 4 of the 16 taps reach each output pixel
+    return 2.0 * d->batch * static_cast<double>(g.out_h) * g.out_w * 4 * d->cin_real * co;
   // ConvT counted as 9 taps per *input* pixel
-  return 2.0 * d->batch * static_cast<double>(g.gemm_h) * g.gemm_w * taps * d->cin_real * d->cout;
+  return 2.0 * d->batch * static_cast<double>(g.gemm_h) * g.gemm_w * taps * d->cin_real * co;
 }
 
 namespace jpdse {
@@ -908,7 +987,8 @@ extern "C" int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w,
       return check_launch("pack3x3_full_kernel");
     }
   }
-  PackParams q{d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt, g.path};
+  PackParams q{d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt, g.path,
+               (d->cout_real > 0 && d->cout_real <= d->cout) ? d->cout_real : d->cout};
   const size_t total = static_cast<size_t>(g.rows) * g.ktot;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
@@ -923,7 +1003,9 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   if (rc != JPDSE_OK) return rc;
   if (x == nullptr || w_packed == nullptr || y == nullptr) return fail(JPDSE_ERR_INVALID, "conv_forward: NULL pointer");
   if (d->epilogue == JPDSE_EPI_RAW_STATS && stats == nullptr) return fail(JPDSE_ERR_INVALID, "conv_forward: stats is NULL");
-  if (d->epilogue == JPDSE_EPI_BIAS_TANH_NCHW && bias == nullptr) return fail(JPDSE_ERR_INVALID, "conv_forward: bias is NULL");
+  if ((d->epilogue == JPDSE_EPI_BIAS_TANH_NCHW || d->epilogue == JPDSE_EPI_BIAS_ACT || d->epilogue == JPDSE_EPI_BIAS_NCHW) &&
+      bias == nullptr)
+    return fail(JPDSE_ERR_INVALID, "conv_forward: bias is NULL");
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w_packed) & 15) ||
       (reinterpret_cast<uintptr_t>(y) & 15))
     return fail(JPDSE_ERR_INVALID, "conv_forward: pointers must be 16-byte aligned");
@@ -934,7 +1016,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  const bool flat = d->kind == JPDSE_CONV3X3_FULL || d->kind == JPDSE_CONV7X7_FULL;
+  const bool flat = d->kind == JPDSE_CONV3X3_FULL || d->kind == JPDSE_CONV7X7_FULL || d->kind == JPDSE_CONV4X4_S1_FULL;
   p.batch = d->batch;
   if (flat) {
     // M runs over flat positions y*pitch + x of the zero-bordered input; pitch = stored width
@@ -960,6 +1042,8 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   p.ldc = d->cout;
   p.n_valid = d->cout;
   p.epilogue = d->epilogue;
+  p.out_pad = d->out_pad;
+  p.slope = d->slope;
   p.out = y;
   p.stats = stats;
   p.bias = bias;
@@ -980,10 +1064,15 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     const char* e = getenv("JPDSE_STAGED_KBLOCKS");
     staged_limit = e ? atoi(e) : 48;
   }
-  const int kblocks_per_tile = (d->kind == JPDSE_CONV1X1 ? 1 : 9) * g.cpt;
+  int dev_taps = d->kind == JPDSE_CONV1X1 ? 1 : 9;  // taps of one tile's K loop as the kernel walks them
+  if (d->kind == JPDSE_CONV4X4_S2) dev_taps = 8;
+  if (d->kind == JPDSE_CONV4X4_S1) dev_taps = 16;
+  if (d->kind == JPDSE_CONV4X4_S2_DGRAD) dev_taps = 4;
+  const int kblocks_per_tile = dev_taps * g.cpt;
+  const bool odd_phase_out = d->kind == JPDSE_CONV4X4_S2_DGRAD && ((g.out_h | g.out_w) & 1);  // no {2C, W/2, 2, H/2} view
   const bool staged_out = (g.bn == 64 || g.bn == 128 || (g.bn == 256 && kblocks_per_tile <= staged_limit)) && !flat &&
-                          (d->cout % 64) == 0 && d->kind != JPDSE_CONV7X7_PAD3 &&
-                          (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW);
+                          (d->cout % 64) == 0 && d->kind != JPDSE_CONV7X7_PAD3 && !odd_phase_out &&
+                          (d->epilogue == JPDSE_EPI_RAW_STATS || d->epilogue == JPDSE_EPI_RAW || d->epilogue == JPDSE_EPI_BIAS_ACT);
   const uint64_t C = static_cast<uint64_t>(d->cin);
   const uint64_t H = static_cast<uint64_t>(d->in_h), W = static_cast<uint64_t>(d->in_w), B = static_cast<uint64_t>(d->batch);
   // physical (stored) extent of x and the address of its logical pixel (0,0)
@@ -1041,6 +1130,52 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     return JPDSE_OK;
   }
 
+  if (d->kind == JPDSE_CONV4X4_S2_DGRAD) {
+    // dx_padded[2a+r, 2b+s] = sum_{i,j in {0,1}} dy[a-i, b-j] * W[2i+r][2j+s] in the coordinates of the forward input
+    // padded by 2; with y = 2a'+r the interior pixel is a = a'+1, so phase (r, s) is a 2x2-tap GEMM over dy rows
+    // a'+1-i, columns b'+1-j (index -1 never occurs; index h / w is the zero border behind the gradient).
+    if (d->out_pad) return fail(JPDSE_ERR_UNSUPPORTED, "CONV4X4_S2_DGRAD writes a dense output (out_pad must be 0)");
+    dims[0] = C; dims[1] = W + d->in_pad; dims[2] = H + d->in_pad; dims[3] = B;
+    strides[0] = C * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
+    box[0] = 64; box[1] = p.tile_w; box[2] = p.tile_h; box[3] = 1;
+    rc = make_tmap_bf16(&ta, xin, 4, dims, strides, box);
+    if (rc != JPDSE_OK) return rc;
+    p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
+    p.os_h = p.os_w = 2;
+    p.check_out = 1;
+    CUtensorMap tc = ta;
+    if (staged_out) {
+      const uint64_t Co = static_cast<uint64_t>(d->cout), GW = static_cast<uint64_t>(g.gemm_w), GH = static_cast<uint64_t>(g.gemm_h);
+      uint64_t cd[5] = {2 * Co, GW, 2, GH, B};
+      uint64_t cs[4] = {2 * Co * 2, 2 * GW * Co * 2, 2 * 2 * GW * Co * 2, 2 * GH * 2 * GW * Co * 2};
+      uint32_t cb[5] = {64, static_cast<uint32_t>(p.tile_w), 1, static_cast<uint32_t>(p.tile_h), 1};
+      rc = make_tmap_bf16(&tc, y, 5, cd, cs, cb);
+      if (rc != JPDSE_OK) return rc;
+      p.tma_store = 1;
+      p.c_rank = 5;
+    }
+    const uint64_t kp = 4 * C;
+    for (int pidx = 0; pidx < 4; ++pidx) {
+      p.ntaps = 4;
+      memset(p.tap_off, 0, sizeof(p.tap_off));
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+          p.tap_off[i * 2 + j][1] = 1 - j;
+          p.tap_off[i * 2 + j][2] = 1 - i;
+        }
+      p.op_h = pidx >> 1; p.op_w = pidx & 1;
+      uint64_t bd[2] = {kp, static_cast<uint64_t>(g.rows)};
+      uint64_t bs[1] = {kp * 2};
+      uint32_t bb[2] = {64, static_cast<uint32_t>(g.bn)};
+      rc = make_tmap_bf16(&tb, static_cast<const uint8_t*>(w_packed) + static_cast<size_t>(pidx) * g.rows * kp * 2, 2, bd, bs, bb);
+      if (rc != JPDSE_OK) return rc;
+      p.b_k_offset = 0;
+      rc = launch_igemm_bn(g.bn, ta, tb, tc, p, stream);
+      if (rc != JPDSE_OK) return rc;
+    }
+    return JPDSE_OK;
+  }
+
   if (flat) {
     // {K-inner, flat position, image}; reads past the last position of an image meet the next image's zero
     // border (or TMA zero fill behind the last image) and only feed rows that are never stored
@@ -1054,6 +1189,11 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       dims[0] = C;
       p.ntaps = 9;
       for (int t = 0; t < 9; ++t) p.tap_off[t][1] = (t / 3) * static_cast<int>(Wp) + (t % 3);
+    } else if (d->kind == JPDSE_CONV4X4_S1_FULL) {
+      // dx[y, x] = sum_{kh', kw'} dy_padded[y + 1 + kh', x + 1 + kw'] * W[3-kh'][3-kw'] (dy stored with a zero border of 2)
+      dims[0] = C;
+      p.ntaps = 16;
+      for (int t = 0; t < 16; ++t) p.tap_off[t][1] = (1 + t / 4) * static_cast<int>(Wp) + (1 + t % 4);
     } else {
       dims[0] = 64;  // 7*C window elements (+ zero-weight tail) under a filter row
       p.ntaps = 7;
@@ -1071,6 +1211,36 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       for (int t = 0; t < 9; ++t) {
         p.tap_off[t][1] = t % 3;
         p.tap_off[t][2] = t / 3;
+      }
+      break;
+    }
+    case JPDSE_CONV4X4_S1: {
+      xin = static_cast<const uint8_t*>(x);  // taps address the stored zero border directly
+      dims[0] = C; dims[1] = Wp; dims[2] = Hp; dims[3] = B;
+      strides[0] = C * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
+      box[0] = 64; box[1] = p.tile_w; box[2] = p.tile_h; box[3] = 1;
+      p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
+      p.ntaps = 16;
+      for (int t = 0; t < 16; ++t) {
+        p.tap_off[t][1] = t % 4;
+        p.tap_off[t][2] = t / 4;
+      }
+      break;
+    }
+    case JPDSE_CONV4X4_S2: {
+      // the stored (B,H+4,W+4,C) tensor viewed as {2C, (W+4)/2, 2, (H+4)/2, B}: tap (kh, column pair kp) covers kw = 2kp
+      // and 2kp+1 as 2C contiguous elements; output (oh, ow) reads row 2*oh+kh = pair oh + kh/2, parity kh % 2
+      xin = static_cast<const uint8_t*>(x);
+      dims[0] = 2 * C; dims[1] = Wp / 2; dims[2] = 2; dims[3] = Hp / 2; dims[4] = B;
+      strides[0] = 2 * C * 2; strides[1] = Wp * C * 2; strides[2] = 2 * Wp * C * 2; strides[3] = Hp * Wp * C * 2;
+      box[0] = 64; box[1] = p.tile_w; box[2] = 1; box[3] = p.tile_h; box[4] = 1;
+      p.a_rank = 5; p.dim_w = 1; p.dim_h = 3; p.dim_b = 4;
+      p.ntaps = 8;
+      for (int t = 0; t < 8; ++t) {
+        const int kh = t / 2, kp = t % 2;
+        p.tap_off[t][1] = kp;
+        p.tap_off[t][2] = kh & 1;
+        p.tap_off[t][3] = kh >> 1;
       }
       break;
     }
@@ -1122,11 +1292,13 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   if (rc != JPDSE_OK) return rc;
   CUtensorMap tc = ta;
   if (staged_out) {
+    // dims = the logical output (the store clips overhanging tiles there); strides / base step over the caller's border
     const uint64_t Co = static_cast<uint64_t>(d->cout), OW = static_cast<uint64_t>(g.out_w), OH = static_cast<uint64_t>(g.out_h);
+    const uint64_t OP = static_cast<uint64_t>(d->out_pad), OWp = OW + 2 * OP, OHp = OH + 2 * OP;
     uint64_t cd[4] = {Co, OW, OH, B};
-    uint64_t cs[3] = {Co * 2, OW * Co * 2, OH * OW * Co * 2};
+    uint64_t cs[3] = {Co * 2, OWp * Co * 2, OHp * OWp * Co * 2};
     uint32_t cb[4] = {64, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h), 1};
-    rc = make_tmap_bf16(&tc, y, 4, cd, cs, cb);
+    rc = make_tmap_bf16(&tc, static_cast<uint8_t*>(y) + (OP * OWp + OP) * Co * 2, 4, cd, cs, cb);
     if (rc != JPDSE_OK) return rc;
     p.tma_store = 1;
     p.c_rank = 4;

@@ -40,7 +40,7 @@ namespace jpdse {
 constexpr int kWgThreads = 320;
 constexpr int kWgProducerWarp = 8;
 constexpr int kWgMmaWarp = 9;
-constexpr int kWgMaxGroups = 9;
+constexpr int kWgMaxGroups = 16;  // 4x4 PatchGAN convs: one tap per group when Q has >= 192 channels
 constexpr int kWgBox = 64 * 64 * 2;          // one {64 channels, 64 pixels} box, bytes
 constexpr int kWgStageBytes = 6 * kWgBox;    // 2 A boxes + up to 4 B boxes
 constexpr int kWgStages = 4;
@@ -406,6 +406,9 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
   } else if (d->kind == JPDSE_CONV3X3_S2) {
     grid_h = H / 2;
     grid_w = W / 2;
+  } else if (d->kind == JPDSE_CONV4X4_S2 || d->kind == JPDSE_CONV4X4_S1) {
+    grid_h = g.out_h;
+    grid_w = g.out_w;
   } else {
     return fail(JPDSE_ERR_UNSUPPORTED, "conv_wgrad: kind %d has no weight gradient", d->kind);
   }
@@ -478,8 +481,11 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
   } else {
     // generic 3x3 / 1x1: P channels on M, (tap, Q channel block) on N
     const bool convt = d->kind == JPDSE_CONVT3X3_S2;
-    const int taps = d->kind == JPDSE_CONV1X1 ? 1 : 9;
-    const int pc = convt ? Cin : Cout;   // P channels
+    const bool k4 = d->kind == JPDSE_CONV4X4_S2 || d->kind == JPDSE_CONV4X4_S1;
+    const int taps = d->kind == JPDSE_CONV1X1 ? 1 : (k4 ? 16 : 9);
+    const int kdim = k4 ? 4 : 3;
+    // the PatchGAN's 1-channel output conv: its gradient tensor is stored with 64 channels (zeros beyond cout)
+    const int pc = convt ? Cin : (k4 ? (Cout + 63) / 64 * 64 : Cout);   // P channels (as stored)
     const int qc = convt ? Cout : Cin;   // Q channels
     if (pc % 64 || qc % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv_wgrad: channels must be multiples of 64 (got %d, %d)", pc, qc);
     w->a_is_dy = convt ? 0 : 1;
@@ -487,12 +493,13 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
     if (convt) {
       plain_view(w->a_dims, w->a_strides, w->a_box, &w->a_base_off, Cin, H, W, B, d->in_pad, 0, 0, H, W, p.kw_cols, p.kh_rows);
     } else {
-      plain_view(w->a_dims, w->a_strides, w->a_box, &w->a_base_off, Cout, g.out_h, g.out_w, B, dy_pad, 0, 0, g.out_h, g.out_w,
+      plain_view(w->a_dims, w->a_strides, w->a_box, &w->a_base_off, pc, g.out_h, g.out_w, B, dy_pad, 0, 0, g.out_h, g.out_w,
                  p.kw_cols, p.kh_rows);
     }
     p.a = WgView{4, 1, 2, 3};
     // ---- Q view
     const bool strided = convt || d->kind == JPDSE_CONV3X3_S2;
+    if (k4 && d->in_pad != 2) return fail(JPDSE_ERR_INVALID, "conv_wgrad 4x4: in_pad must be 2");
     if (d->kind == JPDSE_CONV3X3_PAD1) {
       plain_view(w->b_dims, w->b_strides, w->b_box, &w->b_base_off, Cin, H, W, B, 1, -1, -1, H + 2, W + 2, p.kw_cols, p.kh_rows);
       p.b = WgView{4, 1, 2, 3};
@@ -502,6 +509,18 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
     } else if (d->kind == JPDSE_CONV3X3_S2) {
       if ((H & 1) || (W & 1)) return fail(JPDSE_ERR_UNSUPPORTED, "conv_wgrad s2: odd input size");
       s2_view(w->b_dims, w->b_strides, w->b_box, &w->b_base_off, Cin, H, W, B, d->in_pad, p.kw_cols, p.kh_rows);
+      p.b = WgView{5, 1, 3, 4};
+    } else if (d->kind == JPDSE_CONV4X4_S1) {
+      plain_view(w->b_dims, w->b_strides, w->b_box, &w->b_base_off, Cin, H, W, B, 2, -2, -2, H + 4, W + 4, p.kw_cols, p.kh_rows);
+      p.b = WgView{4, 1, 2, 3};
+    } else if (d->kind == JPDSE_CONV4X4_S2) {
+      // the stored zero-bordered (B,H+4,W+4,C) tensor as {2C, (W+4)/2, 2, (H+4)/2, B}, origin at the stored corner
+      const uint64_t Wst = W + 4, Hst = H + 4;
+      w->b_dims[0] = 2ull * Cin; w->b_dims[1] = Wst / 2; w->b_dims[2] = 2; w->b_dims[3] = Hst / 2; w->b_dims[4] = B;
+      w->b_strides[0] = 2ull * Cin * 2; w->b_strides[1] = Wst * Cin * 2; w->b_strides[2] = 2 * Wst * Cin * 2;
+      w->b_strides[3] = Hst * Wst * Cin * 2;
+      w->b_box[0] = 64; w->b_box[1] = p.kw_cols; w->b_box[2] = 1; w->b_box[3] = p.kh_rows; w->b_box[4] = 1;
+      w->b_base_off = 0;
       p.b = WgView{5, 1, 3, 4};
     } else {
       s2_view(w->b_dims, w->b_strides, w->b_box, &w->b_base_off, Cout, 2 * H, 2 * W, B, dy_pad, p.kw_cols, p.kh_rows);
@@ -532,10 +551,15 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
         int* off = p.b_off[gi][j];
         off[0] = 64 * blk;
         if (t < taps) {
-          const int kh = taps == 1 ? 0 : t / 3, kw = taps == 1 ? 0 : t % 3;
+          const int kh = taps == 1 ? 0 : t / kdim, kw = taps == 1 ? 0 : t % kdim;
           if (strided) {
             s2_tap(off, qc, kh, kw);
-          } else if (taps == 9) {
+          } else if (d->kind == JPDSE_CONV4X4_S2) {
+            off[0] += (kw & 1) * qc;
+            off[1] = kw >> 1;
+            off[2] = kh & 1;
+            off[3] = kh >> 1;
+          } else if (taps == 9 || taps == 16) {
             off[1] = kw;
             off[2] = kh;
           }
@@ -559,7 +583,7 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
     p.m_tot = pc;
     p.n_tot = qc;
     const int n_real = convt ? Cout : d->cin_real;
-    f = WgFinalize{0, taps, p.m_tot, p.n_tot, pc, n_real, 0, 0};
+    f = WgFinalize{0, taps, p.m_tot, p.n_tot, k4 ? Cout : pc, n_real, 0, 0};
   }
   // split K so that the launch fills the machine
   const int per_split = p.n_groups * p.m_tiles * p.n_tiles;

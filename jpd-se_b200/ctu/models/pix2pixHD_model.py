@@ -137,12 +137,11 @@ class Pix2PixHDModel(nn.Module):
             self.criterionGAN = networks.GANLoss(use_lsgan=not _opt(opt, 'no_lsgan', False))
             self.criterionFeat = torch.nn.L1Loss()
             self.criterionVGG = networks.VGGLoss(self.gpu_ids)
-            # The PyTorch-side networks (netD, VGG) are 70 % of a step: run them channels_last with cuDNN autotuning.
-            # Same fp32/TF32 arithmetic and parameter shapes -- a layout choice only (JPDSE_NO_CHANNELS_LAST=1 disables).
+            # netD runs on the sm_100a kernels (jpdse_b200.discriminator). The PyTorch-side VGG runs channels_last with
+            # cuDNN autotuning: same arithmetic and parameter shapes, a layout choice only (JPDSE_NO_CHANNELS_LAST=1 disables).
             self.channels_last = len(self.gpu_ids) > 0 and os.environ.get('JPDSE_NO_CHANNELS_LAST', '0') != '1'
             if self.channels_last:
                 torch.backends.cudnn.benchmark = True
-                self.netD.to(memory_format=torch.channels_last)
                 self.criterionVGG.vgg.to(memory_format=torch.channels_last)
         else:
             self.loss_names = ('G_Distortion')  # sic: a plain string in the reference (:215)
@@ -350,7 +349,7 @@ class Pix2PixHDModel(nn.Module):
     def discriminate(self, input_label, test_image, use_pool=False, keep_input=False):
         # cuts the graph of both inputs: this is the discriminator's own loss
         input_concat = torch.cat((input_label.detach(), test_image.detach()), dim=1)
-        return self.netD.forward(self._cl(input_concat), keep_input)
+        return self.netD.forward(input_concat, keep_input)
 
     def get_train_loss(self, x_dict):
         opt = self.opt
@@ -382,17 +381,23 @@ class Pix2PixHDModel(nn.Module):
 
     def _losses(self, input_label, fake_image, real_image, keep_input):
         opt = self.opt
-        pred_fake_pool = self.discriminate(input_label, fake_image, use_pool=True)
-        loss_D_fake = self.criterionGAN(pred_fake_pool, False)
-        pred_real = self.discriminate(input_label, real_image, keep_input=keep_input)
-        loss_D_real = self.criterionGAN(pred_real, True)
-        pred_fake = self.netD.forward(self._cl(torch.cat((input_label, fake_image), dim=1)), keep_input=keep_input)
-        loss_G_GAN = self.criterionGAN(pred_fake, True)
-        loss_G_GAN_Feat = 0.
-        D_weights = 1.0 / _opt(opt, 'num_D', 2)
-        for i in range(_opt(opt, 'num_D', 2)):
-            for j in range(len(pred_fake[i]) - 1):
-                loss_G_GAN_Feat = loss_G_GAN_Feat + D_weights * self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
+        fused = not keep_input and not _opt(opt, 'no_lsgan', False) and os.environ.get('JPDSE_NO_FUSED_D', '0') != '1' 
+        if fused:
+            # pix2pixHD_model.py:715-753 in one kernel-side pass per image set (see MultiscaleDiscriminator.fused_losses)
+            loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake = self.netD.fused_losses(input_label, fake_image, real_image)
+        else:
+            # the reference's call sequence, one autograd node per netD call
+            pred_fake_pool = self.discriminate(input_label, fake_image, use_pool=True)
+            loss_D_fake = self.criterionGAN(pred_fake_pool, False)
+            pred_real = self.discriminate(input_label, real_image, keep_input=keep_input)
+            loss_D_real = self.criterionGAN(pred_real, True)
+            pred_fake = self.netD.forward(torch.cat((input_label, fake_image), dim=1), keep_input=keep_input)
+            loss_G_GAN = self.criterionGAN(pred_fake, True)
+            loss_G_GAN_Feat = 0.
+            D_weights = 1.0 / _opt(opt, 'num_D', 2)
+            for i in range(_opt(opt, 'num_D', 2)):
+                for j in range(len(pred_fake[i]) - 1):
+                    loss_G_GAN_Feat = loss_G_GAN_Feat + D_weights * self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
         loss_G_VGG = self.criterionVGG(self._cl(fake_image), self._cl(real_image))
         loss_G_distortion = self.criterionDistortion(fake_image, real_image)
         return loss_G_GAN, loss_G_GAN_Feat, loss_G_VGG, loss_G_distortion, loss_D_real, loss_D_fake

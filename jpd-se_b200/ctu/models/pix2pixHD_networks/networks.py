@@ -247,8 +247,8 @@ class GlobalGenerator(nn.Module):
 
 
 # ================================================================================================== training-only parts
-# Plain PyTorch (cuDNN) -- outside the accelerated path. Parameter names follow the
-# reference so checkpoints interchange.
+# The discriminator runs on the sm_100a kernels through jpdse_b200.discriminator; parameter
+# names follow the reference so checkpoints interchange.
 def define_D(input_nc, ndf, n_layers_D, norm='instance', use_sigmoid=False, num_D=1, getIntermFeat=False, gpu_ids=[]):
     # networks.py:58-66
     netD = MultiscaleDiscriminator(input_nc, ndf, n_layers_D, get_norm_layer(norm_type=norm), use_sigmoid, num_D,
@@ -278,6 +278,8 @@ def _patchgan_stages(input_nc, ndf, n_layers, norm_layer, use_sigmoid):
 
 
 class NLayerDiscriminator(nn.Module):
+    """Parameter holder with the reference's key layout (networks.py:422-471); executed by DiscriminatorPlan."""
+
     def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, use_sigmoid=False, getIntermFeat=False):
         super(NLayerDiscriminator, self).__init__()
         self.getIntermFeat = getIntermFeat
@@ -290,20 +292,142 @@ class NLayerDiscriminator(nn.Module):
             self.model = nn.Sequential(*[m for st in stages for m in st])
 
     def forward(self, input):
-        if not self.getIntermFeat:
-            return self.model(input)
-        feats, x = [], input
-        for n in range(self.n_layers + 2):
-            x = getattr(self, 'model' + str(n))(x)
-            feats.append(x)
-        return feats
+        raise JpdseError('NLayerDiscriminator is executed inside MultiscaleDiscriminator.forward by the jpdse_b200 kernels')
+
+
+class _DiscriminatorFunction(torch.autograd.Function):
+    """Autograd node of one MultiscaleDiscriminator call: forward / backward are DiscriminatorPlan kernel sequences.
+    Outputs: the num_D x (n_layers + 2) intermediate feature maps as float32 NCHW, like the reference returns them."""
+
+    @staticmethod
+    def forward(ctx, module, plan, input, *params):
+        ctx.set_materialize_grads(False)
+        slot = plan.new_slot()
+        with torch.cuda.device(plan.device):
+            gen = plan.forward(slot, input.detach().contiguous().float())
+            outs = tuple(plan.feature_nchw(slot, i, j) for i in range(plan.num_D) for j in range(plan.n_layers + 2))
+        ctx.module, ctx.plan, ctx.slot, ctx.gen = module, plan, slot, gen
+        return outs
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from .... import ops
+        plan, module = ctx.plan, ctx.module
+        need_input = ctx.needs_input_grad[2]
+        need_params = any(ctx.needs_input_grad[3:])
+        n = plan.n_layers + 2
+        with torch.cuda.device(plan.device):
+            feat_grads, final_grads = [], []
+            for i in range(plan.num_D):
+                row = []
+                for j in range(n - 1):
+                    g = grads[i * n + j]
+                    row.append(None if g is None else ops.nchw_to_nhwc_bf16(g.contiguous().float()))
+                feat_grads.append(row)
+                g = grads[i * n + n - 1]
+                final_grads.append(None if g is None else g.contiguous().float())
+            pg = {}
+            gin = plan.backward(ctx.slot, ctx.gen, feat_grads, final_grads, need_input, need_params, pg)
+        out = []
+        for k, (name, p) in enumerate(module.named_parameters()):
+            g = pg.get(name) if ctx.needs_input_grad[3 + k] else None
+            if g is None and ctx.needs_input_grad[3 + k] and need_params:
+                g = torch.zeros_like(p)
+            out.append(g)
+        return (None, None, gin) + tuple(out)
+
+
+class _DiscriminatorLossD(torch.autograd.Function):
+    """The discriminator's own LSGAN loss on two stored passes (fake, real): pix2pixHD_model.py:715-730 with GANLoss
+    (networks.py:80-122). Outputs (loss_D_fake, loss_D_real); backward produces parameter gradients only."""
+
+    @staticmethod
+    def forward(ctx, module, plan, fake, real, *params):
+        ctx.module, ctx.plan, ctx.fake, ctx.real = module, plan, fake, real
+        sf, sr = plan.slots[fake[0]], plan.slots[real[0]]
+        loss_fake = sum((m * m).mean() for m in sf.final)
+        loss_real = sum(((m - 1.0) ** 2).mean() for m in sr.final)
+        return loss_fake, loss_real
+
+    @staticmethod
+    def backward(ctx, g_fake, g_real):
+        plan, module = ctx.plan, ctx.module
+        sf, sr = plan.slots[ctx.fake[0]], plan.slots[ctx.real[0]]
+        none_feats = [[None] * (plan.n_layers + 1) for _ in range(plan.num_D)]
+        pg = {}
+        with torch.cuda.device(plan.device):
+            if g_fake is not None:
+                fin = [g_fake * (2.0 / m.numel()) * m for m in sf.final]
+                plan.backward(ctx.fake[0], ctx.fake[1], none_feats, fin, False, True, pg, accumulate=False)
+            if g_real is not None:
+                fin = [g_real * (2.0 / m.numel()) * (m - 1.0) for m in sr.final]
+                plan.backward(ctx.real[0], ctx.real[1], none_feats, fin, False, True, pg, accumulate=bool(pg))
+        out = []
+        for name, p in module.named_parameters():
+            g = pg.get(name)
+            out.append(g if g is not None else (torch.zeros_like(p) if p.requires_grad else None))
+        return (None, None, None, None) + tuple(out)
+
+
+class _DiscriminatorLossG(torch.autograd.Function):
+    """The generator's adversarial + feature-matching losses (pix2pixHD_model.py:733-753) on the stored fake / real
+    passes. Outputs (loss_G_GAN, loss_G_GAN_Feat); backward produces the gradient w.r.t. the fake image only -- the netD
+    parameter gradients the reference deposits here are discarded by optimizer_D.zero_grad()
+    (ctu/trainers/pix2pixHD_trainer.py:73) and are not computed."""
+
+    @staticmethod
+    def forward(ctx, plan, fake, real, fake_image):
+        from .... import ops
+        ctx.plan, ctx.fake, ctx.real = plan, fake, real
+        sf, sr = plan.slots[fake[0]], plan.slots[real[0]]
+        loss_gan = sum(((m - 1.0) ** 2).mean() for m in sf.final)
+        n_feat = plan.n_layers + 1
+        acc = torch.zeros(plan.num_D * n_feat, dtype=torch.float64, device=plan.device)
+        numel = []
+        with torch.cuda.device(plan.device):
+            for i in range(plan.num_D):
+                for j in range(n_feat):
+                    L = plan.scales[i][j]
+                    ops.l1_pair(sf.feat[i][j], sr.feat[i][j], acc[i * n_feat + j: i * n_feat + j + 1])
+                    numel.append(float(plan.B * L.cout * L.out_h * L.out_w))
+        w = torch.tensor([1.0 / (plan.num_D * n_) for n_ in numel], dtype=torch.float64, device=plan.device)
+        ctx.numel = numel
+        return loss_gan, (acc * w).sum().float()
+
+    @staticmethod
+    def backward(ctx, g_gan, g_fm):
+        from .... import ops
+        plan = ctx.plan
+        sf, sr = plan.slots[ctx.fake[0]], plan.slots[ctx.real[0]]
+        n_feat = plan.n_layers + 1
+        with torch.cuda.device(plan.device):
+            fin = [None] * plan.num_D
+            if g_gan is not None:
+                fin = [g_gan * (2.0 / m.numel()) * (m - 1.0) for m in sf.final]
+            feats = [[None] * n_feat for _ in range(plan.num_D)]
+            if g_fm is not None:
+                scale = g_fm.detach().reshape(1).float().contiguous()
+                for i in range(plan.num_D):
+                    for j in range(n_feat):
+                        L = plan.scales[i][j]
+                        out = plan._buf("fm%d_%d" % (i, j), (plan.B, L.out_h, L.out_w, L.cout))
+                        ops.l1_pair_backward(sf.feat[i][j], sr.feat[i][j], out, scale, 1.0 / (plan.num_D * ctx.numel[i * n_feat + j]),
+                                             plan.B, L.out_h, L.out_w, L.cout, 2)
+                        feats[i][j] = out
+            ic = plan.image_channels  # the image is the last `ic` channels of cat(input_label, image)
+            gin = plan.backward(ctx.fake[0], ctx.fake[1], feats, fin, True, False, input_channels=(plan.input_nc - ic, ic))
+        return None, None, None, gin
 
 
 class MultiscaleDiscriminator(nn.Module):
+    """networks.py:371-419. The nn modules hold the parameters under the reference's names (scale{i}_layer{j}.0.weight,
+    so net_D.pth loads unchanged); the computation is DiscriminatorPlan's kernel sequence."""
+
     def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, use_sigmoid=False, num_D=3,
                  getIntermFeat=False):
         super(MultiscaleDiscriminator, self).__init__()
         self.num_D, self.n_layers, self.getIntermFeat = num_D, n_layers, getIntermFeat
+        self.input_nc, self.ndf, self.use_sigmoid = input_nc, ndf, use_sigmoid
         for i in range(num_D):
             netD = NLayerDiscriminator(input_nc, ndf, n_layers, norm_layer, use_sigmoid, getIntermFeat)
             if getIntermFeat:
@@ -312,27 +436,62 @@ class MultiscaleDiscriminator(nn.Module):
             else:
                 setattr(self, 'layer' + str(i), netD.model)
         self.downsample = nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
+        self._plans = {}
+        self._packed_version = {}
 
-    def singleD_forward(self, model, input, keep_input=False):
-        if self.getIntermFeat:
-            result = [input]
-            for stage in model:
-                result.append(stage(result[-1]))
-            return result if keep_input else result[1:]
-        return [input, model(input)] if keep_input else [model(input)]
+    # ------------------------------------------------------------------ engine plumbing
+    def plan_for(self, batch, height, width, device):
+        from ....discriminator import DiscriminatorPlan
+        if not self.getIntermFeat:
+            raise NotImplementedError('jpdse_b200: MultiscaleDiscriminator(getIntermFeat=False) is outside the accelerated path '
+                                      '(Pix2PixHDModel always builds it with getIntermFeat=True, pix2pixHD_model.py:158-162)')
+        if self.use_sigmoid:
+            raise NotImplementedError('jpdse_b200: the sigmoid (non-LSGAN) discriminator is outside the accelerated path')
+        key = (batch, height, width, str(device))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = DiscriminatorPlan(self.input_nc, self.ndf, self.n_layers, self.num_D, batch, height, width, device)
+            plan.image_channels = 3
+            self._plans = {key: plan}
+            self._packed_version = {}
+        ver = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._packed_version.get(key) != ver:
+            with torch.cuda.device(device):
+                plan.load_weights(self.state_dict())
+            self._packed_version[key] = ver
+        return plan
 
     def forward(self, input, keep_input=False):
-        result, x = [], input
-        for i in range(self.num_D):
-            s = self.num_D - 1 - i  # the last-registered scale sees the full-resolution input
-            if self.getIntermFeat:
-                model = [getattr(self, 'scale%d_layer%d' % (s, j)) for j in range(self.n_layers + 2)]
-            else:
-                model = getattr(self, 'layer' + str(s))
-            result.append(self.singleD_forward(model, x, keep_input=keep_input))
-            if i != self.num_D - 1:
-                x = self.downsample(x)
-        return result
+        if keep_input:
+            raise NotImplementedError('jpdse_b200: keep_input (--match_raw_feat) is outside the accelerated path')
+        if not input.is_cuda:
+            raise JpdseError('jpdse_b200 MultiscaleDiscriminator runs on a B200 only; got a %s tensor (no CPU fallback)'
+                             % input.device)
+        B, _, H, W = input.shape
+        plan = self.plan_for(B, H, W, input.device)
+        outs = _DiscriminatorFunction.apply(self, plan, input, *self.parameters())
+        n = self.n_layers + 2
+        return [list(outs[i * n:(i + 1) * n]) for i in range(self.num_D)]
+
+    def fused_losses(self, input_label, fake_image, real_image):
+        """The discriminator half of get_train_loss (pix2pixHD_model.py:715-753) for the LSGAN configuration, without the
+        reference's redundancy: D(label, fake.detach()) and D(label, fake) are ONE forward (identical values; only the
+        autograd graph differs), the feature maps never leave NHWC bf16 (the L1 of the feature-matching loss is a
+        kernel over them), and the generator's backward through D skips the parameter gradients the reference throws
+        away. Returns (loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake) with the reference's values / gradients."""
+        B, _, H, W = fake_image.shape
+        dev = fake_image.device
+        plan = self.plan_for(B, H, W, dev)
+        plan.image_channels = fake_image.shape[1]
+        label = input_label.detach().contiguous().float()
+        with torch.cuda.device(dev):
+            s_real = plan.new_slot()
+            real = (s_real, plan.forward(s_real, label, real_image.detach().contiguous().float()))
+            s_fake = plan.new_slot()
+            fake = (s_fake, plan.forward(s_fake, label, fake_image.detach().contiguous().float()))
+        loss_D_fake, loss_D_real = _DiscriminatorLossD.apply(self, plan, fake, real, *self.parameters())
+        loss_G_GAN, loss_G_GAN_Feat = _DiscriminatorLossG.apply(plan, fake, real, fake_image)
+        return loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake
 
 
 class GANLoss(nn.Module):

@@ -9,7 +9,8 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (CONV1X1, CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_FULL, CONV7X7_PAD3, CONVT3X3_S2,
+from ._lib import (CONV1X1, CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, CONV4X4_S1, CONV4X4_S1_FULL, CONV4X4_S2,
+                   CONV4X4_S2_DGRAD, CONV7X7_FULL, CONV7X7_PAD3, CONVT3X3_S2, EPI_BIAS_ACT, EPI_BIAS_NCHW,
                    EPI_BIAS_TANH_NCHW, EPI_RAW, EPI_RAW_STATS, EPI_SIGN_NCHW, ConvDesc, JpdseError, check)
 
 _LABEL_DTYPES = {torch.float32: 0, torch.uint8: 1, torch.int64: 2}
@@ -122,9 +123,11 @@ def alloc_nhwc(B, H, W, C, device, slack_bytes=4096):
 class Conv:
     """One convolution of the generator: descriptor + packed bf16 weights (+ bias for the head)."""
 
-    def __init__(self, kind, epilogue, batch, in_h, in_w, in_pad, cin, cin_real, cout, device):
+    def __init__(self, kind, epilogue, batch, in_h, in_w, in_pad, cin, cin_real, cout, device, out_pad=0, out_hw=None,
+                 slope=0.0, cout_real=0):
         self.lib = _lib.load()
-        self.desc = ConvDesc(kind, epilogue, batch, in_h, in_w, in_pad, cin, cin_real, cout)
+        self.desc = ConvDesc(kind, epilogue, batch, in_h, in_w, in_pad, cin, cin_real, cout, out_pad,
+                             0 if out_hw is None else out_hw[0], 0 if out_hw is None else out_hw[1], float(slope), cout_real)
         nbytes = self.lib.jpdse_conv_packed_weight_bytes(ctypes.byref(self.desc))
         if nbytes == 0:
             raise JpdseError("conv descriptor rejected: %s" % self.lib.jpdse_last_error().decode())
@@ -134,7 +137,10 @@ class Conv:
         self.launches = self.lib.jpdse_conv_launch_count(ctypes.byref(self.desc))
         self.kind, self.epilogue = kind, epilogue
         self.out_hw = {CONV3X3_S2: (in_h // 2, in_w // 2), CONVT3X3_S2: (in_h * 2, in_w * 2),
-                       CONV3X3_FULL: (in_h + 2, in_w + 2), CONV7X7_FULL: (in_h + 6, in_w + 6)}.get(kind, (in_h, in_w))
+                       CONV3X3_FULL: (in_h + 2, in_w + 2), CONV7X7_FULL: (in_h + 6, in_w + 6),
+                       CONV4X4_S2: (in_h // 2 + 1, in_w // 2 + 1), CONV4X4_S1: (in_h + 1, in_w + 1),
+                       CONV4X4_S2_DGRAD: out_hw, CONV4X4_S1_FULL: (in_h - 1, in_w - 1)}.get(kind, (in_h, in_w))
+        self.out_pad = out_pad
         self.cout = cout
         self.batch = batch
 
@@ -231,6 +237,142 @@ def instnorm_backward_apply(dy, raw, stats, sums, dx, dx_pad, batch, height, wid
                                             width, channels, eps, _stream()))
     _count()
     return dx
+
+
+def instnorm_backward_reduce_act(g, g_pad, skip, raw, stats, dy, sums, batch, height, width, channels, slope, eps=1e-5):
+    """InstanceNorm backward reduce with a LeakyReLU(slope) mask (PatchGAN layers 1-3)."""
+    lib = _lib.load()
+    _need(g, "g", torch.bfloat16)
+    _need(raw, "raw", torch.bfloat16)
+    _need(stats, "stats", torch.float64)
+    _need(dy, "dy", torch.bfloat16)
+    _need(sums, "sums", torch.float64)
+    if skip is not None:
+        _need(skip, "skip", torch.bfloat16)
+    check(lib.jpdse_instnorm_backward_reduce_act(_ptr(g), g_pad, _ptr(skip), _ptr(raw), _ptr(stats), _ptr(dy), _ptr(sums),
+                                                 batch, height, width, channels, 1, float(slope), eps, _stream()))
+    _count()
+    return dy
+
+
+# ------------------------------------------------------------------------------------------------ discriminator / feature losses
+def d_input(a, b, out, c_pad, pool, out_pad=2):
+    """cat(a, b) over channels [+ AvgPool2d(3,2,1,count_include_pad=False)] -> interior of the zero-bordered NHWC bf16 `out`."""
+    lib = _lib.load()
+    _need(a, "a", torch.float32)
+    if b is not None:
+        _need(b, "b", torch.float32)
+    _need(out, "out", torch.bfloat16)
+    B, ca, H, W = a.shape
+    cb = 0 if b is None else b.shape[1]
+    if b is not None and (b.shape[0], b.shape[2], b.shape[3]) != (B, H, W):
+        raise JpdseError("d_input: a and b must share batch and spatial size")
+    Ho, Wo = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if pool else (H, W)
+    if tuple(out.shape) != (B, Ho + 2 * out_pad, Wo + 2 * out_pad, c_pad):
+        raise JpdseError("d_input: out must be %s, got %s" % ((B, Ho + 2 * out_pad, Wo + 2 * out_pad, c_pad), tuple(out.shape)))
+    check(lib.jpdse_d_input(_ptr(a), ca, _ptr(b), cb, _ptr(out), B, H, W, c_pad, int(bool(pool)), out_pad, _stream()))
+    _count()
+    return out
+
+
+def d_input_backward(g0, g1, c0, c, out=None):
+    """float32 (B,c,H,W) = g0[..., c0:c0+c] + AvgPool backward of g1[..., c0:c0+c] (g1 optional)."""
+    lib = _lib.load()
+    _need(g0, "g0", torch.bfloat16)
+    if g1 is not None:
+        _need(g1, "g1", torch.bfloat16)
+    B, H, W, cs = g0.shape
+    if g1 is not None and tuple(g1.shape) != (B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, cs):
+        raise JpdseError("d_input_backward: g1 has the wrong shape")
+    if out is None:
+        out = torch.empty((B, c, H, W), dtype=torch.float32, device=g0.device)
+    check(lib.jpdse_d_input_backward(_ptr(g0), _ptr(g1), _ptr(out), B, H, W, cs, c0, c, _stream()))
+    _count()
+    return out
+
+
+def instnorm_apply_act(raw, stats, out, batch, height, width, channels, out_pad, slope, eps=1e-5):
+    lib = _lib.load()
+    _need(raw, "raw", torch.bfloat16)
+    _need(stats, "stats", torch.float64)
+    _need(out, "out", torch.bfloat16)
+    check(lib.jpdse_instnorm_apply_act(_ptr(raw), _ptr(stats), _ptr(out), batch, height, width, channels, out_pad, float(slope),
+                                       eps, _stream()))
+    _count()
+    return out
+
+
+def act_backward(g, skip, f, d_pre, dbias, batch, height, width, channels, f_pad, out_pad, slope):
+    lib = _lib.load()
+    _need(g, "g", torch.bfloat16)
+    _need(f, "f", torch.bfloat16)
+    _need(d_pre, "d_pre", torch.bfloat16)
+    if skip is not None:
+        _need(skip, "skip", torch.bfloat16)
+    if dbias is not None:
+        _need(dbias, "dbias", torch.float32)
+    check(lib.jpdse_act_backward(_ptr(g), _ptr(skip), _ptr(f), _ptr(d_pre), _ptr(dbias), batch, height, width, channels, f_pad,
+                                 out_pad, float(slope), _stream()))
+    _count()
+    return d_pre
+
+
+def l1_pair(a, b, acc):
+    """acc (float64, 1 element) += sum |a - b| over two bf16 tensors of one stored shape."""
+    lib = _lib.load()
+    _need(a, "a", torch.bfloat16)
+    _need(b, "b", torch.bfloat16)
+    _need(acc, "acc", torch.float64)
+    if a.shape != b.shape:
+        raise JpdseError("l1_pair: shapes differ")
+    check(lib.jpdse_l1_pair(_ptr(a), _ptr(b), a.numel(), _ptr(acc), _stream()))
+    _count()
+    return acc
+
+
+def l1_pair_backward(a, b, out, scale_dev, scale_host, batch, height, width, channels, pad):
+    lib = _lib.load()
+    _need(a, "a", torch.bfloat16)
+    _need(b, "b", torch.bfloat16)
+    _need(out, "out", torch.bfloat16)
+    if scale_dev is not None:
+        _need(scale_dev, "scale", torch.float32)
+    check(lib.jpdse_l1_pair_backward(_ptr(a), _ptr(b), _ptr(out), _ptr(scale_dev), float(scale_host), batch, height, width,
+                                     channels, pad, _stream()))
+    _count()
+    return out
+
+
+def maxpool2x2(x, y, batch, height, width, channels, in_pad, out_pad):
+    lib = _lib.load()
+    _need(x, "x", torch.bfloat16)
+    _need(y, "y", torch.bfloat16)
+    check(lib.jpdse_maxpool2x2(_ptr(x), _ptr(y), batch, height, width, channels, in_pad, out_pad, _stream()))
+    _count()
+    return y
+
+
+def maxpool2x2_backward(x, g, dx, batch, height, width, channels, in_pad):
+    lib = _lib.load()
+    _need(x, "x", torch.bfloat16)
+    _need(g, "g", torch.bfloat16)
+    _need(dx, "dx", torch.bfloat16)
+    check(lib.jpdse_maxpool2x2_backward(_ptr(x), _ptr(g), _ptr(dx), batch, height, width, channels, in_pad, _stream()))
+    _count()
+    return dx
+
+
+def nhwc_pad_to_nchw(x, channels, pad, out=None):
+    """stored bf16 (B,H+2pad,W+2pad,Cs) -> float32 (B,channels,H,W)"""
+    lib = _lib.load()
+    _need(x, "x", torch.bfloat16)
+    B, Hs, Ws, cs = x.shape
+    H, W = Hs - 2 * pad, Ws - 2 * pad
+    if out is None:
+        out = torch.empty((B, channels, H, W), dtype=torch.float32, device=x.device)
+    check(lib.jpdse_nhwc_pad_to_nchw_f32(_ptr(x), _ptr(out), B, channels, H, W, pad, cs, _stream()))
+    _count()
+    return out
 
 
 def tanh_backward_nchw(grad_out, out, d_pre, dbias):

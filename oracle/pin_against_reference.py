@@ -151,7 +151,8 @@ def main():
                                 mse=np.float32(torch.nn.MSELoss()(ta, tb).item()))
     print("eval metric: oracle tensor2im == reference (bit-exact bytes); L1 / MSE within 2 float32 ulp; golden written")
 
-    # ---------------------------------------------------------------- training-step networks of the mirror
+    # ---------------------------------------------------------------- training-step networks: discriminator, losses, VGG
+    from oracle import discriminator_oracle as dorc
     torch.manual_seed(7)
     Dr = networks.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[])
     torch.manual_seed(7)
@@ -159,13 +160,66 @@ def main():
     sr, so = Dr.state_dict(), Do.state_dict()
     assert list(sr.keys()) == list(so.keys()) and all(torch.equal(sr[k], so[k]) for k in sr), "netD init/keys differ"
     xd = torch.randn(2, 39, 64, 128, generator=g)
-    for keep in (False, True):
-        fr, fo = Dr(xd, keep), Do(xd, keep)
-        assert all(torch.equal(a, b) for s_, t_ in zip(fr, fo) for a, b in zip(s_, t_)), "netD outputs differ"
-    gr, go = networks.GANLoss(use_lsgan=True), ours.GANLoss(use_lsgan=True)
+    fr = Dr(xd)
+    fo = dorc.discriminator_forward(sr, xd, 3, 2)
+    assert len(fr) == len(fo) == 2 and all(len(a) == len(b) == 5 for a, b in zip(fr, fo))
+    assert all(torch.equal(a, b) for s_, t_ in zip(fr, fo) for a, b in zip(s_, t_)), "oracle netD != reference netD"
+    gr = networks.GANLoss(use_lsgan=True)
     for target_is_real in (True, False):
-        assert torch.equal(gr(Dr(xd), target_is_real), go(Do(xd), target_is_real)), "GANLoss differs"
-    print("training mirror: define_D / MultiscaleDiscriminator / GANLoss == reference (bit-exact)")
+        assert torch.equal(gr(Dr(xd), target_is_real), dorc.gan_loss(dorc.discriminator_forward(sr, xd, 3, 2), target_is_real))
+    # the discriminator half of get_train_loss (pix2pixHD_model.py:715-753) incl. its autograd: losses and the gradients
+    # w.r.t. every netD parameter (loss_D) and w.r.t. the fake image (loss_G_GAN + 10 * loss_G_GAN_Feat)
+    lab, fake, real = xd[:, :36].clone(), xd[:, 36:].clone().requires_grad_(True), torch.randn(2, 3, 64, 128, generator=g)
+    crit_feat = torch.nn.L1Loss()
+    pfp = Dr(torch.cat((lab.detach(), fake.detach()), 1))
+    l_d_fake = gr(pfp, False)
+    pr = Dr(torch.cat((lab.detach(), real.detach()), 1))
+    l_d_real = gr(pr, True)
+    pf = Dr(torch.cat((lab, fake), 1))
+    l_g_gan = gr(pf, True)
+    l_fm = 0
+    for i in range(2):
+        for j in range(len(pf[i]) - 1):
+            l_fm += 0.5 * crit_feat(pf[i][j], pr[i][j].detach())
+    (l_g_gan + 10.0 * l_fm).backward()
+    g_fake_ref = fake.grad.clone()
+    Dr.zero_grad()
+    ((l_d_fake + l_d_real) * 0.5).backward()
+    sdg = {k: v.detach().clone().requires_grad_(True) for k, v in sr.items()}
+    fake2 = fake.detach().clone().requires_grad_(True)
+    o_gan, o_fm, o_real, o_fake = dorc.discriminator_losses(sdg, lab, fake2, real, 3, 2)
+    assert torch.equal(o_gan, l_g_gan) and torch.equal(o_fm, l_fm) and torch.equal(o_real, l_d_real) and torch.equal(o_fake, l_d_fake)
+    (o_gan + 10.0 * o_fm).backward()
+    assert torch.equal(fake2.grad, g_fake_ref), "oracle d(loss_G)/d(fake) != reference"
+    for v in sdg.values():
+        v.grad = None
+    ((o_fake + o_real) * 0.5).backward()
+    for name, p_ in Dr.named_parameters():
+        assert torch.equal(p_.grad, sdg[name].grad), "oracle netD gradient != reference for %s" % name
+    np.savez_compressed(os.path.join(GOLDEN, "discriminator_small.npz"), x=xd.numpy(), real=real.numpy(),
+                        losses=np.array([float(l_g_gan), float(l_fm), float(l_d_real), float(l_d_fake)]),
+                        final0=fr[0][-1].detach().numpy(), final1=fr[1][-1].detach().numpy(),
+                        feat_sums=np.array([float(t_.double().sum()) for s_ in fr for t_ in s_]),
+                        g_fake_sum=np.array([float(g_fake_ref.double().sum()), float(g_fake_ref.double().abs().sum())]),
+                        weight_sum=float(sum(v.double().sum() for v in sr.values())))
+    print("discriminator: oracle netD / GANLoss / feature matching == reference (values and autograd, bit-exact); same keys "
+          "and init as our define_D; golden written")
+    # VGG19 perceptual loss (networks.py:124-139, 474-504) with random weights (the pretrained checkpoint is a download)
+    import torchvision
+    _v = torchvision.models.vgg19
+    networks.models.vgg19 = lambda pretrained=False, **k: _v(weights=None)
+    torch.manual_seed(3)
+    vl = networks.VGGLoss([])
+    vx, vy = torch.randn(1, 3, 32, 64, generator=g), torch.randn(1, 3, 32, 64, generator=g)
+    vsd = vl.vgg.state_dict()
+    with torch.no_grad():
+        assert all(torch.equal(a, b) for a, b in zip(vl.vgg(vx), dorc.vgg_forward(vsd, vx))), "oracle VGG19 != reference"
+        assert torch.equal(vl(vx, vy), dorc.vgg_loss(vsd, vx, vy)), "oracle VGGLoss != reference"
+    os.environ["JPDSE_VGG_RANDOM"] = "1"
+    torch.manual_seed(3)
+    vo = ours.Vgg19()
+    assert list(vo.state_dict().keys()) == list(vsd.keys()) and all(torch.equal(vo.state_dict()[k], vsd[k]) for k in vsd)
+    print("VGG19 / VGGLoss: oracle == reference (bit-exact); our Vgg19 has the same keys and (seeded) init")
 
     # ---------------------------------------------------------------- quantisers
     q = (torch.randn(4099, generator=g) * 3).float()

@@ -1,0 +1,395 @@
+"""GPU parity tests of the PatchGAN discriminator path on a B200, through the C ABI.
+
+Reference: MultiscaleDiscriminator / NLayerDiscriminator (ctu/models/pix2pixHD_networks/networks.py:371-471), GANLoss
+(:80-122), discriminate + feature matching (ctu/models/pix2pixHD_model.py:451-460, 715-753). The checker is
+oracle/discriminator_oracle.py, pinned bit-identical to the reference (values and autograd) by
+oracle/pin_against_reference.py, and torch CPU fp32 ops on the same bf16-rounded operands for the single kernels.
+
+Tolerances
+  single conv / data gradient (bf16 operands, fp32 accumulate): |err| <= 2^-7 of the output max (one bf16 rounding)
+  weight gradient: |err| <= 2e-3 * max|ref| (fp32 summation order only)
+  bandwidth kernels on identical operands: one bf16 rounding of the result; pooling / concat of the input: bit-exact
+  whole discriminator (bf16 kernels) vs the fp32 oracle: every feature map |err| mean <= 2 % of its RMS, losses within
+  2 %, gradients cosine >= 0.99 and norm within 5 % (w.r.t. the fake image and w.r.t. every netD weight)
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import discriminator_oracle as dorc
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+def _ops():
+    import jpdse_b200  # noqa: F401
+    from jpdse_b200 import ops
+    return ops
+
+
+def _networks():
+    return importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
+
+
+def _stored(t, pad, c_pad=None):
+    """fp32 NCHW cpu -> bf16 NHWC with a zero border (and zero pad channels)"""
+    t = F.pad(t, (pad, pad, pad, pad))
+    t = t.permute(0, 2, 3, 1).contiguous()
+    if c_pad is not None and c_pad > t.shape[-1]:
+        t = F.pad(t, (0, c_pad - t.shape[-1]))
+    return t.bfloat16().contiguous()
+
+
+def _nchw(t, pad=0, c=None):
+    t = t.float().cpu()
+    if pad:
+        t = t[:, pad:-pad, pad:-pad]
+    t = t.permute(0, 3, 1, 2)
+    return t if c is None else t[:, :c]
+
+
+def _cos(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------ 4x4 convolutions
+@pytest.mark.parametrize("case", [
+    ("s2", 2, 16, 32, 39, 64), ("s2", 1, 33, 65, 64, 128), ("s2", 2, 64, 128, 128, 256), ("s2", 1, 257, 513, 64, 128),
+    ("s1", 2, 9, 17, 256, 512), ("s1", 1, 33, 65, 128, 128), ("s1", 1, 66, 130, 512, 1),
+])
+def test_conv4x4_forward(cuda, case):
+    ops = _ops()
+    from jpdse_b200._lib import CONV4X4_S1, CONV4X4_S2, EPI_BIAS_ACT, EPI_BIAS_NCHW, EPI_RAW_STATS
+    name, B, H, W, cin_real, cout = case
+    cin = (cin_real + 63) // 64 * 64
+    g = torch.Generator().manual_seed(H * 7 + cout)
+    x = _bf(torch.randn(B, cin_real, H, W, generator=g))
+    w = _bf(torch.randn(cout, cin_real, 4, 4, generator=g) * 0.05)
+    bias = torch.randn(cout, generator=g) * 0.1
+    stride = 2 if name == "s2" else 1
+    ref = F.conv2d(x, w, None, stride=stride, padding=2)
+    kind = CONV4X4_S2 if name == "s2" else CONV4X4_S1
+    xs = _stored(x, 2, cin).to(cuda)
+    oh, ow = ref.shape[2:]
+    scale = float(ref.abs().max())
+    if cout == 1:
+        cv = ops.Conv(kind, EPI_BIAS_NCHW, B, H, W, 2, cin, cin_real, cout, cuda)
+        cv.pack(w.to(cuda), bias.to(cuda))
+        y = torch.empty(B, 1, oh, ow, device=cuda)
+        cv.forward(xs, y)
+        assert float((y.cpu() - (ref + bias.view(1, -1, 1, 1))).abs().max()) <= 2e-3 * scale + 1e-5
+        return
+    # raw + statistics
+    cv = ops.Conv(kind, EPI_RAW_STATS, B, H, W, 2, cin, cin_real, cout, cuda)
+    assert cv.out_hw == (oh, ow)
+    cv.pack(w.to(cuda))
+    raw = torch.empty(B, oh, ow, cout, dtype=torch.bfloat16, device=cuda)
+    stats = torch.zeros(B, cout, 2, dtype=torch.float64, device=cuda)
+    cv.forward(xs, raw, stats)
+    got = _nchw(raw)
+    assert float((got - ref).abs().max()) <= 2.0 ** -7 * scale
+    s1, s2 = got.double().sum(dim=(2, 3)), (got.double() ** 2).sum(dim=(2, 3))
+    assert torch.allclose(stats[:, :, 0].cpu(), s1, rtol=1e-5, atol=1e-3) and torch.allclose(stats[:, :, 1].cpu(), s2, rtol=1e-5, atol=1e-3)
+    # bias + LeakyReLU into the interior of a zero-bordered tensor
+    cv2 = ops.Conv(kind, EPI_BIAS_ACT, B, H, W, 2, cin, cin_real, cout, cuda, out_pad=2, slope=0.2)
+    cv2.pack(w.to(cuda), bias.to(cuda))
+    out = ops.alloc_nhwc(B, oh + 4, ow + 4, cout, cuda)
+    out.fill_(7.0)  # the border must not be touched
+    cv2.forward(xs, out)
+    want = F.leaky_relu(ref + bias.view(1, -1, 1, 1), 0.2)
+    assert float((_nchw(out, 2) - want).abs().max()) <= 2.0 ** -7 * float(want.abs().max())
+    border = out.float().cpu().clone()
+    border[:, 2:-2, 2:-2] = 7.0
+    assert float((border - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", [
+    ("s2", 2, 16, 32, 39, 64), ("s2", 1, 33, 65, 64, 128), ("s2", 1, 129, 257, 128, 256), ("s2", 2, 64, 128, 64, 128),
+    ("s1", 2, 9, 17, 256, 512), ("s1", 1, 33, 65, 128, 128), ("s1", 1, 66, 130, 512, 1),
+])
+def test_conv4x4_data_and_weight_gradients(cuda, case):
+    ops = _ops()
+    from jpdse_b200._lib import CONV4X4_S1, CONV4X4_S1_FULL, CONV4X4_S2, CONV4X4_S2_DGRAD, EPI_RAW, EPI_RAW_STATS
+    name, B, H, W, cin_real, cout = case
+    cin, cst = (cin_real + 63) // 64 * 64, (cout + 63) // 64 * 64
+    g = torch.Generator().manual_seed(H * 11 + cout)
+    x = _bf(torch.randn(B, cin_real, H, W, generator=g)).requires_grad_(True)
+    w = _bf(torch.randn(cout, cin_real, 4, 4, generator=g) * 0.05).requires_grad_(True)
+    stride = 2 if name == "s2" else 1
+    y = F.conv2d(x, w, None, stride=stride, padding=2)
+    dy = _bf(torch.randn(y.shape, generator=g))
+    y.backward(dy)
+    oh, ow = y.shape[2:]
+    dys = _stored(dy, 2, cst).to(cuda)
+    if name == "s2":
+        dg = ops.Conv(CONV4X4_S2_DGRAD, EPI_RAW, B, oh, ow, 2, cst, cout, cin, cuda, out_hw=(H, W), cout_real=cin_real)
+        fwd = ops.Conv(CONV4X4_S2, EPI_RAW_STATS if cout >= 32 else EPI_RAW, B, H, W, 2, cin, cin_real, cout, cuda)
+    else:
+        dg = ops.Conv(CONV4X4_S1_FULL, EPI_RAW, B, oh, ow, 2, cst, cout, cin, cuda, cout_real=cin_real)
+        from jpdse_b200._lib import EPI_BIAS_NCHW
+        fwd = ops.Conv(CONV4X4_S1, EPI_RAW_STATS if cout >= 32 else EPI_BIAS_NCHW, B, H, W, 2, cin, cin_real, cout, cuda)
+    dg.pack(w.detach().to(cuda))
+    assert dg.out_hw == (H, W)
+    dx = torch.full((B, H, W, cin), 3.0, dtype=torch.bfloat16, device=cuda)
+    dg.forward(dys, dx)
+    got = _nchw(dx)
+    assert float((got[:, :cin_real] - x.grad).abs().max()) <= 2.0 ** -7 * float(x.grad.abs().max())
+    if cin > cin_real:
+        assert float(got[:, cin_real:].abs().max()) == 0.0  # stored pad channels carry no gradient
+    xs = _stored(x.detach(), 2, cin).to(cuda)
+    dw = torch.empty(cout, cin_real, 4, 4, device=cuda)
+    fwd.wgrad(xs, dys, 2, dw)
+    assert float((dw.cpu() - w.grad).abs().max()) <= 2e-3 * float(w.grad.abs().max())
+    fwd.wgrad(xs, dys, 2, dw, accumulate=True)
+    assert float((dw.cpu() - 2 * w.grad).abs().max()) <= 4e-3 * float(w.grad.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ bandwidth kernels
+@pytest.mark.parametrize("H,W", [(16, 32), (33, 47), (64, 128)])
+def test_d_input_and_its_backward(cuda, H, W):
+    ops = _ops()
+    g = torch.Generator().manual_seed(H)
+    B = 2
+    a = torch.randn(B, 36, H, W, generator=g)
+    b = torch.randn(B, 3, H, W, generator=g)
+    x = torch.cat((a, b), 1)
+    for pool in (False, True):
+        ref = F.avg_pool2d(x, 3, stride=2, padding=1, count_include_pad=False) if pool else x
+        Ho, Wo = ref.shape[2:]
+        out = ops.alloc_nhwc(B, Ho + 4, Wo + 4, 64, cuda)
+        ops.d_input(a.to(cuda), b.to(cuda), out, 64, pool)
+        got = out.float().cpu()
+        # the pooled mean is s / count in float32 like ATen's; compare after the same bf16 rounding with 1-ulp slack
+        want = _bf(ref)
+        diff = (_nchw(got, 2, 39) - want).abs()
+        assert float(diff.max()) <= (2.0 ** -8 * float(want.abs().max()) if pool else 0.0)
+        assert float(got[:, 2:-2, 2:-2, 39:].abs().max()) == 0.0 and float(got[:, :2].abs().max()) == 0.0
+    # backward: gradient w.r.t. the image channels (and w.r.t. everything) through identity + pool
+    xr = x.clone().requires_grad_(True)
+    pooled = F.avg_pool2d(xr, 3, stride=2, padding=1, count_include_pad=False)
+    g0 = _bf(torch.randn(B, 39, H, W, generator=g))
+    g1 = _bf(torch.randn(pooled.shape, generator=g))
+    ((xr * g0).sum() + (pooled * g1).sum()).backward()
+    g0s, g1s = _stored(g0, 0, 64).to(cuda), _stored(g1, 0, 64).to(cuda)
+    got = ops.d_input_backward(g0s, g1s, 36, 3).cpu()
+    assert torch.allclose(got, xr.grad[:, 36:], rtol=1e-5, atol=1e-5)
+    got_all = ops.d_input_backward(g0s, g1s, 0, 39).cpu()
+    assert torch.allclose(got_all, xr.grad, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(ops.d_input_backward(g0s, None, 36, 3).cpu(), g0[:, 36:], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("C,H,W", [(128, 17, 33), (512, 9, 18), (64, 30, 40)])
+def test_instnorm_act_forward_and_backward(cuda, C, H, W):
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + H)
+    B = 2
+    raw = _bf(torch.randn(B, C, H, W, generator=g) * 2 + 0.3).requires_grad_(True)
+    y = F.leaky_relu(F.instance_norm(raw, eps=1e-5), 0.2)
+    gy = _bf(torch.randn(B, C, H, W, generator=g))
+    sk = _bf(torch.randn(B, C, H, W, generator=g))
+    y.backward(gy + sk)
+    raws = _stored(raw.detach(), 0).to(cuda)
+    st = torch.stack((raw.detach().double().sum(dim=(2, 3)), (raw.detach().double() ** 2).sum(dim=(2, 3))), -1).to(cuda).contiguous()
+    out = ops.alloc_nhwc(B, H + 4, W + 4, C, cuda)
+    out.fill_(5.0)
+    ops.instnorm_apply_act(raws, st, out, B, H, W, C, 2, 0.2)
+    got = out.float().cpu()
+    assert float((_nchw(got, 2) - y.detach()).abs().max()) <= 2.0 ** -7 * float(y.abs().max())
+    ring = got.clone()
+    ring[:, 2:-2, 2:-2] = 0
+    assert float(ring.abs().max()) == 0.0  # zero border written
+    dy = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=cuda)
+    sums = torch.zeros(B, C, 2, dtype=torch.float64, device=cuda)
+    ops.instnorm_backward_reduce_act(_stored(gy, 0).to(cuda), 0, _stored(sk, 0).to(cuda), raws, st, dy, sums, B, H, W, C, 0.2)
+    dx = ops.alloc_nhwc(B, H + 4, W + 4, C, cuda)
+    ops.instnorm_backward_apply(dy, raws, st, sums, dx, 2, B, H, W, C)
+    assert float((_nchw(dx, 2) - raw.grad).abs().max()) <= 2.0 ** -6 * float(raw.grad.abs().max())
+
+
+def test_act_backward_l1_pair_and_maxpool(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 64, 18, 26
+    pre = _bf(torch.randn(B, C, H, W, generator=g)).requires_grad_(True)
+    f = F.leaky_relu(pre, 0.2)
+    gy, sk = _bf(torch.randn(B, C, H, W, generator=g)), _bf(torch.randn(B, C, H, W, generator=g))
+    f.backward(gy + sk)
+    fs = _stored(_bf(f.detach()), 2).to(cuda)
+    d_pre = ops.alloc_nhwc(B, H + 4, W + 4, C, cuda)
+    d_pre.fill_(9.0)
+    db = torch.zeros(C, device=cuda)
+    ops.act_backward(_stored(gy, 0).to(cuda), _stored(sk, 0).to(cuda), fs, d_pre, db, B, H, W, C, 2, 2, 0.2)
+    got = _nchw(d_pre, 2)
+    assert float((got - pre.grad).abs().max()) <= 2.0 ** -7 * float(pre.grad.abs().max())
+    assert float(d_pre.float().cpu()[:, :2].abs().max()) == 0.0
+    assert torch.allclose(db.cpu(), got.sum(dim=(0, 2, 3)), rtol=1e-4, atol=1e-3)
+    # ReLU flavour without a second gradient / bias
+    ops.act_backward(_stored(gy, 0).to(cuda), None, fs, d_pre, None, B, H, W, C, 2, 2, 0.0)
+    want = gy * (f.detach() > 0)
+    assert float((_nchw(d_pre, 2) - want).abs().max()) == 0.0
+    # L1 between two stored feature maps and its gradient
+    a, b = _bf(torch.randn(B, C, H, W, generator=g)), _bf(torch.randn(B, C, H, W, generator=g))
+    b[:, :, 0, 0] = a[:, :, 0, 0]  # exact ties -> zero gradient
+    sa, sb = _stored(a, 2).to(cuda), _stored(b, 2).to(cuda)
+    acc = torch.zeros(1, dtype=torch.float64, device=cuda)
+    ops.l1_pair(sa, sb, acc)
+    assert abs(float(acc) - float((a - b).abs().double().sum())) <= 1e-5 * float((a - b).abs().double().sum())
+    scale = torch.tensor([0.5], device=cuda)
+    out = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=cuda)
+    ops.l1_pair_backward(sa, sb, out, scale, 0.25, B, H, W, C, 2)
+    assert float((_nchw(out) - 0.125 * torch.sign(a - b)).abs().max()) == 0.0
+    # MaxPool2d(2, 2) and its backward (first maximum of the window takes the gradient, like ATen)
+    x = _bf(torch.randn(B, C, H, W, generator=g))
+    x[:, :, 0, 0] = x[:, :, 0, 1]  # a tie inside a window
+    xr = x.clone().requires_grad_(True)
+    y = F.max_pool2d(xr, 2, 2)
+    gp = _bf(torch.randn(y.shape, generator=g))
+    y.backward(gp)
+    xs = _stored(x, 1).to(cuda)
+    ys = ops.alloc_nhwc(B, H // 2 + 2, W // 2 + 2, C, cuda)
+    ops.maxpool2x2(xs, ys, B, H, W, C, 1, 1)
+    assert float((_nchw(ys, 1) - y.detach()).abs().max()) == 0.0 and float(ys.float().cpu()[:, 0].abs().max()) == 0.0
+    dx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=cuda)
+    ops.maxpool2x2_backward(xs, _stored(gp, 0).to(cuda), dx, B, H, W, C, 1)
+    assert float((_nchw(dx) - xr.grad).abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------ whole discriminator
+def _setup(cuda, B, H, W, seed=7):
+    nw = _networks()
+    torch.manual_seed(seed)
+    netD = nw.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[])
+    sd = {k: v.detach().clone() for k, v in netD.state_dict().items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    lab_ids = torch.randint(0, 35, (B, H // 8, W // 8), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2)
+    label = F.one_hot(lab_ids, 35).permute(0, 3, 1, 2).float()
+    edge = (torch.rand(B, 1, H, W, generator=g) < 0.07).float()
+    input_label = torch.cat((label, edge), 1)
+    real = torch.rand(B, 3, H, W, generator=g) - 0.5
+    fake = (real + 0.1 * torch.randn(B, 3, H, W, generator=g)).clamp(-1, 1)
+    return netD.to(cuda), sd, input_label, fake, real
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 128, 256), (1, 72, 104)])
+def test_discriminator_features_vs_oracle(cuda, B, H, W):
+    """netD.forward (the reference's API: list over scales of the n_layers + 2 intermediate outputs, float32 NCHW)."""
+    netD, sd, input_label, fake, real = _setup(cuda, B, H, W)
+    x = torch.cat((input_label, fake), 1)
+    with torch.no_grad():
+        ref = dorc.discriminator_forward(sd, x, 3, 2)
+        emu = dorc.discriminator_forward(sd, x, 3, 2, round_fn=_bf)
+        got = netD(x.to(cuda))
+    assert len(got) == 2 and all(len(s_) == 5 for s_ in got)
+    for i in range(2):
+        for j in range(5):
+            a, r, e = got[i][j].cpu(), ref[i][j], emu[i][j]
+            assert a.shape == r.shape and a.dtype == torch.float32
+            rms = float(r.pow(2).mean().sqrt())
+            assert float((a - r).abs().mean()) <= 0.02 * rms, (i, j, float((a - r).abs().mean()), rms)
+            assert float((a - e).abs().mean()) <= 0.01 * rms, (i, j)  # same-arithmetic emulation: tighter
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 128, 256)])
+def test_discriminator_losses_and_gradients_vs_oracle(cuda, B, H, W, monkeypatch):
+    """The discriminator half of get_train_loss (pix2pixHD_model.py:715-753): loss values, d(loss_G)/d(fake image) and
+    d(loss_D)/d(every netD parameter), fused route and the reference's call sequence (one autograd node per netD call),
+    both against the oracle's autograd (pinned bit-identical to the reference)."""
+    netD, sd, input_label, fake, real = _setup(cuda, B, H, W)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    fake_o = fake.clone().requires_grad_(True)
+    o_gan, o_fm, o_real, o_fake = dorc.discriminator_losses(sdg, input_label, fake_o, real, 3, 2)
+    (o_gan + 10.0 * o_fm).backward()
+    ref_gfake = fake_o.grad.clone()
+    for v in sdg.values():
+        v.grad = None
+    ((o_fake + o_real) * 0.5).backward()
+    ref_losses = [float(v) for v in (o_gan, o_fm, o_real, o_fake)]
+
+    def run(fused):
+        for p in netD.parameters():
+            p.grad = None
+        f = fake.clone().to(cuda).requires_grad_(True)
+        il, re = input_label.to(cuda), real.to(cuda)
+        if fused:
+            l_gan, l_fm, l_real, l_fake = netD.fused_losses(il, f, re)
+        else:
+            crit = torch.nn.MSELoss()
+
+            def gan(pred, val):
+                return sum(crit(s_[-1], torch.full_like(s_[-1], val)) for s_ in pred)
+            pfp = netD(torch.cat((il.detach(), f.detach()), 1))
+            l_fake = gan(pfp, 0.0)
+            pr = netD(torch.cat((il.detach(), re.detach()), 1))
+            l_real = gan(pr, 1.0)
+            pf = netD(torch.cat((il, f), 1))
+            l_gan = gan(pf, 1.0)
+            l_fm = sum(0.5 * F.l1_loss(pf[i][j], pr[i][j].detach()) for i in range(2) for j in range(4))
+        (l_gan + 10.0 * l_fm).backward()
+        gfake = f.grad.detach().cpu().clone()
+        for p in netD.parameters():
+            p.grad = None  # optimizer_D.zero_grad() (pix2pixHD_trainer.py:73)
+        ((l_fake + l_real) * 0.5).backward()
+        torch.cuda.synchronize()
+        return [float(v) for v in (l_gan, l_fm, l_real, l_fake)], gfake, {n: p.grad.detach().cpu().clone() for n, p in netD.named_parameters()}
+
+    for fused in (True, False):
+        losses, gfake, pgrads = run(fused)
+        for got, want in zip(losses, ref_losses):
+            assert abs(got - want) <= 0.02 * abs(want) + 1e-4, (fused, losses, ref_losses)
+        c = _cos(gfake, ref_gfake)
+        ratio = float(gfake.norm() / ref_gfake.norm())
+        assert c >= 0.99 and 0.95 <= ratio <= 1.05, "fused=%s d(loss_G)/d(fake): cosine %.5f norm ratio %.4f" % (fused, c, ratio)
+        for name, gr in pgrads.items():
+            ref = sdg[name].grad
+            if name.endswith(".bias") and any(name.startswith("scale%d_layer%d." % (s_, j)) for s_ in range(2) for j in (1, 2, 3)):
+                assert float(gr.abs().max()) == 0.0  # bias in front of InstanceNorm: exactly zero
+                continue
+            c = _cos(gr, ref)
+            ratio = float(gr.norm() / (ref.norm() + 1e-30))
+            assert c >= 0.99 and 0.95 <= ratio <= 1.05, "fused=%s %s: cosine %.5f norm ratio %.4f" % (fused, name, c, ratio)
+
+
+def test_discriminator_golden_and_state_dict(cuda, golden_dir):
+    """tests/golden/discriminator_small.npz (outputs of the imported reference): seeded init equality, final maps and losses."""
+    g = np.load(os.path.join(golden_dir, "discriminator_small.npz"))
+    nw = _networks()
+    torch.manual_seed(7)
+    netD = nw.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[])
+    assert abs(float(sum(v.double().sum() for v in netD.state_dict().values())) - float(g["weight_sum"])) < 1e-6
+    netD = netD.to(cuda)
+    x = torch.from_numpy(g["x"]).to(cuda)
+    with torch.no_grad():
+        out = netD(x)
+    for i, key in enumerate(("final0", "final1")):
+        ref = torch.from_numpy(g[key])
+        assert float((out[i][-1].cpu() - ref).abs().mean()) <= 0.03 * float(ref.pow(2).mean().sqrt())
+    lab, fake, real = x[:, :36], x[:, 36:].clone().requires_grad_(True), torch.from_numpy(g["real"]).to(cuda)
+    losses = [float(v) for v in netD.fused_losses(lab, fake, real)]
+    for got, want in zip(losses, g["losses"]):
+        assert abs(got - float(want)) <= 0.02 * abs(float(want)) + 1e-4
+
+
+def test_discriminator_guards(cuda):
+    import jpdse_b200
+    nw = _networks()
+    netD = nw.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[0])
+    with pytest.raises(jpdse_b200.JpdseError):
+        netD(torch.zeros(1, 39, 32, 64))  # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        netD(torch.zeros(1, 39, 32, 64, device=cuda), keep_input=True)
+    # a pass that was overwritten (more live passes than the plan keeps) must refuse its backward
+    x = torch.randn(1, 39, 32, 64, device=cuda)
+    first = netD(x)
+    for _ in range(3):
+        netD(x)
+    with pytest.raises(jpdse_b200.JpdseError):
+        first[0][-1].sum().backward()

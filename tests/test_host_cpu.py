@@ -27,7 +27,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, n), "libjpdse_b200.so does not export %s" % n
     # every declared function has a ctypes signature and vice versa
     assert sorted(jpdse_b200._lib.SIGNATURES) == names
-    assert lib.jpdse_abi_version() == 1
+    assert lib.jpdse_abi_version() == jpdse_b200._lib.ABI_VERSION == 2
     assert lib.jpdse_last_error() is not None
 
 
@@ -35,7 +35,7 @@ def test_conv_desc_validation_without_gpu():
     import jpdse_b200
     from jpdse_b200._lib import CONV3X3_PAD1, CONV7X7_PAD3, EPI_RAW_STATS, ConvDesc
     lib = jpdse_b200._lib.load()
-    assert ctypes.sizeof(ConvDesc) == 9 * 4
+    assert ctypes.sizeof(ConvDesc) == 14 * 4  # ABI version 2: + out_pad, out_h, out_w, slope, cout_real
     good = ConvDesc(CONV3X3_PAD1, EPI_RAW_STATS, 16, 32, 64, 1, 1024, 1024, 1024)
     assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(good)) == 1024 * 9 * 1024 * 2
     assert lib.jpdse_conv_flops(ctypes.byref(good)) == 16 * 38654705664.0
@@ -46,6 +46,19 @@ def test_conv_desc_validation_without_gpu():
     assert b"multiple of 64" in lib.jpdse_last_error()
     bad2 = ConvDesc(CONV3X3_PAD1, EPI_RAW_STATS, 1, 32, 64, 0, 64, 64, 64)  # PAD1 kind needs the border
     assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(bad2)) == 0
+    # PatchGAN convs (networks.py:430-449): 4x4, zero pad 2; odd sizes; data gradients need the forward input size
+    from jpdse_b200._lib import CONV4X4_S1, CONV4X4_S1_FULL, CONV4X4_S2, CONV4X4_S2_DGRAD, EPI_BIAS_ACT, EPI_BIAS_NCHW, EPI_RAW
+    d0 = ConvDesc(CONV4X4_S2, EPI_BIAS_ACT, 2, 512, 1024, 2, 64, 39, 64, 2, 0, 0, 0.2, 0)
+    assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(d0)) == 64 * 16 * 64 * 2
+    assert lib.jpdse_conv_flops(ctypes.byref(d0)) == 2.0 * 2 * 257 * 513 * 16 * 39 * 64
+    d4 = ConvDesc(CONV4X4_S1, EPI_BIAS_NCHW, 2, 66, 130, 2, 512, 512, 1)
+    assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(d4)) == 16 * 16 * 512 * 2  # N tile of 16 for the 1-channel output
+    dg = ConvDesc(CONV4X4_S2_DGRAD, EPI_RAW, 2, 129, 257, 2, 128, 128, 64, 0, 257, 513, 0.0, 64)
+    assert lib.jpdse_conv_launch_count(ctypes.byref(dg)) == 4
+    dg_bad = ConvDesc(CONV4X4_S2_DGRAD, EPI_RAW, 2, 129, 257, 2, 128, 128, 64, 0, 255, 513, 0.0, 64)
+    assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(dg_bad)) == 0 and b"forward input size" in lib.jpdse_last_error()
+    df = ConvDesc(CONV4X4_S1_FULL, EPI_RAW, 2, 66, 130, 2, 512, 512, 256)
+    assert lib.jpdse_conv_packed_weight_bytes(ctypes.byref(df)) == 256 * 16 * 512 * 2
 
 
 def _networks():

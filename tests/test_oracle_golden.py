@@ -127,3 +127,26 @@ def test_eval_metric_golden(golden_dir):
     assert np.array_equal(np.stack([orc.tensor2im_uint8(t) for t in b]), g["b_u8"])
     assert orc.eval_distortion(a, b, mode="l1") == g["l1"]   # sums below 2^24: the reference's float32 mean is exact
     assert orc.eval_distortion(a, b, mode="mse") == g["mse"]
+
+
+def test_discriminator_golden(golden_dir):
+    """netD / GANLoss / feature matching of the reference (networks.py:371-471, 80-122; pix2pixHD_model.py:715-753):
+    outputs stored by oracle/pin_against_reference.py from the imported reference, reproduced by the oracle."""
+    import importlib
+    from oracle import discriminator_oracle as dorc
+    nw = importlib.import_module("jpd-se_b200.ctu.models.pix2pixHD_networks.networks")
+    g = np.load(os.path.join(golden_dir, "discriminator_small.npz"))
+    torch.manual_seed(7)
+    sd = nw.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[]).state_dict()
+    assert abs(float(sum(v.double().sum() for v in sd.values())) - float(g["weight_sum"])) < 1e-6
+    x, real = torch.from_numpy(g["x"]), torch.from_numpy(g["real"])
+    with torch.no_grad():
+        feats = dorc.discriminator_forward(sd, x, 3, 2)
+    assert np.allclose(feats[0][-1].numpy(), g["final0"], atol=1e-5) and np.allclose(feats[1][-1].numpy(), g["final1"], atol=1e-5)
+    sums = np.array([float(t.double().sum()) for s_ in feats for t in s_])
+    assert np.allclose(sums, g["feat_sums"], rtol=1e-5, atol=1e-2)
+    fake = x[:, 36:].clone().requires_grad_(True)
+    l_gan, l_fm, l_real, l_fake = dorc.discriminator_losses(sd, x[:, :36], fake, real, 3, 2)
+    assert np.allclose([float(l_gan), float(l_fm), float(l_real), float(l_fake)], g["losses"], rtol=1e-5)
+    (l_gan + 10.0 * l_fm).backward()
+    assert np.allclose([float(fake.grad.double().sum()), float(fake.grad.double().abs().sum())], g["g_fake_sum"], rtol=1e-4, atol=1e-6)
