@@ -350,6 +350,11 @@ def test_discriminator_losses_and_gradients_vs_oracle(cuda, B, H, W, monkeypatch
         assert c >= 0.99 and 0.95 <= ratio <= 1.05, "fused=%s d(loss_G)/d(fake): cosine %.5f norm ratio %.4f" % (fused, c, ratio)
         for name, gr in pgrads.items():
             ref = sdg[name].grad
+            if gr.numel() == 1:
+                # the output conv's bias: ONE number = mean of (prediction - target) over the map, a cancelling sum
+                # that moves with the bf16 rounding of the predictions; absolute gate on the prediction scale
+                assert abs(float(gr) - float(ref)) <= 0.02, (fused, name, float(gr), float(ref))
+                continue
             if name.endswith(".bias") and any(name.startswith("scale%d_layer%d." % (s_, j)) for s_ in range(2) for j in (1, 2, 3)):
                 assert float(gr.abs().max()) == 0.0  # bias in front of InstanceNorm: exactly zero
                 continue
