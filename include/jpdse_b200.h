@@ -219,10 +219,12 @@ int jpdse_d_input_backward(const void* g0, const void* g1, float* out, int batch
 int jpdse_instnorm_apply_act(const void* raw, const double* stats, void* out, int batch, int height, int width,
                              int channels, int out_pad, float slope, float eps, void* stream);
 /* Backward through y = LeakyReLU_slope(conv + bias) (no norm): d_pre = (g + skip) * (f > 0 ? 1 : slope).
- *   g, skip (optional): dense bf16 (B,H,W,C); f: the stored activation (B,H+2*f_pad,W+2*f_pad,C);
+ *   g: bf16 (B,H+2*g_pad,W+2*g_pad,C), border skipped (the data gradient of a zero-padded conv also holds the gradient
+ *   w.r.t. the padding); skip (optional): dense bf16 (B,H,W,C); f: the stored activation (B,H+2*f_pad,W+2*f_pad,C);
  *   d_pre: bf16 (B,H+2*out_pad,W+2*out_pad,C), zero border written; dbias (optional): float32 (C) += sum of d_pre. */
-int jpdse_act_backward(const void* g, const void* skip, const void* f, void* d_pre, float* dbias, int batch,
-                       int height, int width, int channels, int f_pad, int out_pad, float slope, void* stream);
+int jpdse_act_backward(const void* g, int g_pad, const void* skip, const void* f, void* d_pre, float* dbias,
+                       int batch, int height, int width, int channels, int f_pad, int out_pad, float slope,
+                       void* stream);
 /* nn.L1Loss numerator between two bf16 tensors of one stored shape: *sum += sum |a - b| over n_elements (borders and pad
  * channels are zero in both). Backward: out dense bf16 (B,H,W,C) = sign(a - b) * (*scale_dev) * scale_host, a / b stored
  * with a border of `pad` (scale_dev: optional device scalar, e.g. the upstream gradient). */
@@ -230,11 +232,12 @@ int jpdse_l1_pair(const void* a, const void* b, size_t n_elements, double* sum, 
 int jpdse_l1_pair_backward(const void* a, const void* b, void* out, const float* scale_dev, float scale_host,
                            int batch, int height, int width, int channels, int pad, void* stream);
 /* nn.MaxPool2d(2, 2) (torchvision VGG19): x (B,H+2*in_pad,W+2*in_pad,C) -> y (B,H/2+2*out_pad,W/2+2*out_pad,C), zero border
- * written. Backward: dx dense (B,H,W,C) = g (dense (B,H/2,W/2,C)) at the first maximum of each window, else 0. */
+ * written. Backward: dx dense (B,H,W,C) = g ((B,H/2+2*g_pad,W/2+2*g_pad,C), border skipped) at the first maximum of
+ * each window, else 0. */
 int jpdse_maxpool2x2(const void* x, void* y, int batch, int height, int width, int channels, int in_pad,
                      int out_pad, void* stream);
-int jpdse_maxpool2x2_backward(const void* x, const void* g, void* dx, int batch, int height, int width,
-                              int channels, int in_pad, void* stream);
+int jpdse_maxpool2x2_backward(const void* x, const void* g, int g_pad, void* dx, int batch, int height,
+                              int width, int channels, int in_pad, void* stream);
 /* Stored bf16 (B,H+2*pad,W+2*pad,c_stored) -> float32 NCHW (B,channels,H,W) (feature maps handed back to PyTorch). */
 int jpdse_nhwc_pad_to_nchw_f32(const void* x, float* y, int batch, int channels, int height, int width, int pad,
                                int c_stored, void* stream);

@@ -827,9 +827,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
       const int k = static_cast<int>(i % q.ktot);
       if (q.kind == JPDSE_CONV3X3_FULL) {
         // W'[n = ci_fwd][t' = kh'*3+kw'][c = co_fwd] = W_fwd[co_fwd][ci_fwd][2-kh'][2-kw']
+        // (the forward weight is (cin_real, cout_real, 3, 3): cout_real < cout for the VGG's 3-channel input conv)
         const int t = k / q.cin, c = k % q.cin;
         const int kh = 2 - t / 3, kw = 2 - t % 3;
-        if (n < q.cout && c < q.cin_real) val = w[((static_cast<size_t>(c) * q.cout + n) * 3 + kh) * 3 + kw];
+        if (n < q.cout_real && c < q.cin_real) val = w[((static_cast<size_t>(c) * q.cout_real + n) * 3 + kh) * 3 + kw];
       } else if (q.kind == JPDSE_CONV7X7_FULL) {
         // per filter row kh': window element e = kw'*cin + c ; W'[n][kh'][e] = W_fwd[c][n][6-kh'][6-kw']
         const int khp = k / 64, e = k % 64;
@@ -973,7 +974,8 @@ extern "C" int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w,
   {
     const char* e = getenv("JPDSE_GENERIC_PACK");  // tests: force the generic gather kernel
     const bool fast = !(e && e[0] == '1') && g.path != kPathRowHead && g.path != kPathRowStem && d->cin_real == d->cin &&
-                      g.rows == d->cout && d->cin % 64 == 0 && d->cout % 16 == 0;
+                      g.rows == d->cout && d->cin % 64 == 0 && d->cout % 16 == 0 &&
+                      (d->cout_real == 0 || d->cout_real == d->cout);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (fast && (d->kind == JPDSE_CONV3X3_PAD1 || d->kind == JPDSE_CONV3X3_S2)) {
       if (d->cin % 256 == 0)

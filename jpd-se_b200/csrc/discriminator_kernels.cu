@@ -202,12 +202,13 @@ instnorm_apply_act_kernel(const __nv_bfloat16* __restrict__ raw, const double* _
 }
 
 // d_pre (zero-bordered by out_pad) = (g + skip) * act'(f), act' = 1 where the stored activation f > 0, else slope.
-// f is (B, H + 2 f_pad, W + 2 f_pad, C); g and skip are dense (B,H,W,C). dbias[c] += sum of d_pre (optional).
+// f is (B, H + 2 f_pad, W + 2 f_pad, C); g is (B, H + 2 g_pad, W + 2 g_pad, C) (its border -- the gradient w.r.t. a zero
+// padding -- is skipped), skip is dense (B,H,W,C). dbias[c] += sum of d_pre (optional).
 template <bool kSkip, bool kBias>
 __global__ void __launch_bounds__(kDThreads)
 act_backward_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ skip, const __nv_bfloat16* __restrict__ f,
                     __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int H, int W, int C, int f_pad, int out_pad,
-                    float slope, int iters) {
+                    float slope, int iters, int g_pad) {
   __shared__ float s_red[kBias ? kDThreads : 1][9];
   const int vpp = C >> 3;
   const int ppi = kDThreads / vpp;
@@ -217,7 +218,8 @@ act_backward_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
   const int Ho = H + 2 * out_pad, Wo = W + 2 * out_pad;
   const int Wf = W + 2 * f_pad;
   const int npix = Ho * Wo;
-  const uint4* g4 = reinterpret_cast<const uint4*>(g) + static_cast<size_t>(b) * H * W * vpp;
+  const int Wg = W + 2 * g_pad;
+  const uint4* g4 = reinterpret_cast<const uint4*>(g) + static_cast<size_t>(b) * (H + 2 * g_pad) * Wg * vpp;
   const uint4* s4 = reinterpret_cast<const uint4*>(skip) + static_cast<size_t>(b) * H * W * vpp;
   const uint4* f4 = reinterpret_cast<const uint4*>(f) + static_cast<size_t>(b) * (H + 2 * f_pad) * Wf * vpp;
   uint4* o4 = reinterpret_cast<uint4*>(dpre) + static_cast<size_t>(b) * npix * vpp;
@@ -234,7 +236,7 @@ act_backward_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __
       if (h >= 0 && h < H && w >= 0 && w < W) {
         const size_t src = (static_cast<size_t>(h) * W + w) * vpp + vec;
         float d[8], a[8];
-        d_unpack8(__ldg(g4 + src), d);
+        d_unpack8(__ldg(g4 + (static_cast<size_t>(h + g_pad) * Wg + w + g_pad) * vpp + vec), d);
         if (kSkip) {
           float e[8];
           d_unpack8(__ldg(s4 + src), e);
@@ -376,11 +378,11 @@ maxpool2x2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict
     }
 }
 
-// dx (dense B,H,W,C) = the pooled gradient g (dense B,H/2,W/2,C) routed to the FIRST position of each 2x2 window that
+// dx (dense B,H,W,C) = the pooled gradient g ((B, H/2 + 2 g_pad, W/2 + 2 g_pad, C), border skipped) routed to the FIRST position of each 2x2 window that
 // holds the maximum (row-major scan order, like ATen's max_pool2d backward); other positions get zero.
 __global__ void __launch_bounds__(kDThreads)
 maxpool2x2_backward_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ g, __nv_bfloat16* __restrict__ dx,
-                           int H, int W, int C, int in_pad, int iters) {
+                           int H, int W, int C, int in_pad, int iters, int g_pad) {
   const int vpp = C >> 3;
   const int ppi = kDThreads / vpp;
   const int vec = threadIdx.x % vpp;
@@ -390,7 +392,8 @@ maxpool2x2_backward_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloa
   const int Wi = W + 2 * in_pad;
   const int npix = Ho * Wo;
   const uint4* x4 = reinterpret_cast<const uint4*>(x) + static_cast<size_t>(b) * (H + 2 * in_pad) * Wi * vpp;
-  const uint4* g4 = reinterpret_cast<const uint4*>(g) + static_cast<size_t>(b) * npix * vpp;
+  const int Wg = Wo + 2 * g_pad;
+  const uint4* g4 = reinterpret_cast<const uint4*>(g) + static_cast<size_t>(b) * (Ho + 2 * g_pad) * Wg * vpp;
   uint4* d4 = reinterpret_cast<uint4*>(dx) + static_cast<size_t>(b) * H * W * vpp;
   for (int pix0 = blockIdx.x * (ppi * iters); pix0 < npix; pix0 += gridDim.x * (ppi * iters))
     for (int it = 0; it < iters; ++it) {
@@ -403,7 +406,7 @@ maxpool2x2_backward_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloa
       d_unpack8(__ldg(x4 + base + vpp), v[1]);
       d_unpack8(__ldg(x4 + base + static_cast<size_t>(Wi) * vpp), v[2]);
       d_unpack8(__ldg(x4 + base + static_cast<size_t>(Wi + 1) * vpp), v[3]);
-      d_unpack8(__ldg(g4 + static_cast<size_t>(pp) * vpp + vec), gg);
+      d_unpack8(__ldg(g4 + (static_cast<size_t>(oh + g_pad) * Wg + ow_ + g_pad) * vpp + vec), gg);
       float o[4][8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -503,10 +506,11 @@ extern "C" int jpdse_instnorm_apply_act(const void* raw, const double* stats, vo
   return check_launch("instnorm_apply_act_kernel");
 }
 
-extern "C" int jpdse_act_backward(const void* g, const void* skip, const void* f, void* d_pre, float* dbias, int batch, int height,
-                                  int width, int channels, int f_pad, int out_pad, float slope, void* stream_v) {
+extern "C" int jpdse_act_backward(const void* g, int g_pad, const void* skip, const void* f, void* d_pre, float* dbias, int batch,
+                                  int height, int width, int channels, int f_pad, int out_pad, float slope, void* stream_v) {
   if (g == nullptr || f == nullptr || d_pre == nullptr) return fail(JPDSE_ERR_INVALID, "act_backward: NULL pointer");
-  if (batch <= 0 || height <= 0 || width <= 0 || f_pad < 0 || out_pad < 0) return fail(JPDSE_ERR_INVALID, "act_backward: bad sizes");
+  if (batch <= 0 || height <= 0 || width <= 0 || f_pad < 0 || out_pad < 0 || g_pad < 0)
+    return fail(JPDSE_ERR_INVALID, "act_backward: bad sizes");
   int rc = check_vec_channels(channels, "act_backward");
   if (rc != JPDSE_OK) return rc;
   if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(f) |
@@ -521,13 +525,13 @@ extern "C" int jpdse_act_backward(const void* g, const void* skip, const void* f
   const __nv_bfloat16* fp = static_cast<const __nv_bfloat16*>(f);
   __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(d_pre);
   if (skip && dbias)
-    act_backward_kernel<true, true><<<grid, kDThreads, 0, stream>>>(gp, sp, fp, dp, dbias, height, width, channels, f_pad, out_pad, slope, iters);
+    act_backward_kernel<true, true><<<grid, kDThreads, 0, stream>>>(gp, sp, fp, dp, dbias, height, width, channels, f_pad, out_pad, slope, iters, g_pad);
   else if (skip)
-    act_backward_kernel<true, false><<<grid, kDThreads, 0, stream>>>(gp, sp, fp, dp, dbias, height, width, channels, f_pad, out_pad, slope, iters);
+    act_backward_kernel<true, false><<<grid, kDThreads, 0, stream>>>(gp, sp, fp, dp, dbias, height, width, channels, f_pad, out_pad, slope, iters, g_pad);
   else if (dbias)
-    act_backward_kernel<false, true><<<grid, kDThreads, 0, stream>>>(gp, sp, fp, dp, dbias, height, width, channels, f_pad, out_pad, slope, iters);
+    act_backward_kernel<false, true><<<grid, kDThreads, 0, stream>>>(gp, sp, fp, dp, dbias, height, width, channels, f_pad, out_pad, slope, iters, g_pad);
   else
-    act_backward_kernel<false, false><<<grid, kDThreads, 0, stream>>>(gp, sp, fp, dp, dbias, height, width, channels, f_pad, out_pad, slope, iters);
+    act_backward_kernel<false, false><<<grid, kDThreads, 0, stream>>>(gp, sp, fp, dp, dbias, height, width, channels, f_pad, out_pad, slope, iters, g_pad);
   return check_launch("act_backward_kernel");
 }
 
@@ -576,8 +580,8 @@ extern "C" int jpdse_maxpool2x2(const void* x, void* y, int batch, int height, i
   return check_launch("maxpool2x2_kernel");
 }
 
-extern "C" int jpdse_maxpool2x2_backward(const void* x, const void* g, void* dx, int batch, int height, int width, int channels,
-                                         int in_pad, void* stream) {
+extern "C" int jpdse_maxpool2x2_backward(const void* x, const void* g, int g_pad, void* dx, int batch, int height, int width,
+                                         int channels, int in_pad, void* stream) {
   if (x == nullptr || g == nullptr || dx == nullptr) return fail(JPDSE_ERR_INVALID, "maxpool2x2_backward: NULL pointer");
   if (batch <= 0 || height <= 0 || width <= 0 || (height & 1) || (width & 1) || in_pad < 0)
     return fail(JPDSE_ERR_INVALID, "maxpool2x2_backward: bad sizes");
@@ -588,7 +592,7 @@ extern "C" int jpdse_maxpool2x2_backward(const void* x, const void* g, void* dx,
   dim3 grid = sweep_grid(static_cast<long long>(height / 2) * (width / 2), ppi, batch, &iters);
   maxpool2x2_backward_kernel<<<grid, kDThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(g), static_cast<__nv_bfloat16*>(dx), height, width,
-      channels, in_pad, iters);
+      channels, in_pad, iters, g_pad);
   return check_launch("maxpool2x2_backward_kernel");
 }
 

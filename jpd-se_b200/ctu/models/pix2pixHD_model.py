@@ -98,9 +98,9 @@ class Pix2PixHDModel(nn.Module):
                                           '(shipped scripts use %r)' % (flag, getattr(opt, flag), want))
         if self.is_train and _opt(opt, 'niter_fix_global', 0) > 0:
             raise NotImplementedError('jpdse_b200 Pix2PixHDModel: --niter_fix_global is outside the accelerated path')
-        # --fp16 in the reference = apex AMP O1 around the whole step (pix2pixHD_trainer.py:65-67,75-76). Here the
-        # generator already computes in bf16 operands / fp32 accumulate; the flag puts the PyTorch-side networks (netD,
-        # VGG) under torch.autocast(bfloat16) -- no loss scaling needed for bf16. Off by default like the reference.
+        # --fp16 in the reference = apex AMP O1 around the whole step (pix2pixHD_trainer.py:65-67,75-76). Here every
+        # network of the step (generator, netD, VGG19) already computes with bf16 operands / fp32 accumulation on the
+        # sm_100a kernels, with fp32 master weights and no loss scaling needed: the flag is accepted and changes nothing.
         self.amp = bool(self.is_train and _opt(opt, 'fp16', False))
         self.num_labels = opt.num_labels + 1 if _opt(opt, 'contain_dontcare_label', False) else opt.num_labels
         netG_input_nc = self.num_labels
@@ -137,12 +137,7 @@ class Pix2PixHDModel(nn.Module):
             self.criterionGAN = networks.GANLoss(use_lsgan=not _opt(opt, 'no_lsgan', False))
             self.criterionFeat = torch.nn.L1Loss()
             self.criterionVGG = networks.VGGLoss(self.gpu_ids)
-            # netD runs on the sm_100a kernels (jpdse_b200.discriminator). The PyTorch-side VGG runs channels_last with
-            # cuDNN autotuning: same arithmetic and parameter shapes, a layout choice only (JPDSE_NO_CHANNELS_LAST=1 disables).
-            self.channels_last = len(self.gpu_ids) > 0 and os.environ.get('JPDSE_NO_CHANNELS_LAST', '0') != '1'
-            if self.channels_last:
-                torch.backends.cudnn.benchmark = True
-                self.criterionVGG.vgg.to(memory_format=torch.channels_last)
+            # netD and VGG19 run on the sm_100a kernels (jpdse_b200.discriminator / jpdse_b200.vgg)
         else:
             self.loss_names = ('G_Distortion')  # sic: a plain string in the reference (:215)
         fn = _opt(opt, 'distortion_loss_fn', 'l1')
@@ -343,9 +338,6 @@ class Pix2PixHDModel(nn.Module):
         image = x_dict['image'].cuda(non_blocking=True).float().contiguous()
         return label, inst, image
 
-    def _cl(self, t):
-        return t.contiguous(memory_format=torch.channels_last) if getattr(self, 'channels_last', False) else t
-
     def discriminate(self, input_label, test_image, use_pool=False, keep_input=False):
         # cuts the graph of both inputs: this is the discriminator's own loss
         input_concat = torch.cat((input_label.detach(), test_image.detach()), dim=1)
@@ -376,8 +368,7 @@ class Pix2PixHDModel(nn.Module):
             real_image = pre['real_image']
             fake_image, input_label = self._get_img(pre)
         keep_input = bool(_opt(opt, 'match_raw_feat', False))
-        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.amp):
-            return self._losses(input_label, fake_image, real_image, keep_input)
+        return self._losses(input_label, fake_image, real_image, keep_input)
 
     def _losses(self, input_label, fake_image, real_image, keep_input):
         opt = self.opt
@@ -398,7 +389,7 @@ class Pix2PixHDModel(nn.Module):
             for i in range(_opt(opt, 'num_D', 2)):
                 for j in range(len(pred_fake[i]) - 1):
                     loss_G_GAN_Feat = loss_G_GAN_Feat + D_weights * self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
-        loss_G_VGG = self.criterionVGG(self._cl(fake_image), self._cl(real_image))
+        loss_G_VGG = self.criterionVGG(fake_image, real_image)
         loss_G_distortion = self.criterionDistortion(fake_image, real_image)
         return loss_G_GAN, loss_G_GAN_Feat, loss_G_VGG, loss_G_distortion, loss_D_real, loss_D_fake
 

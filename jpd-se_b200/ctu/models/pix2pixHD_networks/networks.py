@@ -550,11 +550,26 @@ class Vgg19(nn.Module):
                 param.requires_grad = False
 
     def forward(self, X):
-        out = []
-        for k in range(5):
-            X = getattr(self, 'slice%d' % (k + 1))(X)
-            out.append(X)
-        return out
+        raise JpdseError('Vgg19 is executed inside VGGLoss.forward by the jpdse_b200 kernels (jpdse_b200.vgg.VGGPlan)')
+
+
+class _VGGLossFunction(torch.autograd.Function):
+    """Autograd node of the whole perceptual loss: forward / backward are VGGPlan kernel sequences (frozen weights:
+    the only gradient is the one w.r.t. the first image)."""
+
+    @staticmethod
+    def forward(ctx, plan, x, y):
+        with torch.cuda.device(plan.device):
+            loss = plan.forward(x.detach().contiguous().float(), y.detach().contiguous().float())
+        ctx.plan, ctx.generation = plan, plan.generation
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        if g is None or not ctx.needs_input_grad[1]:
+            return None, None, None
+        with torch.cuda.device(ctx.plan.device):
+            return None, ctx.plan.backward(ctx.generation, g), None
 
 
 class VGGLoss(nn.Module):
@@ -563,10 +578,30 @@ class VGGLoss(nn.Module):
         self.vgg = Vgg19().cuda() if len(gpu_ids) else Vgg19()
         self.criterion = nn.L1Loss()
         self.weights = [1.0 / 32, 1.0 / 16, 1.0 / 8, 1.0 / 4, 1.0]
+        self._plans = {}
+        self._packed_version = {}
+
+    def plan_for(self, batch, height, width, device):
+        from ....vgg import VGGPlan
+        key = (batch, height, width, str(device))
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = VGGPlan(batch, height, width, device)
+            self._plans = {key: plan}
+            self._packed_version = {}
+        ver = tuple((p.data_ptr(), p._version) for p in self.vgg.parameters())
+        if self._packed_version.get(key) != ver:
+            with torch.cuda.device(device):
+                plan.load_weights(self.vgg.state_dict())
+            self._packed_version[key] = ver
+        return plan
 
     def forward(self, x, y):
-        x_vgg, y_vgg = self.vgg(x), self.vgg(y)
-        loss = 0
-        for wgt, fx, fy in zip(self.weights, x_vgg, y_vgg):
-            loss = loss + wgt * self.criterion(fx, fy.detach())
-        return loss
+        # networks.py:134-139: sum_k w_k * L1(vgg(x)_k, vgg(y)_k.detach())
+        if not x.is_cuda:
+            raise JpdseError('jpdse_b200 VGGLoss runs on a B200 only; got a %s tensor (no CPU fallback)' % x.device)
+        if any(p.requires_grad for p in self.vgg.parameters()):
+            raise NotImplementedError('jpdse_b200: VGG19 is frozen in the reference (networks.py:493-495); trainable VGG '
+                                      'weights are outside the accelerated path')
+        B, _, H, W = x.shape
+        return _VGGLossFunction.apply(self.plan_for(B, H, W, x.device), x, y)

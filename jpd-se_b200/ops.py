@@ -302,7 +302,7 @@ def instnorm_apply_act(raw, stats, out, batch, height, width, channels, out_pad,
     return out
 
 
-def act_backward(g, skip, f, d_pre, dbias, batch, height, width, channels, f_pad, out_pad, slope):
+def act_backward(g, skip, f, d_pre, dbias, batch, height, width, channels, f_pad, out_pad, slope, g_pad=0):
     lib = _lib.load()
     _need(g, "g", torch.bfloat16)
     _need(f, "f", torch.bfloat16)
@@ -311,8 +311,8 @@ def act_backward(g, skip, f, d_pre, dbias, batch, height, width, channels, f_pad
         _need(skip, "skip", torch.bfloat16)
     if dbias is not None:
         _need(dbias, "dbias", torch.float32)
-    check(lib.jpdse_act_backward(_ptr(g), _ptr(skip), _ptr(f), _ptr(d_pre), _ptr(dbias), batch, height, width, channels, f_pad,
-                                 out_pad, float(slope), _stream()))
+    check(lib.jpdse_act_backward(_ptr(g), g_pad, _ptr(skip), _ptr(f), _ptr(d_pre), _ptr(dbias), batch, height, width, channels,
+                                 f_pad, out_pad, float(slope), _stream()))
     _count()
     return d_pre
 
@@ -352,12 +352,12 @@ def maxpool2x2(x, y, batch, height, width, channels, in_pad, out_pad):
     return y
 
 
-def maxpool2x2_backward(x, g, dx, batch, height, width, channels, in_pad):
+def maxpool2x2_backward(x, g, dx, batch, height, width, channels, in_pad, g_pad=0):
     lib = _lib.load()
     _need(x, "x", torch.bfloat16)
     _need(g, "g", torch.bfloat16)
     _need(dx, "dx", torch.bfloat16)
-    check(lib.jpdse_maxpool2x2_backward(_ptr(x), _ptr(g), _ptr(dx), batch, height, width, channels, in_pad, _stream()))
+    check(lib.jpdse_maxpool2x2_backward(_ptr(x), _ptr(g), g_pad, _ptr(dx), batch, height, width, channels, in_pad, _stream()))
     _count()
     return dx
 
