@@ -5,7 +5,9 @@ oracle/discriminator_oracle.py::vgg_forward / vgg_loss (pinned bit-identical to 
 random weights by oracle/pin_against_reference.py; the pretrained checkpoint is a download and absent offline).
 
 Tolerances: every cut feature map |err| mean <= 2 % of its RMS (bf16 operands, fp32 accumulate, 13 layers deep); the
-loss within 2 %; d(loss)/d(fake image): cosine >= 0.98 and norm within 5 % of the fp32 oracle's autograd.
+loss within 2 %; d(loss)/d(fake image): norm within 5 % of the fp32 oracle's autograd and cosine >= 0.98, or -- where bf16
+rounding of the forward activations flips ReLU / max-pool choices -- >= what the oracle's own bf16-operand emulation reaches
+against its fp32 self minus 0.02 (the calibration used for the generator, tests/test_gpu_backward.py).
 """
 import importlib
 
@@ -44,6 +46,18 @@ def test_vgg_features_loss_and_gradient_vs_oracle(cuda, B, H, W):
     fo = fake.clone().requires_grad_(True)
     ref_loss = dorc.vgg_loss(sd, fo, real)
     ref_loss.backward()
+
+    class _RoundSTE(torch.autograd.Function):  # bf16 rounding with a straight-through gradient
+        @staticmethod
+        def forward(ctx, t):
+            return t.bfloat16().float()
+
+        @staticmethod
+        def backward(ctx, g_):
+            return g_
+    fe = fake.clone().requires_grad_(True)
+    dorc.vgg_loss(sd, fe, real, round_fn=_RoundSTE.apply).backward()
+    cal = _cos(fe.grad, fo.grad)  # how close ANY bf16-operand path gets to the fp32 gradient (ReLU / max-pool choices flip)
     with torch.no_grad():
         ref_feats = dorc.vgg_forward(sd, torch.cat((fake, real), 0))
     f = fake.clone().to(cuda).requires_grad_(True)
@@ -66,7 +80,9 @@ def test_vgg_features_loss_and_gradient_vs_oracle(cuda, B, H, W):
     c = _cos(got_g, fo.grad)
     ratio = float(got_g.norm() / fo.grad.norm())
     print("VGG loss %.5f (oracle %.5f); gradient cosine %.5f, norm ratio %.4f" % (float(loss), float(ref_loss), c, ratio))
-    assert c >= 0.98 and 0.95 <= ratio <= 1.05
+    c_emu = _cos(got_g, fe.grad)
+    print("bf16-emulation oracle vs fp32 oracle: cosine %.5f; ours vs the emulation: %.5f" % (cal, c_emu))
+    assert c >= min(0.98, cal - 0.02) and c_emu >= min(0.98, cal - 0.01) and 0.95 <= ratio <= 1.05
 
 
 def test_vgg_loss_guards(cuda):
