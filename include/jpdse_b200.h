@@ -92,7 +92,11 @@ enum jpdse_conv_kind {
   /* = h, w; y = gradient w.r.t. the forward INPUT, dense (B,out_h,out_w,Cout = Cin_fwd). The weight handed to       */
   /* jpdse_conv_pack_weights is the FORWARD conv's (Cout_fwd, Cin_fwd_real, 4, 4); cin_real = Cout_fwd real channels. */
   JPDSE_CONV4X4_S2_DGRAD = 9, /* four output-phase GEMMs; out_h/out_w (forward input size: 2h-2 or 2h-1) are required */
-  JPDSE_CONV4X4_S1_FULL = 10  /* out (B, h-1, w-1, Cout)                                                            */
+  JPDSE_CONV4X4_S1_FULL = 10, /* out (B, h-1, w-1, Cout)                                                            */
+  /* 3x3 stride 1 on an input padded by 1 with FEW channels (the VGG19's RGB input conv, networks.py:479): x is       */
+  /* (B,H+2,W+2,Cin) with Cin*2 bytes a multiple of 16 and 3*Cin <= 64; the 3*Cin contiguous elements under a filter  */
+  /* row are one K block (K = 3 x 64 instead of 9 x 64). The buffer must extend 128 B past its last pixel.            */
+  JPDSE_CONV3X3_PAD1_NARROW = 11
 };
 enum jpdse_conv_epilogue {
   JPDSE_EPI_RAW_STATS = 0,      /* y = bf16 NHWC raw conv output, stats += (sum, sumsq) per (b,c)    */
@@ -215,6 +219,14 @@ int jpdse_d_input(const float* a, int ca, const float* b, int cb, void* out, int
                   int c_pad, int pool, int out_pad, void* stream);
 int jpdse_d_input_backward(const void* g0, const void* g1, float* out, int batch, int height, int width,
                            int c_stored, int c0, int c, void* stream);
+/* The same discriminator input(s) straight from the ids: channels [one-hot(label) (num_labels), instance edge, image (3)],
+ * i.e. preprocess (pix2pixHD_model.py:376-396) + cat with the image (:451-460) [+ the AvgPool] without the float32
+ * (B,39,H,W) tensor. label / instance and their dtype codes as in jpdse_build_input; image_a / image_b: float32 (B,3,H,W);
+ * out_a / out_b: bf16 (B,Ho+2*out_pad,Wo+2*out_pad,c_pad). The second image / output pair is optional (both NULL): the fake
+ * and the real pass share the label channels, so both operands are written in one pass. Border not written. */
+int jpdse_d_input_ids(const void* label, int label_dtype, const void* instance, int inst_dtype, const float* image_a,
+                      void* out_a, const float* image_b, void* out_b, int batch, int height, int width,
+                      int num_labels, int c_pad, int pool, int out_pad, void* stream);
 /* InstanceNorm2d apply + LeakyReLU(slope): out (B,H+2*out_pad,W+2*out_pad,C) bf16 with a ZERO border (written). */
 int jpdse_instnorm_apply_act(const void* raw, const double* stats, void* out, int batch, int height, int width,
                              int channels, int out_pad, float slope, float eps, void* stream);

@@ -22,7 +22,7 @@ class ConvDesc(ctypes.Structure):
 
 # enum jpdse_conv_kind / jpdse_conv_epilogue
 (CONV3X3_PAD1, CONV3X3_S2, CONVT3X3_S2, CONV7X7_PAD3, CONV1X1, CONV3X3_FULL, CONV7X7_FULL, CONV4X4_S2, CONV4X4_S1,
- CONV4X4_S2_DGRAD, CONV4X4_S1_FULL) = range(11)
+ CONV4X4_S2_DGRAD, CONV4X4_S1_FULL, CONV3X3_PAD1_NARROW) = range(12)
 EPI_RAW_STATS, EPI_BIAS_TANH_NCHW, EPI_SIGN_NCHW, EPI_RAW, EPI_BIAS_ACT, EPI_BIAS_NCHW = range(6)
 ABI_VERSION = 2
 
@@ -71,6 +71,8 @@ SIGNATURES = {
     "jpdse_instnorm_backward_reduce_act": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                    c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "jpdse_d_input": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "jpdse_d_input_ids": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                  c_int, c_int, c_int, c_int, c_void_p]),
     "jpdse_d_input_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "jpdse_instnorm_apply_act": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float,
                                          c_void_p]),

@@ -156,6 +156,103 @@ build_input_nchw_kernel(const void* __restrict__ label, int label_dtype, const v
   }
 }
 
+// ------------------------------------------------------------------------------------------ discriminator input from ids
+// cat(one-hot(label), edge(instance), image) [+ AvgPool2d(3, 2, 1, count_include_pad=False)] for the PatchGAN, straight
+// from the class / instance ids (pix2pixHD_model.py:376-396 + :451-460 + networks.py:387) -- 20 B read per pixel instead
+// of the 156 B of the reference's float32 (B,39,H,W) tensor. One thread per OUTPUT pixel builds the c_pad channels
+// (8 x 16-byte stores); the one-hot / edge channels are shared by two images (fake and real): both outputs are written in
+// one pass. The pooled one-hot is count / taps and the pooled image sum / taps in the tap order of ATen's kernel.
+__global__ void __launch_bounds__(256)
+d_input_ids_kernel(const void* __restrict__ label, int label_dtype, const void* __restrict__ inst, int inst_dtype,
+                   const float* __restrict__ img_a, __nv_bfloat16* __restrict__ out_a, const float* __restrict__ img_b,
+                   __nv_bfloat16* __restrict__ out_b, int B, int H, int W, int Ho, int Wo, int L, int c_pad, int pool, int out_pad) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t oplane = static_cast<size_t>(Ho) * Wo;
+  const size_t total = static_cast<size_t>(B) * oplane;
+  const int Wst = Wo + 2 * out_pad;
+  const size_t ost = static_cast<size_t>(Ho + 2 * out_pad) * Wst;
+  for (size_t op = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; op < total;
+       op += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(op / oplane);
+    const size_t ohw = op % oplane;
+    const int oy = static_cast<int>(ohw / Wo), ox = static_cast<int>(ohw % Wo);
+    int labs[9];
+    float edge = 0.f, ia[3] = {0.f, 0.f, 0.f}, ib[3] = {0.f, 0.f, 0.f};
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) labs[t] = -2;  // -2: tap not present
+    const size_t ibase = static_cast<size_t>(b) * 3 * plane;
+    if (!pool) {
+      const size_t pix = static_cast<size_t>(b) * plane + static_cast<size_t>(oy) * W + ox;
+      labs[0] = load_label(label, label_dtype, pix, L);
+      edge = load_edge(inst, inst_dtype, static_cast<size_t>(b) * plane, oy, ox, H, W) ? 1.f : 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        ia[c] = __ldg(img_a + ibase + c * plane + static_cast<size_t>(oy) * W + ox);
+        if (img_b != nullptr) ib[c] = __ldg(img_b + ibase + c * plane + static_cast<size_t>(oy) * W + ox);
+      }
+      cnt = 1;
+    } else {
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy) {
+        const int y = 2 * oy + dy;
+        if (y < 0 || y >= H) continue;
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const int x = 2 * ox + dx;
+          if (x < 0 || x >= W) continue;
+          const size_t hw = static_cast<size_t>(y) * W + x;
+          labs[(dy + 1) * 3 + dx + 1] = load_label(label, label_dtype, static_cast<size_t>(b) * plane + hw, L);
+          edge += load_edge(inst, inst_dtype, static_cast<size_t>(b) * plane, y, x, H, W) ? 1.f : 0.f;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            ia[c] += __ldg(img_a + ibase + c * plane + hw);
+            if (img_b != nullptr) ib[c] += __ldg(img_b + ibase + c * plane + hw);
+          }
+          ++cnt;
+        }
+      }
+    }
+    const float fc = static_cast<float>(cnt);
+    edge = edge / fc;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ia[c] = ia[c] / fc;
+      ib[c] = ib[c] / fc;
+    }
+    const size_t o = (static_cast<size_t>(b) * ost + static_cast<size_t>(oy + out_pad) * Wst + ox + out_pad) * c_pad;
+    uint4* oa = reinterpret_cast<uint4*>(out_a + o);
+    uint4* ob = out_b != nullptr ? reinterpret_cast<uint4*>(out_b + o) : nullptr;
+    for (int k = 0; k < c_pad / 8; ++k) {
+      float va[8], vb[8];
+      bool differs = false;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = 8 * k + j;
+        float v = 0.f, w2 = 0.f;
+        if (c < L) {
+          int n = 0;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) n += (labs[t] == c) ? 1 : 0;
+          v = w2 = static_cast<float>(n) / fc;
+        } else if (c == L) {
+          v = w2 = edge;
+        } else if (c < L + 4) {
+          v = ia[c - L - 1];
+          w2 = ib[c - L - 1];
+          differs = true;
+        }
+        va[j] = v;
+        vb[j] = w2;
+      }
+      oa[k] = make_uint4(pack_bf16x2(va[0], va[1]), pack_bf16x2(va[2], va[3]), pack_bf16x2(va[4], va[5]), pack_bf16x2(va[6], va[7]));
+      if (ob != nullptr)
+        ob[k] = differs ? make_uint4(pack_bf16x2(vb[0], vb[1]), pack_bf16x2(vb[2], vb[3]), pack_bf16x2(vb[4], vb[5]), pack_bf16x2(vb[6], vb[7]))
+                        : oa[k];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ InstanceNorm apply
 constexpr int kNormThreads = 256;
 constexpr int kNormIters = 16;
@@ -681,4 +778,25 @@ extern "C" int jpdse_distortion_u8(const float* a, const float* b, unsigned long
   distortion_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, sum, batch, channels, height, width, mode, m[0],
                                                                              m[1], m[2], s[0], s[1], s[2]);
   return check_launch("distortion_u8_kernel");
+}
+
+extern "C" int jpdse_d_input_ids(const void* label, int label_dtype, const void* instance, int inst_dtype, const float* image_a,
+                                 void* out_a, const float* image_b, void* out_b, int batch, int height, int width, int num_labels,
+                                 int c_pad, int pool, int out_pad, void* stream) {
+  if (label == nullptr || instance == nullptr || image_a == nullptr || out_a == nullptr || ((image_b == nullptr) != (out_b == nullptr)))
+    return fail(JPDSE_ERR_INVALID, "d_input_ids: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0 || num_labels <= 0 || num_labels + 4 > c_pad || c_pad % 8 || out_pad < 0)
+    return fail(JPDSE_ERR_INVALID, "d_input_ids: bad sizes");
+  if (label_dtype < 0 || label_dtype > 2 || inst_dtype < 0 || inst_dtype > 3) return fail(JPDSE_ERR_INVALID, "d_input_ids: bad dtype code");
+  if ((reinterpret_cast<uintptr_t>(out_a) | reinterpret_cast<uintptr_t>(out_b)) & 15)
+    return fail(JPDSE_ERR_INVALID, "d_input_ids: outputs must be 16-byte aligned");
+  const int Ho = pool ? (height - 1) / 2 + 1 : height, Wo = pool ? (width - 1) / 2 + 1 : width;
+  const size_t total = static_cast<size_t>(batch) * Ho * Wo;
+  size_t blocks = (total + 255) / 256;
+  const size_t cap = static_cast<size_t>(num_sms()) * 32;
+  if (blocks > cap) blocks = cap;
+  d_input_ids_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      label, label_dtype, instance, inst_dtype, image_a, static_cast<__nv_bfloat16*>(out_a), image_b,
+      static_cast<__nv_bfloat16*>(out_b), batch, height, width, Ho, Wo, num_labels, c_pad, pool ? 1 : 0, out_pad);
+  return check_launch("d_input_ids_kernel");
 }

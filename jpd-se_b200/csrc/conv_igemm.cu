@@ -683,6 +683,15 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
       g->cpt = d->cin / 64;
       g->ktot = 16 * d->cin;
       break;
+    case JPDSE_CONV3X3_PAD1_NARROW:
+      if ((d->cin * 2) % 16 || 3 * d->cin > 64)
+        return fail(JPDSE_ERR_UNSUPPORTED, "conv3x3 narrow: need cin*2 %% 16 == 0 and 3*cin <= 64 (got %d)", d->cin);
+      if (d->in_pad != 1) return fail(JPDSE_ERR_INVALID, "CONV3X3_PAD1_NARROW needs in_pad == 1");
+      g->out_h = g->gemm_h = d->in_h;
+      g->out_w = g->gemm_w = d->in_w;
+      g->cpt = 1;
+      g->ktot = 3 * 64;
+      break;
     case JPDSE_CONV7X7_PAD3:
       if ((d->cin * 2) % 16) return fail(JPDSE_ERR_UNSUPPORTED, "conv7x7: cin*2 bytes must be a multiple of 16");
       g->out_h = g->gemm_h = d->in_h;
@@ -837,12 +846,13 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
         const int kwp = e / q.cin, c = e % q.cin;
         if (n < q.cout && kwp < 7 && c < q.cin_real)
           val = w[((static_cast<size_t>(c) * q.cout + n) * 7 + (6 - khp)) * 7 + (6 - kwp)];
-      } else if (q.kind == JPDSE_CONV7X7_PAD3) {
+      } else if (q.kind == JPDSE_CONV7X7_PAD3 || q.kind == JPDSE_CONV3X3_PAD1_NARROW) {
+        const int ks = q.kind == JPDSE_CONV7X7_PAD3 ? 7 : 3;
         const int kh = k / (q.cpt * 64);
         const int e = k % (q.cpt * 64);
         const int kw = e / q.cin, c = e % q.cin;
-        if (n < q.cout && kw < 7 && c < q.cin_real)
-          val = w[((static_cast<size_t>(n) * q.cin_real + c) * 7 + kh) * 7 + kw];
+        if (n < q.cout && kw < ks && c < q.cin_real)
+          val = w[((static_cast<size_t>(n) * q.cin_real + c) * ks + kh) * ks + kw];
       } else if (q.kind == JPDSE_CONV1X1) {
         if (n < q.cout && k < q.cin_real) val = w[static_cast<size_t>(n) * q.cin_real + k];
       } else if (q.kind == JPDSE_CONV4X4_S2 || q.kind == JPDSE_CONV4X4_S1) {
@@ -1070,6 +1080,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   if (d->kind == JPDSE_CONV4X4_S2) dev_taps = 8;
   if (d->kind == JPDSE_CONV4X4_S1) dev_taps = 16;
   if (d->kind == JPDSE_CONV4X4_S2_DGRAD) dev_taps = 4;
+  if (d->kind == JPDSE_CONV3X3_PAD1_NARROW) dev_taps = 3;
   const int kblocks_per_tile = dev_taps * g.cpt;
   const bool odd_phase_out = d->kind == JPDSE_CONV4X4_S2_DGRAD && ((g.out_h | g.out_w) & 1);  // no {2C, W/2, 2, H/2} view
   const bool staged_out = (g.bn == 64 || g.bn == 128 || (g.bn == 256 && kblocks_per_tile <= staged_limit)) && !flat &&
@@ -1269,6 +1280,17 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
         p.tap_off[t][2] = (kh == 1) ? 0 : 1;
         p.tap_off[t][3] = (kh == 0) ? -1 : 0;
       }
+      break;
+    }
+    case JPDSE_CONV3X3_PAD1_NARROW: {
+      // as the 7x7 case below with three filter rows: window {64 (3*C real), W, H+2, B}, pixel stride C elements
+      xin = static_cast<const uint8_t*>(x);
+      dims[0] = 64; dims[1] = W; dims[2] = Hp; dims[3] = B;
+      strides[0] = C * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
+      box[0] = 64; box[1] = p.tile_w; box[2] = p.tile_h; box[3] = 1;
+      p.a_rank = 4; p.dim_w = 1; p.dim_h = 2; p.dim_b = 3;
+      p.ntaps = 3;
+      for (int t = 0; t < 3; ++t) p.tap_off[t][2] = t;
       break;
     }
     case JPDSE_CONV7X7_PAD3: {

@@ -111,6 +111,31 @@ d_input_kernel(const float* __restrict__ a, int ca, const float* __restrict__ bs
   }
 }
 
+// c_pad == 8 without pooling (the VGG19's RGB operand): one thread per pixel, one 16-byte store
+__global__ void __launch_bounds__(256)
+d_input8_kernel(const float* __restrict__ a, int ca, const float* __restrict__ bsrc, int cb, __nv_bfloat16* __restrict__ out, int B,
+                int H, int W, int out_pad) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * plane;
+  const int Wst = W + 2 * out_pad;
+  const size_t img = static_cast<size_t>(H + 2 * out_pad) * Wst;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(pix / plane);
+    const size_t hw = pix % plane;
+    const int y = static_cast<int>(hw / W), x = static_cast<int>(hw % W);
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      v[c] = 0.f;
+      if (c < ca) v[c] = __ldg(a + (static_cast<size_t>(b) * ca + c) * plane + hw);
+      else if (c < ca + cb) v[c] = __ldg(bsrc + (static_cast<size_t>(b) * cb + (c - ca)) * plane + hw);
+    }
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(b) * img + static_cast<size_t>(y + out_pad) * Wst + x + out_pad) * 8) =
+        make_uint4(d_pack2(v[0], v[1]), d_pack2(v[2], v[3]), d_pack2(v[4], v[5]), d_pack2(v[6], v[7]));
+  }
+}
+
 // out[b, c, y, x] (float32 NCHW) = g0[b, y, x, c0 + c] + sum over the pooled pixels whose 3x3 window holds (y, x) of
 // g1[b, i, j, c0 + c] / (in-bounds taps of that window). One thread per (pixel, channel group of <= 4).
 __global__ void __launch_bounds__(256)
@@ -458,6 +483,28 @@ __global__ void nhwc_pad_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x,
   }
 }
 
+// few channels (the 3-channel image gradient out of a 64-channel data-gradient tensor): one thread per pixel reads the
+// first 16 bytes of the pixel and writes up to 8 planes, coalesced along W
+__global__ void __launch_bounds__(256)
+nhwc_pad_to_nchw_f32_few_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int B, int C, int H, int W, int pad,
+                                int c_stored) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t total = static_cast<size_t>(B) * plane;
+  const int Wp = W + 2 * pad;
+  const size_t img = static_cast<size_t>(H + 2 * pad) * Wp;
+  for (size_t pix = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; pix < total;
+       pix += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(pix / plane);
+    const size_t hw = pix % plane;
+    const int h = static_cast<int>(hw / W), w = static_cast<int>(hw % W);
+    float f[8];
+    d_unpack8(__ldg(reinterpret_cast<const uint4*>(x + (static_cast<size_t>(b) * img + static_cast<size_t>(h + pad) * Wp + w + pad) * c_stored)), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      if (c < C) y[(static_cast<size_t>(b) * C + c) * plane + hw] = f[c];
+  }
+}
+
 }  // namespace jpdse
 
 using namespace jpdse;
@@ -468,6 +515,15 @@ extern "C" int jpdse_d_input(const float* a, int ca, const float* b, int cb, voi
   if (batch <= 0 || height <= 0 || width <= 0 || ca <= 0 || cb < 0 || ca + cb > c_pad || c_pad % 8 || out_pad < 0)
     return fail(JPDSE_ERR_INVALID, "d_input: bad sizes");
   const int Ho = pool ? (height - 1) / 2 + 1 : height, Wo = pool ? (width - 1) / 2 + 1 : width;
+  if (c_pad == 8 && !pool && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    const size_t total = static_cast<size_t>(batch) * height * width;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = static_cast<size_t>(num_sms()) * 32;
+    if (blocks > cap) blocks = cap;
+    d_input8_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        a, ca, b, cb, static_cast<__nv_bfloat16*>(out), batch, height, width, out_pad);
+    return check_launch("d_input8_kernel");
+  }
   dim3 grid((Ho * Wo + 31) / 32, (c_pad + 31) / 32, batch);
   d_input_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(a, ca, b, cb, static_cast<__nv_bfloat16*>(out), height,
                                                                             width, Ho, Wo, c_pad, pool ? 1 : 0, out_pad);
@@ -601,6 +657,15 @@ extern "C" int jpdse_nhwc_pad_to_nchw_f32(const void* x, float* y, int batch, in
   if (x == nullptr || y == nullptr) return fail(JPDSE_ERR_INVALID, "nhwc_pad_to_nchw_f32: NULL pointer");
   if (batch <= 0 || channels <= 0 || height <= 0 || width <= 0 || pad < 0 || channels > c_stored)
     return fail(JPDSE_ERR_INVALID, "nhwc_pad_to_nchw_f32: bad sizes");
+  if (channels <= 8 && c_stored % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const size_t total = static_cast<size_t>(batch) * height * width;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = static_cast<size_t>(num_sms()) * 32;
+    if (blocks > cap) blocks = cap;
+    nhwc_pad_to_nchw_f32_few_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), y, batch, channels, height, width, pad, c_stored);
+    return check_launch("nhwc_pad_to_nchw_f32_few_kernel");
+  }
   dim3 grid((height * width + 31) / 32, (channels + 31) / 32, batch);
   nhwc_pad_to_nchw_f32_kernel<<<grid, dim3(32, 32), 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), y, channels, height, width, pad, c_stored);

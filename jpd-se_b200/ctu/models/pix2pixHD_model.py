@@ -350,15 +350,22 @@ class Pix2PixHDModel(nn.Module):
                              "supply the decoded image tensor")
         plain = not (_opt(opt, 'zero_vis', False) or _opt(opt, 'zero_sem', False) or _opt(opt, 'zero_ins', False)
                      or _opt(opt, 'no_instance', False) or _opt(opt, 'use_compressed', False))
+        keep_input = bool(_opt(opt, 'match_raw_feat', False))
+        ids = None
         if plain:
             label, inst, real_image = self._fast_inputs(x_dict)
-            # one input-build launch gives the reference's input_label (for netD), a second one the stem operand
             # out-of-range ids are counted on the device; Pix2PixHDTrainer.step checks the counter behind its own
             # .item() sync (check_labels), so the training step pays no extra synchronisation
             bad = self._bad_counter(real_image.device)
-            _, nchw = ops.build_input(label, inst, real_image, self.num_labels, nhwc=False, nchw=True, bad_count=bad)
-            input_label = nchw[:, :self.num_labels + 1]
-            fake_image = self.netG.forward_from_maps(label, inst, real_image, self.num_labels)
+            if self._fused_d(keep_input):
+                # the discriminator operands are built straight from the ids too: the reference's float32 (B,36,H,W)
+                # input_label (pix2pixHD_model.py:376-396) is never materialised
+                input_label, ids = None, (label, inst)
+                fake_image = self.netG.forward_from_maps(label, inst, real_image, self.num_labels, bad_count=bad)
+            else:
+                _, nchw = ops.build_input(label, inst, real_image, self.num_labels, nhwc=False, nchw=True, bad_count=bad)
+                input_label = nchw[:, :self.num_labels + 1]
+                fake_image = self.netG.forward_from_maps(label, inst, real_image, self.num_labels)
         else:
             # the reference's own route (pix2pixHD_model.py:711-712): preprocess -> _get_img (zeroing switches,
             # compressed input) -> netG on the (B,39,H,W) tensor; the generator still runs on the sm_100a kernels
@@ -367,15 +374,18 @@ class Pix2PixHDModel(nn.Module):
                 pre['compressed_img'] = x_dict['compressed_img'].cuda(non_blocking=True).float()
             real_image = pre['real_image']
             fake_image, input_label = self._get_img(pre)
-        keep_input = bool(_opt(opt, 'match_raw_feat', False))
-        return self._losses(input_label, fake_image, real_image, keep_input)
+        return self._losses(input_label, fake_image, real_image, keep_input, ids)
 
-    def _losses(self, input_label, fake_image, real_image, keep_input):
+    def _fused_d(self, keep_input):
+        return (not keep_input and not _opt(self.opt, 'no_lsgan', False) and _opt(self.opt, 'num_D', 2) <= 2
+                and os.environ.get('JPDSE_NO_FUSED_D', '0') != '1')
+
+    def _losses(self, input_label, fake_image, real_image, keep_input, ids=None):
         opt = self.opt
-        fused = not keep_input and not _opt(opt, 'no_lsgan', False) and os.environ.get('JPDSE_NO_FUSED_D', '0') != '1' 
-        if fused:
-            # pix2pixHD_model.py:715-753 in one kernel-side pass per image set (see MultiscaleDiscriminator.fused_losses)
-            loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake = self.netD.fused_losses(input_label, fake_image, real_image)
+        if self._fused_d(keep_input):
+            # pix2pixHD_model.py:715-753 in one kernel-side pass over [fake; real] (see MultiscaleDiscriminator.fused_losses)
+            loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake = self.netD.fused_losses(
+                input_label, fake_image, real_image, ids=ids, num_labels=self.num_labels)
         else:
             # the reference's call sequence, one autograd node per netD call
             pred_fake_pool = self.discriminate(input_label, fake_image, use_pool=True)

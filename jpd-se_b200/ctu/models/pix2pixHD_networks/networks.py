@@ -338,49 +338,50 @@ class _DiscriminatorFunction(torch.autograd.Function):
 
 
 class _DiscriminatorLossD(torch.autograd.Function):
-    """The discriminator's own LSGAN loss on two stored passes (fake, real): pix2pixHD_model.py:715-730 with GANLoss
+    """The discriminator's own LSGAN loss on a stored [fake; real] pair pass: pix2pixHD_model.py:715-730 with GANLoss
     (networks.py:80-122). Outputs (loss_D_fake, loss_D_real); backward produces parameter gradients only."""
 
     @staticmethod
-    def forward(ctx, module, plan, fake, real, *params):
-        ctx.module, ctx.plan, ctx.fake, ctx.real = module, plan, fake, real
-        sf, sr = plan.slots[fake[0]], plan.slots[real[0]]
-        loss_fake = sum((m * m).mean() for m in sf.final)
-        loss_real = sum(((m - 1.0) ** 2).mean() for m in sr.final)
+    def forward(ctx, module, plan, gen, *params):
+        ctx.module, ctx.plan, ctx.gen = module, plan, gen
+        h, finals = plan.half, plan.slots[0].final
+        loss_fake = sum((m[:h] * m[:h]).mean() for m in finals)
+        loss_real = sum(((m[h:] - 1.0) ** 2).mean() for m in finals)
         return loss_fake, loss_real
 
     @staticmethod
     def backward(ctx, g_fake, g_real):
         plan, module = ctx.plan, ctx.module
-        sf, sr = plan.slots[ctx.fake[0]], plan.slots[ctx.real[0]]
+        h, finals = plan.half, plan.slots[0].final
         none_feats = [[None] * (plan.n_layers + 1) for _ in range(plan.num_D)]
         pg = {}
         with torch.cuda.device(plan.device):
-            if g_fake is not None:
-                fin = [g_fake * (2.0 / m.numel()) * m for m in sf.final]
-                plan.backward(ctx.fake[0], ctx.fake[1], none_feats, fin, False, True, pg, accumulate=False)
-            if g_real is not None:
-                fin = [g_real * (2.0 / m.numel()) * (m - 1.0) for m in sr.final]
-                plan.backward(ctx.real[0], ctx.real[1], none_feats, fin, False, True, pg, accumulate=bool(pg))
+            fin = []
+            for m in finals:
+                n = float(m[:h].numel())
+                gf = torch.zeros_like(m[:h]) if g_fake is None else g_fake * (2.0 / n) * m[:h]
+                gr = torch.zeros_like(m[h:]) if g_real is None else g_real * (2.0 / n) * (m[h:] - 1.0)
+                fin.append(torch.cat((gf, gr), 0))
+            plan.backward(0, ctx.gen, none_feats, fin, False, True, pg)
         out = []
         for name, p in module.named_parameters():
             g = pg.get(name)
             out.append(g if g is not None else (torch.zeros_like(p) if p.requires_grad else None))
-        return (None, None, None, None) + tuple(out)
+        return (None, None, None) + tuple(out)
 
 
 class _DiscriminatorLossG(torch.autograd.Function):
-    """The generator's adversarial + feature-matching losses (pix2pixHD_model.py:733-753) on the stored fake / real
-    passes. Outputs (loss_G_GAN, loss_G_GAN_Feat); backward produces the gradient w.r.t. the fake image only -- the netD
+    """The generator's adversarial + feature-matching losses (pix2pixHD_model.py:733-753) on the stored pair pass.
+    Outputs (loss_G_GAN, loss_G_GAN_Feat); backward produces the gradient w.r.t. the fake image only -- the netD
     parameter gradients the reference deposits here are discarded by optimizer_D.zero_grad()
     (ctu/trainers/pix2pixHD_trainer.py:73) and are not computed."""
 
     @staticmethod
-    def forward(ctx, plan, fake, real, fake_image):
+    def forward(ctx, plan, gen, fake_image):
         from .... import ops
-        ctx.plan, ctx.fake, ctx.real = plan, fake, real
-        sf, sr = plan.slots[fake[0]], plan.slots[real[0]]
-        loss_gan = sum(((m - 1.0) ** 2).mean() for m in sf.final)
+        ctx.plan, ctx.gen = plan, gen
+        s, h = plan.slots[0], plan.half
+        loss_gan = sum(((m[:h] - 1.0) ** 2).mean() for m in s.final)
         n_feat = plan.n_layers + 1
         acc = torch.zeros(plan.num_D * n_feat, dtype=torch.float64, device=plan.device)
         numel = []
@@ -388,8 +389,8 @@ class _DiscriminatorLossG(torch.autograd.Function):
             for i in range(plan.num_D):
                 for j in range(n_feat):
                     L = plan.scales[i][j]
-                    ops.l1_pair(sf.feat[i][j], sr.feat[i][j], acc[i * n_feat + j: i * n_feat + j + 1])
-                    numel.append(float(plan.B * L.cout * L.out_h * L.out_w))
+                    ops.l1_pair(s.feat[i][j][:h], s.feat[i][j][h:], acc[i * n_feat + j: i * n_feat + j + 1])
+                    numel.append(float(h * L.cout * L.out_h * L.out_w))
         w = torch.tensor([1.0 / (plan.num_D * n_) for n_ in numel], dtype=torch.float64, device=plan.device)
         ctx.numel = numel
         return loss_gan, (acc * w).sum().float()
@@ -398,25 +399,25 @@ class _DiscriminatorLossG(torch.autograd.Function):
     def backward(ctx, g_gan, g_fm):
         from .... import ops
         plan = ctx.plan
-        sf, sr = plan.slots[ctx.fake[0]], plan.slots[ctx.real[0]]
+        s, h = plan.slots[0], plan.half
         n_feat = plan.n_layers + 1
         with torch.cuda.device(plan.device):
             fin = [None] * plan.num_D
             if g_gan is not None:
-                fin = [g_gan * (2.0 / m.numel()) * (m - 1.0) for m in sf.final]
+                fin = [g_gan * (2.0 / m[:h].numel()) * (m[:h] - 1.0) for m in s.final]
             feats = [[None] * n_feat for _ in range(plan.num_D)]
             if g_fm is not None:
                 scale = g_fm.detach().reshape(1).float().contiguous()
                 for i in range(plan.num_D):
                     for j in range(n_feat):
                         L = plan.scales[i][j]
-                        out = plan._buf("fm%d_%d" % (i, j), (plan.B, L.out_h, L.out_w, L.cout))
-                        ops.l1_pair_backward(sf.feat[i][j], sr.feat[i][j], out, scale, 1.0 / (plan.num_D * ctx.numel[i * n_feat + j]),
-                                             plan.B, L.out_h, L.out_w, L.cout, 2)
+                        out = plan._buf("fm%d_%d" % (i, j), (h, L.out_h, L.out_w, L.cout))
+                        ops.l1_pair_backward(s.feat[i][j][:h], s.feat[i][j][h:], out, scale,
+                                             1.0 / (plan.num_D * ctx.numel[i * n_feat + j]), h, L.out_h, L.out_w, L.cout, 2)
                         feats[i][j] = out
             ic = plan.image_channels  # the image is the last `ic` channels of cat(input_label, image)
-            gin = plan.backward(ctx.fake[0], ctx.fake[1], feats, fin, True, False, input_channels=(plan.input_nc - ic, ic))
-        return None, None, None, gin
+            gin = plan.backward(0, ctx.gen, feats, fin, True, False, input_channels=(plan.input_nc - ic, ic), first_half=True)
+        return None, None, gin
 
 
 class MultiscaleDiscriminator(nn.Module):
@@ -440,20 +441,24 @@ class MultiscaleDiscriminator(nn.Module):
         self._packed_version = {}
 
     # ------------------------------------------------------------------ engine plumbing
-    def plan_for(self, batch, height, width, device):
+    def plan_for(self, batch, height, width, device, pair=False):
+        """batch: images per call (pair=False, the reference's netD(x) API) or 2 x B for a [fake; real] pair plan."""
         from ....discriminator import DiscriminatorPlan
         if not self.getIntermFeat:
             raise NotImplementedError('jpdse_b200: MultiscaleDiscriminator(getIntermFeat=False) is outside the accelerated path '
                                       '(Pix2PixHDModel always builds it with getIntermFeat=True, pix2pixHD_model.py:158-162)')
         if self.use_sigmoid:
             raise NotImplementedError('jpdse_b200: the sigmoid (non-LSGAN) discriminator is outside the accelerated path')
-        key = (batch, height, width, str(device))
+        key = (batch, height, width, str(device), bool(pair))
         plan = self._plans.get(key)
         if plan is None:
-            plan = DiscriminatorPlan(self.input_nc, self.ndf, self.n_layers, self.num_D, batch, height, width, device)
+            plan = DiscriminatorPlan(self.input_nc, self.ndf, self.n_layers, self.num_D, batch, height, width, device,
+                                     n_slots=1 if pair else 3, pair=pair)
             plan.image_channels = 3
-            self._plans = {key: plan}
-            self._packed_version = {}
+            # one live plan per flavour (activations are hundreds of MB)
+            self._plans = {k: v for k, v in self._plans.items() if k[4] != bool(pair)}
+            self._plans[key] = plan
+            self._packed_version.pop(key, None)
         ver = tuple((p.data_ptr(), p._version) for p in self.parameters())
         if self._packed_version.get(key) != ver:
             with torch.cuda.device(device):
@@ -473,24 +478,27 @@ class MultiscaleDiscriminator(nn.Module):
         n = self.n_layers + 2
         return [list(outs[i * n:(i + 1) * n]) for i in range(self.num_D)]
 
-    def fused_losses(self, input_label, fake_image, real_image):
+    def fused_losses(self, input_label, fake_image, real_image, ids=None, num_labels=None):
         """The discriminator half of get_train_loss (pix2pixHD_model.py:715-753) for the LSGAN configuration, without the
         reference's redundancy: D(label, fake.detach()) and D(label, fake) are ONE forward (identical values; only the
-        autograd graph differs), the feature maps never leave NHWC bf16 (the L1 of the feature-matching loss is a
-        kernel over them), and the generator's backward through D skips the parameter gradients the reference throws
-        away. Returns (loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake) with the reference's values / gradients."""
-        B, _, H, W = fake_image.shape
+        autograd graph differs) and run together with D(label, real) as one batch of 2B images; the feature maps never
+        leave NHWC bf16 (the L1 of the feature-matching loss is a kernel over the two halves); the generator's backward
+        through D walks the fake half only and skips the parameter gradients the reference throws away.
+        ids = (label ids (B,1,H,W), instance ids (B,1,H,W)): build the operands straight from the ids instead of from the
+        float32 `input_label` (which may then be None). Returns (loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake)
+        with the reference's values / gradients."""
+        B, ic, H, W = fake_image.shape
         dev = fake_image.device
-        plan = self.plan_for(B, H, W, dev)
-        plan.image_channels = fake_image.shape[1]
-        label = input_label.detach().contiguous().float()
+        plan = self.plan_for(2 * B, H, W, dev, pair=True)
+        plan.image_channels = ic
+        fake, real = fake_image.detach().contiguous().float(), real_image.detach().contiguous().float()
         with torch.cuda.device(dev):
-            s_real = plan.new_slot()
-            real = (s_real, plan.forward(s_real, label, real_image.detach().contiguous().float()))
-            s_fake = plan.new_slot()
-            fake = (s_fake, plan.forward(s_fake, label, fake_image.detach().contiguous().float()))
-        loss_D_fake, loss_D_real = _DiscriminatorLossD.apply(self, plan, fake, real, *self.parameters())
-        loss_G_GAN, loss_G_GAN_Feat = _DiscriminatorLossG.apply(plan, fake, real, fake_image)
+            if ids is not None:
+                gen = plan.forward_pair_from_ids(0, ids[0], ids[1], fake, real, num_labels)
+            else:
+                gen = plan.forward_pair(0, input_label.detach().contiguous().float(), fake, real)
+        loss_D_fake, loss_D_real = _DiscriminatorLossD.apply(self, plan, gen, *self.parameters())
+        loss_G_GAN, loss_G_GAN_Feat = _DiscriminatorLossG.apply(plan, gen, fake_image)
         return loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake
 
 

@@ -35,8 +35,8 @@ def _round_up(x, m):
 
 
 class _DLayer:
-    __slots__ = ("key", "conv", "dgrad", "stride", "cin", "cin_real", "cout", "in_h", "in_w", "out_h", "out_w", "norm",
-                 "final")
+    __slots__ = ("key", "conv", "dgrad", "dgrad_half", "stride", "cin", "cin_real", "cout", "in_h", "in_w", "out_h", "out_w",
+                 "norm", "final")
 
 
 class _Slot:
@@ -48,7 +48,9 @@ class _Slot:
 
 
 class DiscriminatorPlan:
-    def __init__(self, input_nc, ndf, n_layers, num_D, batch, height, width, device, n_slots=3):
+    def __init__(self, input_nc, ndf, n_layers, num_D, batch, height, width, device, n_slots=3, pair=False):
+        """pair=True: `batch` = 2 * B images, the first B fake and the last B real, run as ONE batch (the fused-loss route):
+        the generator-side backward then only walks the first half (extra data-gradient descriptors at batch B)."""
         if num_D < 1 or num_D > 2:
             raise JpdseError("jpdse_b200 discriminator supports num_D in {1, 2} (the reference's default is 2); got %d" % num_D)
         if ndf % 64:
@@ -57,6 +59,9 @@ class DiscriminatorPlan:
             raise JpdseError("jpdse_b200 discriminator supports up to 64 input channels (got %d)" % input_nc)
         self.input_nc, self.ndf, self.n_layers, self.num_D = input_nc, ndf, n_layers, num_D
         self.B, self.H, self.W, self.device = batch, height, width, device
+        if pair and batch % 2:
+            raise JpdseError("a pair plan holds an even number of images")
+        self.pair, self.half = pair, batch // 2
         self.c_in = 64
         B = batch
         widths = [ndf]
@@ -92,6 +97,14 @@ class DiscriminatorPlan:
                 else:
                     L.dgrad = ops.Conv(CONV4X4_S1_FULL, EPI_RAW, B, L.out_h, L.out_w, PAD, cst, L.cout, cin, device,
                                        cout_real=cin_real)
+                L.dgrad_half = None
+                if pair:
+                    if L.stride == 2:
+                        L.dgrad_half = ops.Conv(CONV4X4_S2_DGRAD, EPI_RAW, self.half, L.out_h, L.out_w, PAD, cst, L.cout, cin,
+                                                device, out_hw=(lh, lw), cout_real=cin_real)
+                    else:
+                        L.dgrad_half = ops.Conv(CONV4X4_S1_FULL, EPI_RAW, self.half, L.out_h, L.out_w, PAD, cst, L.cout, cin,
+                                                device, cout_real=cin_real)
                 layers.append(L)
                 lh, lw, cin, cin_real = L.out_h, L.out_w, L.cout, L.cout
             self.scales.append(layers)
@@ -144,6 +157,8 @@ class DiscriminatorPlan:
                 b = state_dict[L.key + ".bias"].detach().to(self.device).contiguous().float()
                 L.conv.pack(w, None if L.norm else b)  # a bias in front of an InstanceNorm cancels exactly
                 L.dgrad.pack(w)
+                if L.dgrad_half is not None:
+                    L.dgrad_half.pack(w)
 
     # ------------------------------------------------------------------ forward
     def new_slot(self):
@@ -158,11 +173,43 @@ class DiscriminatorPlan:
             raise JpdseError("discriminator plan built for (%d,%d,%d,%d), got %s%s" % (
                 self.B, self.input_nc, self.H, self.W, tuple(a.shape), "" if b is None else " + %s" % (tuple(b.shape),)))
         s = self.slots[slot]
+        with ops.stream_cached():
+            for i in range(self.num_D):
+                ops.d_input(a, b, s.x_in[i], self.c_in, pool=i > 0, out_pad=PAD)
+        return self._run_layers(slot)
+
+    def forward_pair_from_ids(self, slot, label, instance, fake, real, num_labels):
+        """Pair plan: operands of [fake; real] straight from the class / instance ids (jpdse_d_input_ids), then the layers."""
+        if not self.pair:
+            raise JpdseError("forward_pair_from_ids needs a pair plan")
+        h = self.half
+        if tuple(fake.shape) != (h, self.input_nc - num_labels - 1, self.H, self.W) or fake.shape != real.shape:
+            raise JpdseError("pair plan built for 2 x (%d,%d,%d,%d) images, got %s / %s" % (
+                h, self.input_nc - num_labels - 1, self.H, self.W, tuple(fake.shape), tuple(real.shape)))
+        s = self.slots[slot]
+        with ops.stream_cached():
+            for i in range(self.num_D):
+                ops.d_input_ids(label, instance, fake, s.x_in[i][:h], real, s.x_in[i][h:], num_labels, pool=i > 0, out_pad=PAD)
+        return self._run_layers(slot)
+
+    def forward_pair(self, slot, input_label, fake, real):
+        """Pair plan from the reference's float32 input_label (B,36,H,W) (routes that do not have the ids)."""
+        if not self.pair:
+            raise JpdseError("forward_pair needs a pair plan")
+        h = self.half
+        s = self.slots[slot]
+        with ops.stream_cached():
+            for i in range(self.num_D):
+                ops.d_input(input_label, fake, s.x_in[i][:h], self.c_in, pool=i > 0, out_pad=PAD)
+                ops.d_input(input_label, real, s.x_in[i][h:], self.c_in, pool=i > 0, out_pad=PAD)
+        return self._run_layers(slot)
+
+    def _run_layers(self, slot):
+        s = self.slots[slot]
         self._generation += 1
         s.generation = self._generation
         with ops.stream_cached():
             for i, layers in enumerate(self.scales):
-                ops.d_input(a, b, s.x_in[i], self.c_in, pool=i > 0, out_pad=PAD)
                 x = s.x_in[i]
                 for j, L in enumerate(layers):
                     if L.final:
@@ -189,19 +236,24 @@ class DiscriminatorPlan:
 
     # ------------------------------------------------------------------ backward
     def backward(self, slot, generation, feat_grads, final_grads, need_input, need_params, param_grads=None, accumulate=False,
-                 input_channels=None):
+                 input_channels=None, first_half=False):
         """Backward of the pass stored in `slot`.
 
         feat_grads[i][j]: dense bf16 (B,h,w,C) gradient w.r.t. feature j < n_layers+1 of scale i, or None.
         final_grads[i]: float32 (B,1,h,w) gradient w.r.t. the output map of scale i, or None.
         need_params: fill `param_grads` {state-dict key: float32 tensor in the torch layout} (`accumulate`: add to them).
         need_input: returns float32 (B,c,H,W) = gradient w.r.t. input channels `input_channels` = (c0, c) (default: all).
+        first_half (pair plans): only the first half of the batch (the fake images) is walked; every gradient tensor handed
+        in has that batch size.
         """
         s = self.slots[slot]
         if s.generation != generation:
             raise JpdseError("jpdse_b200: this discriminator pass was overwritten by a later forward before its backward "
                              "(the plan keeps %d passes alive)" % len(self.slots))
-        B = self.B
+        B = self.half if first_half else self.B
+        if first_half and (not self.pair or need_params):
+            raise JpdseError("first_half backward is the input-gradient walk of a pair plan")
+        tag = "h" if first_half else ""
         g_in = [None] * self.num_D
         with ops.stream_cached():
             for i, layers in enumerate(self.scales):
@@ -210,11 +262,12 @@ class DiscriminatorPlan:
                 for j in range(n - 1, -1, -1):
                     L = layers[j]
                     x = s.x_in[i] if j == 0 else s.feat[i][j - 1]
+                    dgrad = L.dgrad_half if first_half else L.dgrad
                     if L.final:
                         if final_grads[i] is None:
                             continue
                         # float32 (B,1,h,w) -> zero-bordered bf16 with 64 stored channels (the GEMMs' K granularity)
-                        d_out = self._buf("dfin%d" % i, (B, L.out_h + 2 * PAD, L.out_w + 2 * PAD, 64))
+                        d_out = self._buf("dfin%s%d" % (tag, i), (B, L.out_h + 2 * PAD, L.out_w + 2 * PAD, 64))
                         ops.d_input(final_grads[i].contiguous(), None, d_out, 64, pool=False, out_pad=PAD)
                         if need_params:
                             self._bias_grad(param_grads, L.key + ".bias", final_grads[i].sum().reshape(1), accumulate)
@@ -224,21 +277,21 @@ class DiscriminatorPlan:
                             continue  # nothing flows into this layer (and hence into none below it)
                         if g is None:
                             g, skip = skip, None
-                        d_out = self._buf("dout%d_%d" % (i, j), (B, L.out_h + 2 * PAD, L.out_w + 2 * PAD, L.cout))
+                        d_out = self._buf("dout%s%d_%d" % (tag, i, j), (B, L.out_h + 2 * PAD, L.out_w + 2 * PAD, L.cout))
                         if L.norm:
-                            dy = self._buf("dy%d_%d" % (i, j), (B, L.out_h, L.out_w, L.cout))
-                            sums = self._buf("sums%d_%d" % (i, j), (B, L.cout, 2), torch.float64, zero=True)
-                            ops.instnorm_backward_reduce_act(g, 0, skip, s.raw[i][j], s.stats[i][j], dy, sums, B, L.out_h,
+                            dy = self._buf("dy%s%d_%d" % (tag, i, j), (B, L.out_h, L.out_w, L.cout))
+                            sums = self._buf("sums%s%d_%d" % (tag, i, j), (B, L.cout, 2), torch.float64, zero=True)
+                            ops.instnorm_backward_reduce_act(g, 0, skip, s.raw[i][j][:B], s.stats[i][j][:B], dy, sums, B, L.out_h,
                                                              L.out_w, L.cout, SLOPE)
-                            ops.instnorm_backward_apply(dy, s.raw[i][j], s.stats[i][j], sums, d_out, PAD, B, L.out_h, L.out_w,
-                                                        L.cout)
+                            ops.instnorm_backward_apply(dy, s.raw[i][j][:B], s.stats[i][j][:B], sums, d_out, PAD, B, L.out_h,
+                                                        L.out_w, L.cout)
                             if need_params:  # analytically zero (the reference's is rounding noise)
                                 self._bias_grad(param_grads, L.key + ".bias", None, accumulate, L.cout)
                         else:
                             db = None
                             if need_params:
                                 db = self._buf("db%d_%d" % (i, j), (L.cout,), torch.float32, zero=True)
-                            ops.act_backward(g, skip, s.feat[i][j], d_out, db, B, L.out_h, L.out_w, L.cout, PAD, PAD, SLOPE)
+                            ops.act_backward(g, skip, s.feat[i][j][:B], d_out, db, B, L.out_h, L.out_w, L.cout, PAD, PAD, SLOPE)
                             if need_params:
                                 self._bias_grad(param_grads, L.key + ".bias", db, accumulate)
                     if need_params:
@@ -250,9 +303,9 @@ class DiscriminatorPlan:
                             param_grads[key] = dw
                         L.conv.wgrad(x, d_out, PAD, dw, accumulate=accumulate and not fresh)
                     if j > 0 or need_input:
-                        oh, ow = L.dgrad.out_hw
-                        g = self._buf("g%d_%d" % (i, j), (B, oh, ow, L.cin))
-                        L.dgrad.forward(d_out, g)
+                        oh, ow = dgrad.out_hw
+                        g = self._buf("g%s%d_%d" % (tag, i, j), (B, oh, ow, L.cin))
+                        dgrad.forward(d_out, g)
                     else:
                         g = None
                 g_in[i] = g

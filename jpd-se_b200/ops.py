@@ -275,6 +275,35 @@ def d_input(a, b, out, c_pad, pool, out_pad=2):
     return out
 
 
+def d_input_ids(label, instance, image_a, out_a, image_b, out_b, num_labels, pool, out_pad=2):
+    """Discriminator operand(s) from class ids + instance ids + image(s); see jpdse_d_input_ids."""
+    lib = _lib.load()
+    _need(label, "label")
+    _need(instance, "instance")
+    _need(image_a, "image_a", torch.float32)
+    _need(out_a, "out_a", torch.bfloat16)
+    if (image_b is None) != (out_b is None):
+        raise JpdseError("d_input_ids: image_b and out_b go together")
+    if image_b is not None:
+        _need(image_b, "image_b", torch.float32)
+        _need(out_b, "out_b", torch.bfloat16)
+    if label.dtype not in _LABEL_DTYPES or instance.dtype not in _INST_DTYPES:
+        raise JpdseError("d_input_ids: unsupported label / instance dtype (%s, %s)" % (label.dtype, instance.dtype))
+    B, _, H, W = image_a.shape
+    if tuple(label.shape) != (B, 1, H, W) or tuple(instance.shape) != (B, 1, H, W) or image_a.shape[1] != 3:
+        raise JpdseError("d_input_ids: label/instance must be (B,1,H,W) and the image (B,3,H,W)")
+    Ho, Wo = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if pool else (H, W)
+    c_pad = out_a.shape[-1]
+    for o in (out_a, out_b):
+        if o is not None and tuple(o.shape) != (B, Ho + 2 * out_pad, Wo + 2 * out_pad, c_pad):
+            raise JpdseError("d_input_ids: output must be %s, got %s" % ((B, Ho + 2 * out_pad, Wo + 2 * out_pad, c_pad), tuple(o.shape)))
+    check(lib.jpdse_d_input_ids(_ptr(label), _LABEL_DTYPES[label.dtype], _ptr(instance), _INST_DTYPES[instance.dtype],
+                                _ptr(image_a), _ptr(out_a), _ptr(image_b), _ptr(out_b), B, H, W, num_labels, c_pad,
+                                int(bool(pool)), out_pad, _stream()))
+    _count()
+    return out_a
+
+
 def d_input_backward(g0, g1, c0, c, out=None):
     """float32 (B,c,H,W) = g0[..., c0:c0+c] + AvgPool backward of g1[..., c0:c0+c] (g1 optional)."""
     lib = _lib.load()

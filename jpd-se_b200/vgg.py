@@ -14,7 +14,7 @@ gradient at a cut) -> JPDSE_CONV3X3_FULL data gradient; pools by jpdse_maxpool2x
 import torch
 
 from . import ops
-from ._lib import CONV3X3_FULL, CONV3X3_PAD1, EPI_BIAS_ACT, EPI_RAW, JpdseError
+from ._lib import CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_PAD1_NARROW, EPI_BIAS_ACT, EPI_RAW, JpdseError
 
 # torchvision vgg19 `features` up to relu5_1: (feature index, 'conv' cin cout | 'pool'), cut after indices 1, 6, 11, 20, 29
 CFG = (64, 64, "M", 128, 128, "M", 256, 256, 256, 256, "M", 512, 512, 512, 512, "M", 512)
@@ -32,9 +32,14 @@ class VGGPlan:
             raise JpdseError("jpdse_b200 VGG19 needs an image size divisible by 16 (got %dx%d)" % (height, width))
         self.B, self.H, self.W, self.device, self.in_channels = batch, height, width, device, in_channels
         B2 = 2 * batch
-        self.x_in = ops.alloc_nhwc(B2, height + 2, width + 2, 64, device)
+        # the RGB input is stored with 8 channels (16 B per pixel); its conv takes the 3 pixels under a filter row as one
+        # 64-element K block (JPDSE_CONV3X3_PAD1_NARROW: K = 3 x 64 instead of 9 x 64 with a 64-channel padding)
+        if in_channels > 8:
+            raise JpdseError("jpdse_b200 VGG19 takes up to 8 input channels")
+        self.c_in = 8
+        self.x_in = ops.alloc_nhwc(B2, height + 2, width + 2, self.c_in, device)
         self.stages = []
-        h, w, cin, cin_real = height, width, 64, in_channels
+        h, w, cin, cin_real = height, width, self.c_in, in_channels
         x = self.x_in
         idx, k = 0, 0
         for v in CFG:
@@ -48,9 +53,12 @@ class VGGPlan:
             else:
                 st.kind, st.cout = "conv", v
                 st.key = "slice%d.%d" % (k + 1, idx)
-                st.conv = ops.Conv(CONV3X3_PAD1, EPI_BIAS_ACT, B2, h, w, 1, cin, cin_real, v, device, out_pad=1, slope=0.0)
-                # data gradient w.r.t. the (zero-)padded input, fake half only
-                st.dgrad = ops.Conv(CONV3X3_FULL, EPI_RAW, batch, h, w, 2, v, v, cin, device, cout_real=cin_real)
+                first = not self.stages
+                st.conv = ops.Conv(CONV3X3_PAD1_NARROW if first else CONV3X3_PAD1, EPI_BIAS_ACT, B2, h, w, 1, cin, cin_real, v,
+                                   device, out_pad=1, slope=0.0)
+                # data gradient w.r.t. the (zero-)padded input, fake half only (the input conv's: 64 stored channels, 3 real)
+                st.dgrad = ops.Conv(CONV3X3_FULL, EPI_RAW, batch, h, w, 2, v, v, 64 if first else cin, device,
+                                    cout_real=cin_real)
                 st.y = ops.alloc_nhwc(B2, h + 2, w + 2, v, device)
                 cin, cin_real = v, v
                 idx += 2
@@ -96,8 +104,8 @@ class VGGPlan:
         acc = torch.zeros(5, dtype=torch.float64, device=self.device)
         numel = [0.0] * 5
         with ops.stream_cached():
-            ops.d_input(fake, None, self.x_in[:B], 64, pool=False, out_pad=1)
-            ops.d_input(real, None, self.x_in[B:], 64, pool=False, out_pad=1)
+            ops.d_input(fake, None, self.x_in[:B], self.c_in, pool=False, out_pad=1)
+            ops.d_input(real, None, self.x_in[B:], self.c_in, pool=False, out_pad=1)
             for st in self.stages:
                 if st.kind == "conv":
                     st.conv.forward(st.x, st.y)
@@ -135,7 +143,7 @@ class VGGPlan:
                     g, skip = skip, None
                 d_pre = self._buf("dpre_%d" % si, (B, st.h + 4, st.w + 4, st.cout))
                 ops.act_backward(g, skip, st.y[:B], d_pre, None, B, st.h, st.w, st.cout, 1, 2, 0.0, g_pad=g_pad)
-                g = self._buf("g_%d" % si, (B, st.h + 2, st.w + 2, st.cin))
+                g = self._buf("g_%d" % si, (B, st.h + 2, st.w + 2, st.dgrad.cout))
                 st.dgrad.forward(d_pre, g)
                 g_pad = 1
             return ops.nhwc_pad_to_nchw(g, self.in_channels, 1)

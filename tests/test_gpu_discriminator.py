@@ -187,6 +187,53 @@ def test_d_input_and_its_backward(cuda, H, W):
     assert torch.allclose(ops.d_input_backward(g0s, None, 36, 3).cpu(), g0[:, 36:], rtol=0, atol=0)
 
 
+@pytest.mark.parametrize("H,W,ldt,idt", [(16, 32, torch.float32, torch.int32), (33, 47, torch.uint8, torch.int16)])
+def test_d_input_from_ids_equals_the_float_route(cuda, H, W, ldt, idt):
+    """jpdse_d_input_ids (operands straight from class / instance ids) == jpdse_d_input on the reference's float32
+    cat(one-hot, edge, image) built by the oracle; both images of a [fake; real] pair in one launch."""
+    from oracle import generator_oracle as orc
+    ops = _ops()
+    g = torch.Generator().manual_seed(W)
+    B = 2
+    lab = torch.randint(0, 35, (B, 1, H, W), generator=g)
+    inst = torch.randint(0, 5, (B, 1, H // 4 + 1, W // 4 + 1), generator=g).repeat_interleave(4, 2).repeat_interleave(4, 3)[:, :, :H, :W]
+    fake, real = torch.randn(B, 3, H, W, generator=g), torch.randn(B, 3, H, W, generator=g)
+    full = torch.from_numpy(orc.build_input(lab.numpy(), inst.numpy(), fake.numpy(), 35))
+    input_label = full[:, :36].contiguous()
+    for pool in (False, True):
+        Ho, Wo = ((H - 1) // 2 + 1, (W - 1) // 2 + 1) if pool else (H, W)
+        want_a, want_b = (ops.alloc_nhwc(B, Ho + 4, Wo + 4, 64, cuda) for _ in range(2))
+        ops.d_input(input_label.to(cuda), fake.to(cuda), want_a, 64, pool)
+        ops.d_input(input_label.to(cuda), real.to(cuda), want_b, 64, pool)
+        got_a, got_b = (ops.alloc_nhwc(B, Ho + 4, Wo + 4, 64, cuda) for _ in range(2))
+        ops.d_input_ids(lab.to(ldt).to(cuda), inst.to(idt).to(cuda), fake.to(cuda), got_a, real.to(cuda), got_b, 35, pool)
+        assert torch.equal(got_a, want_a) and torch.equal(got_b, want_b)
+        single = ops.alloc_nhwc(B, Ho + 4, Wo + 4, 64, cuda)
+        ops.d_input_ids(lab.to(ldt).to(cuda), inst.to(idt).to(cuda), real.to(cuda), single, None, None, 35, pool)
+        assert torch.equal(single, want_b)
+
+
+def test_narrow_3x3_conv_for_few_input_channels(cuda):
+    """JPDSE_CONV3X3_PAD1_NARROW (the VGG19's RGB conv): 8 stored channels, the 3 pixels under a filter row as one K block."""
+    ops = _ops()
+    from jpdse_b200._lib import CONV3X3_PAD1_NARROW, EPI_BIAS_ACT
+    g = torch.Generator().manual_seed(2)
+    for (B, H, W) in ((2, 16, 32), (1, 40, 136)):
+        x = _bf(torch.randn(B, 3, H, W, generator=g))
+        w = _bf(torch.randn(64, 3, 3, 3, generator=g) * 0.2)
+        bias = torch.randn(64, generator=g) * 0.1
+        want = F.relu(F.conv2d(x, w, bias, padding=1))
+        xs = ops.alloc_nhwc(B, H + 2, W + 2, 8, cuda)
+        ops.d_input(x.to(cuda), None, xs, 8, False, out_pad=1)
+        assert float((_nchw(xs, 1, 3) - x).abs().max()) == 0.0
+        cv = ops.Conv(CONV3X3_PAD1_NARROW, EPI_BIAS_ACT, B, H, W, 1, 8, 3, 64, cuda, out_pad=1, slope=0.0)
+        cv.pack(w.to(cuda), bias.to(cuda))
+        out = ops.alloc_nhwc(B, H + 2, W + 2, 64, cuda)
+        cv.forward(xs, out)
+        assert float((_nchw(out, 1) - want).abs().max()) <= 2.0 ** -7 * float(want.abs().max())
+        assert float(out.float().cpu()[:, 0].abs().max()) == 0.0
+
+
 @pytest.mark.parametrize("C,H,W", [(128, 17, 33), (512, 9, 18), (64, 30, 40)])
 def test_instnorm_act_forward_and_backward(cuda, C, H, W):
     ops = _ops()
@@ -270,12 +317,14 @@ def _setup(cuda, B, H, W, seed=7):
     netD = nw.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[])
     sd = {k: v.detach().clone() for k, v in netD.state_dict().items()}
     g = torch.Generator().manual_seed(seed + 1)
-    lab_ids = torch.randint(0, 35, (B, H // 8, W // 8), generator=g).repeat_interleave(8, 1).repeat_interleave(8, 2)
-    label = F.one_hot(lab_ids, 35).permute(0, 3, 1, 2).float()
-    edge = (torch.rand(B, 1, H, W, generator=g) < 0.07).float()
-    input_label = torch.cat((label, edge), 1)
+    from oracle import generator_oracle as orc
+    lab_ids = torch.randint(0, 35, (B, 1, H // 8, W // 8), generator=g).repeat_interleave(8, 2).repeat_interleave(8, 3)
+    inst_ids = torch.randint(0, 9, (B, 1, H // 8, W // 8), generator=g).repeat_interleave(8, 2).repeat_interleave(8, 3)
     real = torch.rand(B, 3, H, W, generator=g) - 0.5
     fake = (real + 0.1 * torch.randn(B, 3, H, W, generator=g)).clamp(-1, 1)
+    # input_label = cat(one-hot, edge) exactly as the reference's preprocess makes it (pix2pixHD_model.py:376-396)
+    input_label = torch.from_numpy(orc.build_input(lab_ids.numpy(), inst_ids.numpy(), real.numpy(), 35))[:, :36].contiguous()
+    _setup.ids = (lab_ids.float(), inst_ids.int())
     return netD.to(cuda), sd, input_label, fake, real
 
 
@@ -319,7 +368,9 @@ def test_discriminator_losses_and_gradients_vs_oracle(cuda, B, H, W, monkeypatch
             p.grad = None
         f = fake.clone().to(cuda).requires_grad_(True)
         il, re = input_label.to(cuda), real.to(cuda)
-        if fused:
+        if fused == "ids":
+            l_gan, l_fm, l_real, l_fake = netD.fused_losses(None, f, re, ids=ids, num_labels=35)
+        elif fused:
             l_gan, l_fm, l_real, l_fake = netD.fused_losses(il, f, re)
         else:
             crit = torch.nn.MSELoss()
@@ -341,7 +392,8 @@ def test_discriminator_losses_and_gradients_vs_oracle(cuda, B, H, W, monkeypatch
         torch.cuda.synchronize()
         return [float(v) for v in (l_gan, l_fm, l_real, l_fake)], gfake, {n: p.grad.detach().cpu().clone() for n, p in netD.named_parameters()}
 
-    for fused in (True, False):
+    ids = tuple(t.to(cuda) for t in _setup.ids)  # the class / instance ids input_label was made from
+    for fused in (True, "ids", False):
         losses, gfake, pgrads = run(fused)
         for got, want in zip(losses, ref_losses):
             assert abs(got - want) <= 0.02 * abs(want) + 1e-4, (fused, losses, ref_losses)
