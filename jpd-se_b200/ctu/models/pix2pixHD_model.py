@@ -382,10 +382,12 @@ class Pix2PixHDModel(nn.Module):
 
     def _losses(self, input_label, fake_image, real_image, keep_input, ids=None):
         opt = self.opt
+        join_vgg = self._start_vgg_loss(fake_image, real_image)
         if self._fused_d(keep_input):
             # pix2pixHD_model.py:715-753 in one kernel-side pass over [fake; real] (see MultiscaleDiscriminator.fused_losses)
             loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake = self.netD.fused_losses(
-                input_label, fake_image, real_image, ids=ids, num_labels=self.num_labels)
+                input_label, fake_image, real_image, ids=ids, num_labels=self.num_labels,
+                d_stream=self.side_stream('dloss', fake_image.device))
         else:
             # the reference's call sequence, one autograd node per netD call
             pred_fake_pool = self.discriminate(input_label, fake_image, use_pool=True)
@@ -399,9 +401,46 @@ class Pix2PixHDModel(nn.Module):
             for i in range(_opt(opt, 'num_D', 2)):
                 for j in range(len(pred_fake[i]) - 1):
                     loss_G_GAN_Feat = loss_G_GAN_Feat + D_weights * self.criterionFeat(pred_fake[i][j], pred_real[i][j].detach())
-        loss_G_VGG = self.criterionVGG(fake_image, real_image)
         loss_G_distortion = self.criterionDistortion(fake_image, real_image)
+        loss_G_VGG = join_vgg()
         return loss_G_GAN, loss_G_GAN_Feat, loss_G_VGG, loss_G_distortion, loss_D_real, loss_D_fake
+
+    # ------------------------------------------------------------------ side streams of the training step
+    # Autograd runs a node's backward on the CUDA stream its forward ran on. The three loss chains of a step only meet at
+    # the generator output, so each gets its own stream and their kernels fill each other's wave tails:
+    #   main    generator forward -> discriminator pass -> loss_G backward through D into the generator backward
+    #   vgg     VGG19 forward (beside the discriminator forward) and backward (beside D's input-gradient walk)
+    #   dloss   the discriminator's own loss: its parameter-gradient walk runs beside the generator backward
+    # Same kernels, same values; JPDSE_TRAIN_STREAMS=0 keeps everything on the current stream.
+    def side_stream(self, name, device):
+        if os.environ.get('JPDSE_TRAIN_STREAMS', '1') == '0':
+            return None
+        streams = getattr(self, '_side_streams', None)
+        if streams is None:
+            streams = self._side_streams = {}
+        st = streams.get((name, str(device)))
+        if st is None:
+            st = streams[(name, str(device))] = torch.cuda.Stream(device=device)
+        return st
+
+    def _start_vgg_loss(self, fake_image, real_image):
+        """criterionVGG(fake, real) (pix2pixHD_model.py:756) enqueued on the `vgg` stream; returns a function that joins
+        the stream and hands back the loss."""
+        side = self.side_stream('vgg', fake_image.device) if fake_image.is_cuda else None
+        if side is None:
+            loss = self.criterionVGG(fake_image, real_image)
+            return lambda: loss
+        main = torch.cuda.current_stream(fake_image.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            loss = self.criterionVGG(fake_image, real_image)
+        fake_image.record_stream(side)
+        real_image.record_stream(side)
+
+        def join():
+            main.wait_stream(side)
+            return loss
+        return join
 
     def get_eval_loss(self, x_dict):
         """pix2pixHD_model.py:621-641: distortion AFTER de-normalisation and uint8 truncation (tensor2im,

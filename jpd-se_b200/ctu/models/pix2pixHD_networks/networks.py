@@ -478,14 +478,15 @@ class MultiscaleDiscriminator(nn.Module):
         n = self.n_layers + 2
         return [list(outs[i * n:(i + 1) * n]) for i in range(self.num_D)]
 
-    def fused_losses(self, input_label, fake_image, real_image, ids=None, num_labels=None):
+    def fused_losses(self, input_label, fake_image, real_image, ids=None, num_labels=None, d_stream=None):
         """The discriminator half of get_train_loss (pix2pixHD_model.py:715-753) for the LSGAN configuration, without the
         reference's redundancy: D(label, fake.detach()) and D(label, fake) are ONE forward (identical values; only the
         autograd graph differs) and run together with D(label, real) as one batch of 2B images; the feature maps never
         leave NHWC bf16 (the L1 of the feature-matching loss is a kernel over the two halves); the generator's backward
         through D walks the fake half only and skips the parameter gradients the reference throws away.
         ids = (label ids (B,1,H,W), instance ids (B,1,H,W)): build the operands straight from the ids instead of from the
-        float32 `input_label` (which may then be None). Returns (loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake)
+        float32 `input_label` (which may then be None). d_stream: CUDA stream that owns the discriminator's own loss
+        (see Pix2PixHDModel.side_stream). Returns (loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake)
         with the reference's values / gradients."""
         B, ic, H, W = fake_image.shape
         dev = fake_image.device
@@ -497,7 +498,18 @@ class MultiscaleDiscriminator(nn.Module):
                 gen = plan.forward_pair_from_ids(0, ids[0], ids[1], fake, real, num_labels)
             else:
                 gen = plan.forward_pair(0, input_label.detach().contiguous().float(), fake, real)
-        loss_D_fake, loss_D_real = _DiscriminatorLossD.apply(self, plan, gen, *self.parameters())
+        if d_stream is None:
+            loss_D_fake, loss_D_real = _DiscriminatorLossD.apply(self, plan, gen, *self.parameters())
+        else:
+            # the discriminator's own loss lives on `d_stream`: its backward (parameter gradients) then runs there, beside
+            # the generator backward (autograd runs a node's backward on its forward's stream)
+            main = torch.cuda.current_stream(dev)
+            d_stream.wait_stream(main)
+            with torch.cuda.stream(d_stream):
+                loss_D_fake, loss_D_real = _DiscriminatorLossD.apply(self, plan, gen, *self.parameters())
+            main.wait_stream(d_stream)  # the two scalars are combined on the main stream
+            loss_D_fake.record_stream(main)
+            loss_D_real.record_stream(main)
         loss_G_GAN, loss_G_GAN_Feat = _DiscriminatorLossG.apply(plan, gen, fake_image)
         return loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake
 

@@ -92,11 +92,28 @@ class Pix2PixHDTrainer(BaseTrainer):
                                           loss_dict['G_VGG'].item(), _opt(opt, 'distortion_loss_fn', 'l1'),
                                           loss_dict['G_Distortion'].item(), loss_dict['D_real'].item(),
                                           loss_dict['D_fake'].item()))
-        self.optimizer_G.zero_grad()
-        loss_G.backward()  # generator gradients come back already averaged over the ranks
-        self.optimizer_G.step()
-        self.optimizer_D.zero_grad()  # drops the netD gradients loss_G.backward() produced
-        loss_D.backward()
+        d_stream = self.model.side_stream('dloss', loss_G.device) if loss_G.is_cuda and self.model._fused_d(False) else None
+        if d_stream is None:
+            # the reference's order (pix2pixHD_trainer.py:64-78)
+            self.optimizer_G.zero_grad()
+            loss_G.backward()  # generator gradients come back already averaged over the ranks
+            self.optimizer_G.step()
+            self.optimizer_D.zero_grad()  # drops the netD gradients loss_G.backward() produced
+            loss_D.backward()
+        else:
+            # Same two updates, other issue order: the discriminator's gradients depend on nothing the generator update
+            # touches (both losses come from ONE forward, and the fused route's loss_G.backward() deposits no netD
+            # gradients to drop), so loss_D.backward() is enqueued FIRST, on its own stream, and runs beside the
+            # generator's backward + Adam; the discriminator's Adam step still comes last.
+            main = torch.cuda.current_stream(loss_G.device)
+            self.optimizer_D.zero_grad()
+            d_stream.wait_stream(main)
+            with torch.cuda.stream(d_stream):
+                loss_D.backward()
+            self.optimizer_G.zero_grad()
+            loss_G.backward()  # generator gradients come back already averaged over the ranks
+            self.optimizer_G.step()
+            main.wait_stream(d_stream)
         ddp.allreduce_grads(self.model.netD.parameters())
         self.optimizer_D.step()
         self.steps_taken += 1

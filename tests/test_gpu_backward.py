@@ -596,3 +596,42 @@ def test_weight_gradients_on_their_own_stream_equal_the_sequential_backward(cuda
         for n in pa:
             scale = float(pb[n].abs().max()) + 1e-12
             assert float((pa[n] - pb[n]).abs().max()) <= 1e-5 * scale, n
+
+
+def test_training_step_side_streams_equal_in_line(cuda, tmp_path, monkeypatch):
+    """The training step's side streams (VGG19 on its own stream, the discriminator's own loss backward beside the
+    generator backward; Pix2PixHDModel.side_stream) only change WHEN kernels run: losses and every gradient of netG /
+    netD must equal the in-line run (JPDSE_TRAIN_STREAMS=0) up to the run-to-run noise of the atomic reductions."""
+    import importlib
+    import bench
+    tr = importlib.import_module("jpd-se_b200.ctu.trainers.pix2pixHD_trainer")
+    g = torch.Generator().manual_seed(3)
+    B, H, W = 2, 64, 128
+    x_dict = {"label": torch.randint(0, 35, (B, 1, H // 8, W // 8), generator=g).repeat_interleave(8, 2).repeat_interleave(8, 3).float(),
+              "instance": torch.randint(0, 5, (B, 1, H // 8, W // 8), generator=g).repeat_interleave(8, 2).repeat_interleave(8, 3).int(),
+              "image": torch.rand(B, 3, H, W, generator=g) - 0.5, "path": ["a", "b"]}
+    results = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("JPDSE_TRAIN_STREAMS", mode)
+        opt = bench.make_opt()
+        opt.is_train, opt.n_downsample_global, opt.n_blocks_global = True, 2, 2
+        opt.quiet, opt.save_dir, opt.checkpoints_dir = True, str(tmp_path), str(tmp_path)
+        torch.manual_seed(5)
+        trainer = tr.Pix2PixHDTrainer(opt, mode="train")
+        grads = {}
+        # capture the gradients the optimizers see (hooks fire when a gradient is accumulated)
+        for n, p in list(trainer.model.netG.named_parameters()) + [("D." + k, v) for k, v in trainer.model.netD.named_parameters()]:
+            p.register_hook(lambda g_, n=n: grads.__setitem__(n, g_.detach().clone()))
+        out = trainer.step(x_dict)
+        torch.cuda.synchronize()
+        results[mode] = (out, grads)
+    (o0, g0), (o1, g1) = results["0"], results["1"]
+    assert abs(o0 - o1) <= 1e-5 * abs(o0)
+    assert set(g0) == set(g1) and len(g0) > 20
+    for n in g0:
+        a, b = g0[n].double().flatten(), g1[n].double().flatten()
+        if float(a.norm()) == 0.0:
+            assert float(b.norm()) == 0.0, n
+            continue
+        c = float((a * b).sum() / (a.norm() * b.norm()))
+        assert c >= 0.99999 and abs(float(b.norm() / a.norm()) - 1.0) <= 1e-3, (n, c)
