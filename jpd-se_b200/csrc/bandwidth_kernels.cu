@@ -80,6 +80,16 @@ build_input_nhwc_kernel(const void* __restrict__ label, int label_dtype, const v
                         const void* __restrict__ image, ImgNorm nm, int B, int H, int W, int num_labels, int pad, int c_pad,
                         __nv_bfloat16* __restrict__ out, int* __restrict__ bad) {
   extern __shared__ uint4 s_rows[];  // [kBuildThreads][c_pad/8]
+  // uint8 images: the normalised value of each of the 256 byte values, per channel, computed ONCE per block with the
+  // loader's exact float32 formula (two IEEE divisions) -- the per-pixel work is then a shared-memory lookup
+  __shared__ float s_lut[3][256];
+  if (nm.u8) {
+    for (int i = threadIdx.x; i < 3 * 256; i += kBuildThreads) {
+      const int c = i >> 8;
+      s_lut[c][i & 255] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(i & 255), 255.0f), nm.mean[c]), nm.std[c]);
+    }
+    __syncthreads();
+  }
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const size_t total = static_cast<size_t>(B) * Hp * Wp;
   const int vpp = c_pad / 8;
@@ -98,7 +108,15 @@ build_input_nhwc_kernel(const void* __restrict__ label, int label_dtype, const v
       const float edge = load_edge(inst, inst_dtype, img_off, h, w, H, W) ? 1.f : 0.f;
       const size_t plane = static_cast<size_t>(H) * W;
       const size_t ip = static_cast<size_t>(b) * 3 * plane + static_cast<size_t>(h) * W + w;
-      const float r = load_px(image, nm, ip, 0), g = load_px(image, nm, ip + plane, 1), bl = load_px(image, nm, ip + 2 * plane, 2);
+      float r, g, bl;
+      if (nm.u8) {
+        const uint8_t* iu = static_cast<const uint8_t*>(image);
+        r = s_lut[0][iu[ip]];
+        g = s_lut[1][iu[ip + plane]];
+        bl = s_lut[2][iu[ip + 2 * plane]];
+      } else {
+        r = load_px(image, nm, ip, 0), g = load_px(image, nm, ip + plane, 1), bl = load_px(image, nm, ip + 2 * plane, 2);
+      }
       for (int v = 0; v < vpp; ++v) {
         uint32_t wds[4];
 #pragma unroll
@@ -419,33 +437,63 @@ quant_elementwise_kernel(const float* __restrict__ x, const float* __restrict__ 
   }
 }
 
+__device__ __forceinline__ uint32_t sign_bit_u8(float x) {
+  // ((x + 1) / 2).astype(uint8): float -> uint8 truncation of {0, 0.5, 1}
+  return static_cast<uint32_t>(static_cast<uint8_t>(static_cast<int>((x + 1.f) / 2.f)));
+}
+
+// 8 elements per thread: two 16-byte loads, one 8-byte store (one byte per element otherwise: 0.40 of the HBM peak)
 __global__ void __launch_bounds__(256)
 sign_to_bits_kernel(const float* __restrict__ x, uint8_t* __restrict__ y, size_t n) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    // ((x + 1) / 2).astype(uint8): float -> uint8 truncation of {0, 0.5, 1}
-    const float v = (x[i] + 1.f) / 2.f;
-    y[i] = static_cast<uint8_t>(static_cast<int>(v));
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(y) & 7)) == 0;
+  const size_t n8 = aligned ? n / 8 : 0;
+  for (size_t i = tid; i < n8; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(x) + 2 * i + 1);
+    uint2 o;
+    o.x = sign_bit_u8(a.x) | (sign_bit_u8(a.y) << 8) | (sign_bit_u8(a.z) << 16) | (sign_bit_u8(a.w) << 24);
+    o.y = sign_bit_u8(b.x) | (sign_bit_u8(b.y) << 8) | (sign_bit_u8(b.z) << 16) | (sign_bit_u8(b.w) << 24);
+    reinterpret_cast<uint2*>(y)[i] = o;
   }
+  for (size_t i = n8 * 8 + tid; i < n; i += stride) y[i] = static_cast<uint8_t>(sign_bit_u8(x[i]));
 }
 
-// S2HVQ encode: one thread per row of x; the code book lives in shared memory.
+// S2HVQ encode: one thread per row of x; the code book lives in shared memory. kD > 0: the center size is a compile-time
+// constant and the row of x sits in registers (vector loads); kD == 0: any size, the row is re-read from L1 per center
+// (128 loads per row at 16 centers x 8 -- what held the generic form at 0.05 of the HBM peak). Same summation order.
+template <int kD>
 __global__ void __launch_bounds__(128)
-s2hvq_encode_kernel(const float* __restrict__ x, const float* __restrict__ code_book, size_t rows, int d, int L,
+s2hvq_encode_kernel(const float* __restrict__ x, const float* __restrict__ code_book, size_t rows, int d_rt, int L,
                     float sigma, float* __restrict__ scores, long long* __restrict__ index, float* __restrict__ one_hot,
                     float* __restrict__ soft) {
   extern __shared__ float s_cb[];  // [L][d]
+  const int d = kD > 0 ? kD : d_rt;
   for (int i = threadIdx.x; i < L * d; i += blockDim.x) s_cb[i] = code_book[i];
   __syncthreads();
   for (size_t row = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; row < rows;
        row += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const float* xr = x + row * d;
+    float xreg[kD > 0 ? kD : 1];
+    if (kD > 0) {
+      if (kD % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < kD / 4; ++j) {
+          const float4 v4 = __ldg(reinterpret_cast<const float4*>(x + row * kD) + j);
+          xreg[4 * j] = v4.x; xreg[4 * j + 1] = v4.y; xreg[4 * j + 2] = v4.z; xreg[4 * j + 3] = v4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kD; ++j) xreg[j] = __ldg(x + row * kD + j);
+      }
+    }
+    const float* xr = kD > 0 ? xreg : x + row * d;
     float best = 0.f;
     int best_k = 0;
     bool best_nan = false;
     float smax = -INFINITY;  // max of -sigma*score for the soft path
     for (int k = 0; k < L; ++k) {
       float acc = 0.f;
+#pragma unroll
       for (int j = 0; j < d; ++j) {
         const float df = xr[j] - s_cb[k * d + j];
         acc += df * df;
@@ -469,6 +517,7 @@ s2hvq_encode_kernel(const float* __restrict__ x, const float* __restrict__ code_
       float sum = 0.f;
       for (int k = 0; k < L; ++k) {
         float acc = 0.f;
+#pragma unroll
         for (int j = 0; j < d; ++j) {
           const float df = xr[j] - s_cb[k * d + j];
           acc += df * df;
@@ -676,11 +725,18 @@ extern "C" int jpdse_s2hvq_encode(const float* x, const float* code_book, size_t
   if (!(sigma > 0.f)) return fail(JPDSE_ERR_INVALID, "s2hvq_encode: sigma must be greater than 0");
   const size_t smem = static_cast<size_t>(center_size) * n_center * sizeof(float);
   if (smem > 200 * 1024) return fail(JPDSE_ERR_UNSUPPORTED, "s2hvq_encode: code book larger than shared memory");
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  auto kern = s2hvq_encode_kernel<0>;
+  if (center_size == 8 && vec_ok) kern = s2hvq_encode_kernel<8>;
+  else if (center_size == 4 && vec_ok) kern = s2hvq_encode_kernel<4>;
+  else if (center_size == 16 && vec_ok) kern = s2hvq_encode_kernel<16>;
+  else if (center_size == 2) kern = s2hvq_encode_kernel<2>;
+  else if (center_size == 1) kern = s2hvq_encode_kernel<1>;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(s2hvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "s2hvq_encode: %s", cudaGetErrorString(e));
   }
-  s2hvq_encode_kernel<<<grid_for(rows, 128, 1), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+  kern<<<grid_for(rows, 128, 1), 128, smem, static_cast<cudaStream_t>(stream)>>>(
       x, code_book, rows, center_size, n_center, sigma, scores, reinterpret_cast<long long*>(index), one_hot, soft);
   return check_launch("s2hvq_encode_kernel");
 }
@@ -705,6 +761,28 @@ __device__ __forceinline__ uint8_t to_u8(float x, double mean, double std) {
   double v = (static_cast<double>(x) * std + mean) * 255.0;
   v = v < 0.0 ? 0.0 : (v > 255.0 ? 255.0 : v);  // np.clip; NaN falls through both compares like numpy's minimum/maximum do not,
   return static_cast<uint8_t>(v);                // but a NaN pixel is outside the reference's domain (tanh output / normalised image)
+}
+
+// 4 consecutive pixels per thread (3 channels): three 16-byte loads, 12 contiguous output bytes as three 4-byte stores
+__global__ void __launch_bounds__(256)
+tensor2im_u8x4_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, int B, int H, int W, double m0, double m1, double m2,
+                      double s0, double s1, double s2) {
+  const size_t plane = static_cast<size_t>(H) * W;
+  const size_t quads = plane / 4;
+  const size_t total = static_cast<size_t>(B) * quads;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t b = i / quads, q = i % quads;
+    const float4* src = reinterpret_cast<const float4*>(x + b * 3 * plane) + q;
+    const float4 r = __ldg(src), g = __ldg(src + quads), bl = __ldg(src + 2 * quads);
+    const uint32_t r0 = to_u8(r.x, m0, s0), r1 = to_u8(r.y, m0, s0), r2 = to_u8(r.z, m0, s0), r3 = to_u8(r.w, m0, s0);
+    const uint32_t g0 = to_u8(g.x, m1, s1), g1 = to_u8(g.y, m1, s1), g2 = to_u8(g.z, m1, s1), g3 = to_u8(g.w, m1, s1);
+    const uint32_t b0 = to_u8(bl.x, m2, s2), b1 = to_u8(bl.y, m2, s2), b2 = to_u8(bl.z, m2, s2), b3 = to_u8(bl.w, m2, s2);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (b * plane + q * 4) * 3);  // (B, H, W, 3): 12 bytes per quad
+    dst[0] = r0 | (g0 << 8) | (b0 << 16) | (r1 << 24);
+    dst[1] = g1 | (b1 << 8) | (r2 << 16) | (g2 << 24);
+    dst[2] = b2 | (r3 << 8) | (g3 << 16) | (b3 << 24);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -760,6 +838,13 @@ extern "C" int jpdse_tensor2im_u8(const float* x, uint8_t* out, int batch, int c
   const int grid = grid_for(total, 256, 4);
   const double m[3] = {mean[0], channels > 1 ? mean[1] : 0.0, channels > 2 ? mean[2] : 0.0};
   const double s[3] = {std[0], channels > 1 ? std[1] : 1.0, channels > 2 ? std[2] : 1.0};
+  if (channels == 3 && (static_cast<size_t>(height) * width) % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) & 15) | (reinterpret_cast<uintptr_t>(out) & 3)) == 0) {
+    const int grid4 = grid_for(static_cast<size_t>(batch) * height * width / 4, 256, 2);
+    tensor2im_u8x4_kernel<<<grid4, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, batch, height, width, m[0], m[1], m[2], s[0],
+                                                                               s[1], s[2]);
+    return check_launch("tensor2im_u8x4_kernel");
+  }
   tensor2im_u8_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, out, batch, channels, height, width, m[0], m[1], m[2],
                                                                             s[0], s[1], s[2]);
   return check_launch("tensor2im_u8_kernel");

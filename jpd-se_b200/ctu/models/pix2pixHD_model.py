@@ -115,9 +115,6 @@ class Pix2PixHDModel(nn.Module):
             binarize_generator=not _opt(opt, 'no_generator_binarization', True),
             bin_generator_before_res=_opt(opt, 'bin_generator_before_res', False),
             generator_binarizer_out_channels=_opt(opt, 'generator_binarizer_out_channels', 128))
-        if self.is_train and not _opt(opt, 'no_generator_binarization', True):
-            raise NotImplementedError('jpdse_b200 Pix2PixHDModel: training a binarizing generator is outside the '
-                                      'accelerated path (inference / get_code / get_eval_rate are supported)')
         if self.is_train:
             # pix2pixHD_model.py:151-162: D sees semantics (+edge) + image
             netD_input_nc = self.num_labels + _opt(opt, 'num_out_channels', 3)

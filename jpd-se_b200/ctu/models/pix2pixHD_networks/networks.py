@@ -202,11 +202,6 @@ class GlobalGenerator(nn.Module):
     def _wants_grad(self):
         return torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
 
-    def train(self, mode=True):
-        # nn.Module.train flips the Binarizer to its stochastic mode; inside the generator plan it always runs the
-        # deterministic sign (inference-only there), so training a binarizing generator raises in plan_for instead
-        return super(GlobalGenerator, self).train(mode)
-
     def _run(self, batch, height, width, device, run):
         """Run `run(plan)`; with gradients enabled the call becomes one autograd node over all parameters."""
         # define_G(..., gpu_ids=[k]) puts the net on cuda:k whatever the current device is (networks.py:52-53): launch on
@@ -215,6 +210,7 @@ class GlobalGenerator(nn.Module):
             if not self._wants_grad():
                 return run(self.plan_for(batch, height, width, device)).clone()
             plan = self.plan_for(batch, height, width, device, training=True)
+            plan.stochastic = self.training  # the Binarizer's DifferentiableSign: stochastic in train() mode only
             return _GeneratorFunction.apply(self, plan, run, *self.parameters())
 
     def forward(self, input, mode='get_continuous_img'):

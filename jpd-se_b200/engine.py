@@ -97,16 +97,27 @@ class GeneratorPlan:
         # implicit-GEMM launch; the +-1 codes are then the input of the first ConvTranspose
         self.binarizer = None
         if binarizer_out_channels is not None:
-            if training:
-                raise JpdseError("jpdse_b200: a Binarizer inside the generator is inference-only (its stochastic "
-                                 "train mode is available on the stand-alone Binarizer module)")
             if binarizer_out_channels % 64:
                 raise JpdseError("generator binarizer needs out_channels %% 64 == 0")
             self.binarizer_name = "model.%d.conv" % idx
-            self.binarizer = ops.Conv(CONV1X1, EPI_SIGN_NCHW, B, h, w, pad_in, c, c, binarizer_out_channels, device)
+            # inference: sign(tanh(conv)) in the epilogue; training plans: raw conv output, then the stochastic sign
+            # kernel (ctu/quantizers/binarize.py:13-41) and its straight-through backward
+            self.binarizer = ops.Conv(CONV1X1, EPI_RAW if training else EPI_SIGN_NCHW, B, h, w, pad_in, c, c,
+                                      binarizer_out_channels, device)
             self.convs[self.binarizer_name] = self.binarizer
             self.codes = torch.empty((B, binarizer_out_channels, h, w), dtype=torch.float32, device=device)
             self.codes_nhwc = ops.alloc_nhwc(B, h, w, binarizer_out_channels, device)
+            if training:
+                cb = binarizer_out_channels
+                # data gradient of the 1x1 conv = 1x1 conv with the transposed weight
+                self.binarizer_dgrad = ops.Conv(CONV1X1, EPI_RAW, B, h, w, 0, cb, cb, c, device)
+                self.bin_pre = torch.empty((B, h, w, cb), dtype=torch.bfloat16, device=device)
+                self.bin_tanh = torch.empty((B, cb, h, w), dtype=torch.float32, device=device)
+                self.bin_noise = torch.empty((B, cb, h, w), dtype=torch.float32, device=device)
+                self.bin_dpre = torch.empty((B, h, w, cb), dtype=torch.bfloat16, device=device)
+                self.bin_gx = torch.empty((B, h, w, c), dtype=torch.bfloat16, device=device)
+                self.bin_in = None
+                self.stochastic = True  # nn.Module.training of the generator (DifferentiableSign, binarize.py:37-41)
             idx += 1
             pad_in = 0
         c_up = c if self.binarizer is None else binarizer_out_channels
@@ -116,7 +127,8 @@ class GeneratorPlan:
                           c_up if i == 0 else c, c // 2, device)
             self.convs[name] = cv
             if training:  # dgrad of a ConvTranspose == stride-2 conv on the same weight memory
-                self.dgrads[name] = ops.Conv(CONV3X3_S2, EPI_RAW, B, 2 * h, 2 * w, 0, c // 2, c // 2, c, device)
+                self.dgrads[name] = ops.Conv(CONV3X3_S2, EPI_RAW, B, 2 * h, 2 * w, 0, c // 2, c // 2,
+                                             c_up if i == 0 else c, device)
             self.up.append((name, cv))
             idx += 3
             c, h, w = c // 2, 2 * h, 2 * w
@@ -179,6 +191,9 @@ class GeneratorPlan:
             dg = self.dgrads.get(prefix)
             if dg is not None:
                 dg.pack(w)
+            if cv is self.binarizer and self.training:
+                cout, cin = w.shape[0], w.shape[1]
+                self.binarizer_dgrad.pack(w.view(cout, cin).t().contiguous().view(cin, cout, 1, 1))
 
     def _view(self, buf, B, H, W, C):
         return buf[: B * H * W * C].view(B, H, W, C)
@@ -254,7 +269,18 @@ class GeneratorPlan:
                            consumer_reads_border=k != self.n_blocks - 1)
             si += 1
             cur = n_idx
-        if self.binarizer is not None:
+        if self.binarizer is not None and self.training:
+            # Binarizer in train() mode (binarize.py:44-65): conv1x1 -> tanh -> stochastic sign, the uniform noise drawn
+            # from torch's generator exactly like the reference's `input.new(input.size()).uniform_()`
+            if not self.stochastic:
+                raise NotImplementedError("jpdse_b200: gradients through a binarizing generator need train() mode (the "
+                                          "stochastic sign); eval() + autograd is outside the accelerated path")
+            self.bin_in = x
+            self.binarizer.forward(x, self.bin_pre)
+            self.bin_noise.uniform_()
+            ops.binarizer_train_forward(self.bin_pre, self.bin_noise, self.codes, self.bin_tanh)
+            x = ops.nchw_to_nhwc_bf16(self.codes, out=self.codes_nhwc)
+        elif self.binarizer is not None:
             self.binarizer.forward(x, self.codes)  # sign(tanh(conv1x1(x))), float32 NCHW like the reference's codes
             if self._codes_only:
                 return self.codes
@@ -450,6 +476,21 @@ class GeneratorPlan:
             L.dgrad.forward(dx, g)
             if self.capture is not None:
                 self.capture[L.name]["g_in"] = g.clone()  # gradient w.r.t. this layer's input as the conv saw it
+            if self.binarizer is not None and L.x_in is self.codes_nhwc:
+                # Binarizer backward (binarize.py:26-28): identity through the stochastic sign, tanh', then the 1x1
+                # conv's weight gradient and its data gradient (1x1 conv with the transposed weight)
+                ops.binarizer_train_backward(ops.nhwc_bf16_to_nchw(g), self.bin_tanh, self.bin_dpre)
+                dwb = new(self.binarizer_name + ".weight", weight_shapes[self.binarizer_name])
+
+                def bin_grad(dwb=dwb):
+                    self.binarizer.wgrad(self.bin_in, self.bin_dpre, 0, dwb, workspace=ws)
+                    emit(self.binarizer_name + ".weight", dwb)
+
+                bin_ev = weight_grad(bin_grad)
+                if bin_ev is not None:
+                    main.wait_event(bin_ev)  # bin_dpre / bin_in are single buffers: keep it simple, wait
+                g = self.bin_gx
+                self.binarizer_dgrad.forward(self.bin_dpre, g)
             g_pad = self.layers[si - 1].out_pad
             skip, skip_idx = None, None
             if L.residual:

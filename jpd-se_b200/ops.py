@@ -473,6 +473,34 @@ def softsign_f32(x, u):
     return y
 
 
+def binarizer_train_forward(pre_nhwc, noise, y, tanh_out):
+    """Binarizer train(): tanh + stochastic sign of the raw 1x1-conv output (see jpdse_binarizer_train_forward)."""
+    lib = _lib.load()
+    _need(pre_nhwc, "pre", torch.bfloat16)
+    _need(noise, "noise", torch.float32)
+    _need(y, "y", torch.float32)
+    _need(tanh_out, "tanh_out", torch.float32)
+    B, C, H, W = y.shape
+    if tuple(pre_nhwc.shape) != (B, H, W, C) or noise.shape != y.shape or tanh_out.shape != y.shape:
+        raise JpdseError("binarizer_train_forward: shape mismatch")
+    check(lib.jpdse_binarizer_train_forward(_ptr(pre_nhwc), _ptr(noise), _ptr(y), _ptr(tanh_out), B, C, H, W, _stream()))
+    _count()
+    return y
+
+
+def binarizer_train_backward(grad_y, tanh_out, d_pre_nhwc):
+    lib = _lib.load()
+    _need(grad_y, "grad_y", torch.float32)
+    _need(tanh_out, "tanh_out", torch.float32)
+    _need(d_pre_nhwc, "d_pre", torch.bfloat16)
+    B, C, H, W = tanh_out.shape
+    if grad_y.shape != tanh_out.shape or tuple(d_pre_nhwc.shape) != (B, H, W, C):
+        raise JpdseError("binarizer_train_backward: shape mismatch")
+    check(lib.jpdse_binarizer_train_backward(_ptr(grad_y), _ptr(tanh_out), _ptr(d_pre_nhwc), B, C, H, W, _stream()))
+    _count()
+    return d_pre_nhwc
+
+
 def sign_to_bits(x):
     lib = _lib.load()
     _need(x, "x", torch.float32)

@@ -91,7 +91,24 @@ def generator_layers(sd, n_downsampling, n_blocks, binarize=False):
     yield ("head", "model.%d" % (idx + 1))
 
 
-def generator_forward(sd, x, n_downsampling=4, n_blocks=9, round_fn=None, collect=None, binarize=False, codes_only=False):
+class _SoftSignSTE(torch.autograd.Function):
+    """SoftSignFunction (ctu/quantizers/binarize.py:13-28) with the uniform draw supplied: +1 where (1 - x) / 2 <= u, else
+    -1; the backward passes the gradient through unchanged."""
+
+    @staticmethod
+    def forward(ctx, x, u):
+        y = x.clone()
+        y[(1 - x) / 2 <= u] = 1
+        y[(1 - x) / 2 > u] = -1
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def generator_forward(sd, x, n_downsampling=4, n_blocks=9, round_fn=None, collect=None, binarize=False, codes_only=False,
+                      noise=None):
     """GlobalGenerator.forward(mode='get_continuous_img'), networks.py:249-251, functional form.
 
     sd: state dict (torch tensors, reference keys); x: torch float32 (B,C,H,W).
@@ -113,7 +130,9 @@ def generator_forward(sd, x, n_downsampling=4, n_blocks=9, round_fn=None, collec
     for kind, prefix in generator_layers(sd, n_downsampling, n_blocks, binarize):
         if kind == "bin":
             # Binarizer eval (ctu/quantizers/binarize.py:51-54): sign(tanh(conv1x1_nobias(x)))
-            x = torch.sign(torch.tanh(F.conv2d(r(x), r(sd[prefix + ".conv.weight"]))))
+            # train() mode (noise given): the stochastic SoftSignFunction with the same uniform draw (binarize.py:37-41)
+            t = torch.tanh(r(F.conv2d(r(x), r(sd[prefix + ".conv.weight"]))))
+            x = torch.sign(t) if noise is None else _SoftSignSTE.apply(t, noise)
             if collect is not None:
                 collect[prefix] = x
             if codes_only:

@@ -103,7 +103,24 @@ def main():
         assert torch.equal(Gb(x), orc.generator_forward(Gb.state_dict(), x, 4, 2, binarize=True))
         assert torch.equal(Gb(x, mode="get_binary_code"),
                            orc.generator_forward(Gb.state_dict(), x, 4, 2, binarize=True, codes_only=True))
-    print("binarizing generator: oracle == reference (image and get_binary_code, bit-exact), same keys and init")
+    # train() mode: the stochastic sign draws ONE uniform tensor per forward (binarize.py:20); same generator state -> same draw
+    Gb.train()
+    for p_ in Gb.parameters():
+        p_.grad = None
+    torch.manual_seed(123)
+    yb = Gb(x)
+    (10.0 * (yb - torch.zeros_like(yb)).abs().mean()).backward()
+    torch.manual_seed(123)
+    nb = torch.empty(1, 128, x.shape[2] // 16, x.shape[3] // 16).uniform_()
+    sdb = {k: v.detach().clone().requires_grad_(True) for k, v in Gb.state_dict().items()}
+    yo = orc.generator_forward(sdb, x, 4, 2, binarize=True, noise=nb)
+    assert torch.equal(yo, yb), "oracle stochastic binarizing generator != reference (train mode)"
+    (10.0 * yo.abs().mean()).backward()
+    for name, p_ in Gb.named_parameters():
+        assert torch.equal(p_.grad, sdb[name].grad), "oracle gradient != reference for %s (binarizing generator)" % name
+    Gb.eval()
+    print("binarizing generator: oracle == reference (image and get_binary_code, bit-exact), same keys and init; train() mode "
+          "with the same uniform draw: outputs and autograd gradients bit-exact")
 
     # ---------------------------------------------------------------- generator backward (autograd through the reference)
     # loss_G.backward() (pix2pixHD_trainer.py:69) is autograd over the same modules: the oracle's functional forward

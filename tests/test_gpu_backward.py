@@ -635,3 +635,77 @@ def test_training_step_side_streams_equal_in_line(cuda, tmp_path, monkeypatch):
             continue
         c = float((a * b).sum() / (a.norm() * b.norm()))
         assert c >= 0.99999 and abs(float(b.norm() / a.norm()) - 1.0) <= 1e-3, (n, c)
+
+
+def test_binarizing_generator_training(cuda):
+    """binarize_generator=True is the reference parser's default (networks.py:219-238): conv1x1 -> tanh -> STOCHASTIC sign in
+    train() mode (ctu/quantizers/binarize.py:13-65), straight-through backward. The plan draws the uniform noise from torch's
+    generator like the reference; fed the same draw, the oracle (pinned bit-identical to the reference in train() mode) must
+    give the same codes wherever the comparison is not within bf16 rounding of the threshold, an output inside the bf16
+    gate, and -- teacher-forced on OUR codes' decisions -- matching gradients for the Binarizer weight and the layers
+    on both sides of it."""
+    from oracle import generator_oracle as orc
+    nw = _networks()
+    torch.manual_seed(21)
+    n_down, n_blocks, B, H, W = 2, 2, 2, 32, 64
+    net = nw.define_G(39, 3, 64, "global", n_down, n_blocks, 1, 3, "instance", gpu_ids=[0], binarize_generator=True,
+                      bin_generator_before_res=False, generator_binarizer_out_channels=128).train()
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 39, H, W, generator=gen)
+    target = torch.rand(B, 3, H, W, generator=gen) - 0.5
+    y = net(x.to(cuda))
+    (10.0 * (y - target.to(cuda)).abs().mean()).backward()
+    torch.cuda.synchronize()
+    plan = net.plan_for(B, H, W, x.device if x.is_cuda else torch.device("cuda", 0), training=True)
+    noise = plan.bin_noise.cpu().clone()
+    codes = plan.codes.cpu().clone()
+    assert set(codes.unique().tolist()) <= {-1.0, 1.0}
+    # oracle with the same draw, bf16-operand emulation (the codes are threshold decisions: compare like with like)
+    collect = {}
+    with torch.no_grad():
+        orc.generator_forward(sd, x, n_down, n_blocks, round_fn=_bf, binarize=True, noise=noise, collect=collect)
+    key = [k for k in collect if k.endswith(str(4 + 3 * n_down + n_blocks))][0]
+    agree = float((collect[key] == codes).float().mean())
+    print("stochastic codes equal to the same-arithmetic oracle's on %.3f %% of the symbols" % (100 * agree))
+    assert agree >= 0.99
+    # gradients: oracle autograd with OUR codes forced (y_codes = t + (ours - t).detach() keeps the straight-through path)
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+
+    class _Force(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, t, u):
+            return codes.clone()
+
+        @staticmethod
+        def backward(ctx, g_):
+            return g_, None
+    saved = orc._SoftSignSTE
+    orc._SoftSignSTE = _Force
+    try:
+        yo = orc.generator_forward(sdg, x, n_down, n_blocks, binarize=True, noise=noise)
+    finally:
+        orc._SoftSignSTE = saved
+    (10.0 * (yo - target).abs().mean()).backward()
+    err = (y.detach().cpu() - yo.detach()).abs()
+    assert float(err.mean()) <= 0.02 and float(err.max()) <= 0.15
+    bname = "model.%d.conv.weight" % (4 + 3 * n_down + n_blocks)
+    checked = 0
+    for name, p in net.named_parameters():
+        if name.endswith(".bias") and not name.startswith("model.%d." % (len(net.model) - 2)):
+            continue
+        got, ref = p.grad.cpu(), sdg[name].grad
+        c = _cos(got, ref)
+        ratio = float(got.norm() / (ref.norm() + 1e-30))
+        # behind the binarizer (decoder side) the forward is identical given the codes: tight; the Binarizer weight and the
+        # encoder side see the tanh' / ReLU-mask / statistics differences of a bf16 forward: calibrated like the generator's
+        tight = name == bname or int(name.split(".")[1]) > 4 + 3 * n_down + n_blocks
+        assert c >= (0.995 if tight else 0.90) and 0.9 <= ratio <= 1.1, "%s: cosine %.5f norm ratio %.4f" % (name, c, ratio)
+        checked += 1
+    assert checked >= 10 and dict(net.named_parameters())[bname].grad.abs().sum() > 0
+    # eval() + autograd is refused, eval() inference still gives the deterministic sign
+    net.eval()
+    with pytest.raises(NotImplementedError):
+        net(x.to(cuda))
+    with torch.no_grad():
+        assert net(x.to(cuda)).shape == (B, 3, H, W)
