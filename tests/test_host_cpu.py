@@ -226,3 +226,37 @@ def test_vgg_refuses_silent_random_weights(monkeypatch):
         nw.Vgg19()
     monkeypatch.setenv("JPDSE_VGG_RANDOM", "1")
     assert nw.Vgg19().pretrained is False
+
+
+def test_compact_host_loader_on_synthetic_files(tmp_path):
+    """jpd-se_b200/ctu/data without the reference: Cityscapes-layout PNGs written here, compact
+    tensors out; the float_tensors flavour equals torchvision's ToTensor + Normalize + the reference's id handling."""
+    import numpy as np
+    from PIL import Image
+    import torchvision.transforms as T
+    data = importlib.import_module("jpd-se_b200.ctu.data")
+    rng = np.random.RandomState(0)
+    for city, stem in (("aachen", "aachen_000000_000019"), ("bonn", "bonn_000001_000019")):
+        os.makedirs(tmp_path / "leftImg8bit" / "val" / city, exist_ok=True)
+        os.makedirs(tmp_path / "gtFine" / "val" / city, exist_ok=True)
+        Image.fromarray(rng.randint(0, 256, (64, 128, 3), dtype=np.uint8)).save(tmp_path / "leftImg8bit" / "val" / city / (stem + "_leftImg8bit.png"))
+        lab = rng.randint(0, 34, (32, 64), dtype=np.uint8)
+        lab[0, 0] = 255  # 'unknown' -> num_labels
+        Image.fromarray(lab, mode="L").save(tmp_path / "gtFine" / "val" / city / (stem + "_gtFine_labelIds.png"))
+        Image.fromarray(rng.randint(0, 40000, (32, 64)).astype(np.uint16)).save(tmp_path / "gtFine" / "val" / city / (stem + "_gtFine_instanceIds.png"))
+    opt = argparse.Namespace(root_dir=str(tmp_path), mode="val", use_gt_semantics=True, no_instance=False, max_dataset_size=10,
+                             preprocess_mode="fixed", crop_size=64, aspect_ratio=2.0, is_train=False, no_flip=True, num_labels=35,
+                             normalize_mean=[0.5, 0.5, 0.5], normalize_std=[1.0, 1.0, 1.0], batch_size=2, num_workers=0,
+                             dataset="cityscapes")
+    batch = next(iter(data.create_dataloader(opt)))
+    assert batch["label"].dtype == torch.uint8 and tuple(batch["label"].shape) == (2, 1, 32, 64)
+    assert batch["image"].dtype == torch.uint8 and tuple(batch["image"].shape) == (2, 3, 32, 64)
+    assert batch["instance"].dtype == torch.int16 and int(batch["label"].max()) == 35
+    ref = next(iter(data.create_dataloader(opt, float_tensors=True)))
+    img0 = Image.open(batch["path"][0]).convert("RGB").resize((64, 32), Image.BICUBIC)
+    want = T.Normalize([0.5] * 3, [1.0] * 3)(T.ToTensor()(img0))
+    assert torch.equal(ref["image"][0], want)
+    assert torch.equal(ref["label"], batch["label"].float()) and torch.equal(ref["instance"], batch["instance"])
+    opt.preprocess_mode = "scale_width"
+    with pytest.raises(NotImplementedError):
+        data.create_dataloader(opt)

@@ -29,3 +29,12 @@ def test_install_into_reference_builds_our_generator_behind_the_reference_traine
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "loaded the reference checkpoint" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "datasets", "cityscapes_test_CVPR20_1024")), reason="reference dataset not mounted here")
+def test_compact_host_loader_equals_the_reference_loader():
+    """jpd-se_b200/ctu/data against the unmodified reference DataLoader on its bundled Cityscapes files."""
+    env = dict(os.environ, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "loader_pin_check.py"), REF, ROOT], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "LOADER_PIN_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
