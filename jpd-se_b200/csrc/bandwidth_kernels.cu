@@ -493,10 +493,25 @@ s2hvq_encode_kernel(const float* __restrict__ x, const float* __restrict__ code_
     float smax = -INFINITY;  // max of -sigma*score for the soft path
     for (int k = 0; k < L; ++k) {
       float acc = 0.f;
+      if (kD > 0 && kD % 4 == 0) {  // 16-byte shared-memory reads of the center (same summation order)
 #pragma unroll
-      for (int j = 0; j < d; ++j) {
-        const float df = xr[j] - s_cb[k * d + j];
-        acc += df * df;
+        for (int j4 = 0; j4 < kD / 4; ++j4) {
+          const float4 c4 = reinterpret_cast<const float4*>(s_cb)[(k * kD) / 4 + j4];
+          float df = xr[4 * j4] - c4.x;
+          acc += df * df;
+          df = xr[4 * j4 + 1] - c4.y;
+          acc += df * df;
+          df = xr[4 * j4 + 2] - c4.z;
+          acc += df * df;
+          df = xr[4 * j4 + 3] - c4.w;
+          acc += df * df;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < d; ++j) {
+          const float df = xr[j] - s_cb[k * d + j];
+          acc += df * df;
+        }
       }
       if (scores) scores[row * L + k] = acc;
       // torch.min: first minimal index; a NaN wins and the first NaN sticks
@@ -511,8 +526,16 @@ s2hvq_encode_kernel(const float* __restrict__ x, const float* __restrict__ code_
       smax = fmaxf(smax, -sigma * acc);
     }
     if (index) index[row] = best_k;
-    if (one_hot)
-      for (int k = 0; k < L; ++k) one_hot[row * L + k] = (k == best_k) ? 1.f : 0.f;
+    if (one_hot) {
+      if ((L & 3) == 0 && (reinterpret_cast<uintptr_t>(one_hot) & 15) == 0) {
+        float4* oh = reinterpret_cast<float4*>(one_hot + row * L);
+        for (int k4 = 0; k4 < L / 4; ++k4)
+          oh[k4] = make_float4(4 * k4 == best_k ? 1.f : 0.f, 4 * k4 + 1 == best_k ? 1.f : 0.f, 4 * k4 + 2 == best_k ? 1.f : 0.f,
+                               4 * k4 + 3 == best_k ? 1.f : 0.f);
+      } else {
+        for (int k = 0; k < L; ++k) one_hot[row * L + k] = (k == best_k) ? 1.f : 0.f;
+      }
+    }
     if (soft) {
       float sum = 0.f;
       for (int k = 0; k < L; ++k) {

@@ -700,7 +700,7 @@ def test_binarizing_generator_training(cuda):
         # behind the binarizer (decoder side) the forward is identical given the codes: tight; the Binarizer weight and the
         # encoder side see the tanh' / ReLU-mask / statistics differences of a bf16 forward: calibrated like the generator's
         tight = name == bname or int(name.split(".")[1]) > 4 + 3 * n_down + n_blocks
-        assert c >= (0.995 if tight else 0.90) and 0.9 <= ratio <= 1.1, "%s: cosine %.5f norm ratio %.4f" % (name, c, ratio)
+        assert c >= (0.99 if tight else 0.90) and 0.9 <= ratio <= 1.1, "%s: cosine %.5f norm ratio %.4f" % (name, c, ratio)
         checked += 1
     assert checked >= 10 and dict(net.named_parameters())[bname].grad.abs().sum() > 0
     # eval() + autograd is refused, eval() inference still gives the deterministic sign
