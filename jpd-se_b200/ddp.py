@@ -26,9 +26,16 @@ def _world(group=None):
 
 
 class GradReducer:
-    def __init__(self, group=None, bucket_bytes=64 << 20):
+    def __init__(self, group=None, bucket_bytes=64 << 20, tail_bytes=32 << 20, tail_bucket_bytes=2 << 20):
+        """bucket_bytes: size at which a run of ready gradients is handed to all_reduce. The LAST `tail_bytes` of the flat
+        buffer (the gradients the backward produces last: the downsampling convs and the stem) go out in buckets of
+        `tail_bucket_bytes` instead, so the reduction that is still in flight when the backward ends -- the exposed part --
+        is a few MB, not a 64 MB bucket."""
         self.group = group
         self.bucket_elems = max(1, bucket_bytes // 4)
+        self.tail_elems = max(0, tail_bytes // 4)
+        self.tail_bucket_elems = max(1, tail_bucket_bytes // 4)
+        self.total = 0
         self.flat = None
         self.stream = None
         self.copy_out = False  # set by begin(): gradients must leave as copies (an earlier .grad exists)
@@ -43,6 +50,7 @@ class GradReducer:
     # ---- protocol used by _GeneratorFunction.backward / GeneratorPlan.backward
     def begin(self, named_params):
         total = sum((p.numel() + 3) // 4 * 4 for _, p in named_params if p.requires_grad)
+        self.total = total
         ref = next(p for _, p in named_params)
         # Gradient accumulation: autograd's AccumulateGrad keeps the tensors `alloc` hands out WITHOUT copying, so after
         # one backward every p.grad is a view of `flat`. A second backward without zero_grad(set_to_none=True) would
@@ -74,7 +82,8 @@ class GradReducer:
         return t
 
     def ready(self, key, tensor):
-        if self._offset - self._bucket_start >= self.bucket_elems:
+        in_tail = self.total - self._offset < self.tail_elems
+        if self._offset - self._bucket_start >= (self.tail_bucket_elems if in_tail else self.bucket_elems):
             self._launch()
 
     def finish(self):

@@ -43,7 +43,7 @@ def _worker(rank, world, port, ret):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ddp = importlib.import_module("jpd-se_b200.ddp")
-    red = ddp.GradReducer(bucket_bytes=64 * 1024)
+    red = ddp.GradReducer(bucket_bytes=64 * 1024, tail_bytes=48 * 1024, tail_bucket_bytes=4 * 1024)
     grads = _walk(red, rank)
     ok = all(torch.allclose(g, torch.full_like(g, (i + 1) * 1.5)) for i, (n, g) in enumerate(grads.items()))
     # discriminator-style flat all-reduce of .grad
@@ -74,6 +74,8 @@ def test_grad_reducer_two_ranks_gloo():
         assert launched[0][0] == 0 and all(a[1] == b[0] for a, b in zip(launched, launched[1:]))
         total = sum((torch.Size(s).numel() + 3) // 4 * 4 for _, s in SHAPES)
         assert launched[-1][1] == total
+        # the gradients produced last leave in small buckets: what is still in flight when the backward ends is tiny
+        assert (launched[-1][1] - launched[-1][0]) * 4 <= 4 * 1024 + 64 * 39 * 49 * 4
     assert all(torch.equal(a, b) for a, b in zip(ret[0][3], ret[1][3]))
 
 
