@@ -58,7 +58,7 @@ __device__ __forceinline__ int fold_sources(int i, int n, int pad, int (&q)[3]) 
 }
 
 template <bool kRelu, bool kSkip>
-__global__ void __launch_bounds__(kBwdThreads, 3)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, const __nv_bfloat16* __restrict__ skip,
                                 const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
                                 __nv_bfloat16* __restrict__ dy, double* __restrict__ sums, int H, int W, int C, float eps, int iters,
@@ -80,33 +80,24 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
   float s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
-  for (int pix0 = blockIdx.x * (ppi * iters); pix0 < npix; pix0 += gridDim.x * (ppi * iters))
-#pragma unroll 2
-  for (int it = 0; it < iters; ++it) {
-    const int pp = pix0 + it * ppi + psub;
-    if (pp >= npix) break;
-    const int h = pp / W, w = pp - h * W;
-    // all three streams are issued before anything is consumed; the extra reflect-fold sources (border pixels
-    // only) are the rare path
-    const size_t off = static_cast<size_t>(pp) * vpp + vec;
-    const uint4 xr = __ldg(raw4 + off);
-    uint4 sk = make_uint4(0, 0, 0, 0);
-    if (kSkip) sk = __ldg(skip4 + off);
-    float acc[8];
+  // gradient of pixel pp's output: the pixel itself plus (border pixels only) the reflect-pad sources folded onto it
+  auto load_g = [&](int h, int w, float (&acc)[8]) {
     unpack8(__ldg(g4 + (static_cast<size_t>(h + gpad) * Wg + (w + gpad)) * vpp + vec), acc);
-    if (gpad > 0) {
-      int qh[3], qw[3];
-      const int nh = fold_sources(h, H, gpad, qh), nw = fold_sources(w, W, gpad, qw);
-      if (nh * nw > 1) {
-        for (int a = 0; a < nh; ++a)
-          for (int c = (a == 0 ? 1 : 0); c < nw; ++c) {
-            float f[8];
-            unpack8(__ldg(g4 + (static_cast<size_t>(qh[a]) * Wg + qw[c]) * vpp + vec), f);
+  };
+  auto fold_g = [&](int h, int w, float (&acc)[8]) {
+    int qh[3], qw[3];
+    const int nh = fold_sources(h, H, gpad, qh), nw = fold_sources(w, W, gpad, qw);
+    if (nh * nw > 1) {
+      for (int a = 0; a < nh; ++a)
+        for (int c = (a == 0 ? 1 : 0); c < nw; ++c) {
+          float f[8];
+          unpack8(__ldg(g4 + (static_cast<size_t>(qh[a]) * Wg + qw[c]) * vpp + vec), f);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += f[j];
-          }
-      }
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
     }
+  };
+  auto finish = [&](int pp, const uint4& xr, const uint4& sk, float (&acc)[8]) {
     if (kSkip) {
       float f[8];
       unpack8(sk, f);
@@ -134,6 +125,45 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
       s2[j + 1] = fmaf(d1, xh1, s2[j + 1]);
     }
     dy4[static_cast<size_t>(pp) * vpp + vec] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  };
+  // The loads of TWO pixels (raw, gradient, skip: up to six 16-byte loads) are issued before anything is consumed; with a
+  // bounds check between the pixels the compiler cannot hoist the second pixel's loads and a thread has one pixel in
+  // flight (the kernel sat at ~1 TB/s at training batch sizes).
+  for (int pix0 = blockIdx.x * (ppi * iters); pix0 < npix; pix0 += gridDim.x * (ppi * iters)) {
+    if (pix0 + ppi * iters <= npix && (iters & 1) == 0) {
+      for (int it = 0; it < iters; it += 2) {
+        const int pa = pix0 + it * ppi + psub, pb = pa + ppi;
+        const int ha = pa / W, wa = pa - ha * W, hb = pb / W, wb = pb - hb * W;
+        const uint4 xa = __ldg(raw4 + static_cast<size_t>(pa) * vpp + vec), xb = __ldg(raw4 + static_cast<size_t>(pb) * vpp + vec);
+        uint4 ska = make_uint4(0, 0, 0, 0), skb = make_uint4(0, 0, 0, 0);
+        if (kSkip) {
+          ska = __ldg(skip4 + static_cast<size_t>(pa) * vpp + vec);
+          skb = __ldg(skip4 + static_cast<size_t>(pb) * vpp + vec);
+        }
+        float ga[8], gb[8];
+        load_g(ha, wa, ga);
+        load_g(hb, wb, gb);
+        if (gpad > 0) {
+          fold_g(ha, wa, ga);
+          fold_g(hb, wb, gb);
+        }
+        finish(pa, xa, ska, ga);
+        finish(pb, xb, skb, gb);
+      }
+    } else {
+      for (int it = 0; it < iters; ++it) {
+        const int pp = pix0 + it * ppi + psub;
+        if (pp >= npix) break;
+        const int h = pp / W, w = pp - h * W;
+        const uint4 xr = __ldg(raw4 + static_cast<size_t>(pp) * vpp + vec);
+        uint4 sk = make_uint4(0, 0, 0, 0);
+        if (kSkip) sk = __ldg(skip4 + static_cast<size_t>(pp) * vpp + vec);
+        float acc[8];
+        load_g(h, w, acc);
+        if (gpad > 0) fold_g(h, w, acc);
+        finish(pp, xr, sk, acc);
+      }
+    }
   }
   // block reduction over the pixel sub-lanes of each channel vector
 #pragma unroll
@@ -159,7 +189,7 @@ instnorm_backward_reduce_kernel(const __nv_bfloat16* __restrict__ g, int gpad, c
   }
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 4)
+__global__ void __launch_bounds__(kBwdThreads, 2)
 instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ raw,
                                const double* __restrict__ stats, const double* __restrict__ sums,
                                __nv_bfloat16* __restrict__ dx, int zpad, int H, int W, int C, float eps, int iters) {
@@ -184,19 +214,12 @@ instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
   const uint4* dy4 = reinterpret_cast<const uint4*>(dy) + static_cast<size_t>(b) * H * W * vpp;
   const uint4* raw4 = reinterpret_cast<const uint4*>(raw) + static_cast<size_t>(b) * H * W * vpp;
   uint4* dx4 = reinterpret_cast<uint4*>(dx) + static_cast<size_t>(b) * npix * vpp;
-  for (int pix0 = blockIdx.x * (ppi * iters); pix0 < npix; pix0 += gridDim.x * (ppi * iters))
-#pragma unroll 4
-  for (int it = 0; it < iters; ++it) {
-    const int pp = pix0 + it * ppi + psub;
-    if (pp >= npix) break;
-    const int ph = pp / Wz, pw = pp - ph * Wz;
-    const int h = ph - zpad, w = pw - zpad;
+  auto finish = [&](int pp, bool inside, const uint4& dv, const uint4& xv) {
     uint4 o = make_uint4(0, 0, 0, 0);
-    if (h >= 0 && h < H && w >= 0 && w < W) {
-      const size_t src = (static_cast<size_t>(h) * W + w) * vpp + vec;
+    if (inside) {
       float d[8], x[8];
-      unpack8(__ldg(dy4 + src), d);
-      unpack8(__ldg(raw4 + src), x);
+      unpack8(dv, d);
+      unpack8(xv, x);
       uint32_t ow[4];
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
@@ -206,6 +229,46 @@ instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
       o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
     dx4[static_cast<size_t>(pp) * vpp + vec] = o;
+  };
+  // four pixels' loads in flight before anything is consumed (see instnorm_backward_reduce_kernel)
+  for (int pix0 = blockIdx.x * (ppi * iters); pix0 < npix; pix0 += gridDim.x * (ppi * iters)) {
+    if (pix0 + ppi * iters <= npix && (iters & 3) == 0) {
+      for (int it0 = 0; it0 < iters; it0 += 4) {
+        uint4 dv[4], xv[4];
+        int pp[4];
+        bool in[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          pp[u] = pix0 + (it0 + u) * ppi + psub;
+          const int ph = pp[u] / Wz, pw = pp[u] - ph * Wz;
+          const int h = ph - zpad, w = pw - zpad;
+          in[u] = h >= 0 && h < H && w >= 0 && w < W;
+          dv[u] = xv[u] = make_uint4(0, 0, 0, 0);
+          if (in[u]) {
+            const size_t src = (static_cast<size_t>(h) * W + w) * vpp + vec;
+            dv[u] = __ldg(dy4 + src);
+            xv[u] = __ldg(raw4 + src);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) finish(pp[u], in[u], dv[u], xv[u]);
+      }
+    } else {
+      for (int it = 0; it < iters; ++it) {
+        const int pp = pix0 + it * ppi + psub;
+        if (pp >= npix) break;
+        const int ph = pp / Wz, pw = pp - ph * Wz;
+        const int h = ph - zpad, w = pw - zpad;
+        const bool inside = h >= 0 && h < H && w >= 0 && w < W;
+        uint4 dv = make_uint4(0, 0, 0, 0), xv = make_uint4(0, 0, 0, 0);
+        if (inside) {
+          const size_t src = (static_cast<size_t>(h) * W + w) * vpp + vec;
+          dv = __ldg(dy4 + src);
+          xv = __ldg(raw4 + src);
+        }
+        finish(pp, inside, dv, xv);
+      }
+    }
   }
 }
 

@@ -100,22 +100,24 @@ class Pix2PixHDTrainer(BaseTrainer):
             self.optimizer_G.step()
             self.optimizer_D.zero_grad()  # drops the netD gradients loss_G.backward() produced
             loss_D.backward()
+            ddp.allreduce_grads(self.model.netD.parameters())
+            self.optimizer_D.step()
         else:
             # Same two updates, other issue order: the discriminator's gradients depend on nothing the generator update
             # touches (both losses come from ONE forward, and the fused route's loss_G.backward() deposits no netD
-            # gradients to drop), so loss_D.backward() is enqueued FIRST, on its own stream, and runs beside the
-            # generator's backward + Adam; the discriminator's Adam step still comes last.
+            # gradients to drop), so loss_D.backward() and the all-reduce of its 22 MB of gradients are enqueued FIRST, on
+            # their own stream, and run beside the generator's backward + Adam; the discriminator's Adam step comes last.
             main = torch.cuda.current_stream(loss_G.device)
             self.optimizer_D.zero_grad()
             d_stream.wait_stream(main)
             with torch.cuda.stream(d_stream):
                 loss_D.backward()
+                ddp.allreduce_grads(self.model.netD.parameters())
             self.optimizer_G.zero_grad()
             loss_G.backward()  # generator gradients come back already averaged over the ranks
             self.optimizer_G.step()
             main.wait_stream(d_stream)
-        ddp.allreduce_grads(self.model.netD.parameters())
-        self.optimizer_D.step()
+            self.optimizer_D.step()
         self.steps_taken += 1
         if _opt(opt, 'anneal_lambda', False) and not (self.steps_taken % _opt(opt, 'anneal_interval', 5000)):
             self.lambda_distortion_weight *= _opt(opt, 'anneal_factor', 5.)

@@ -32,6 +32,9 @@ class GradReducer:
         `tail_bucket_bytes` instead, so the reduction that is still in flight when the backward ends -- the exposed part --
         is a few MB, not a 64 MB bucket."""
         self.group = group
+        import os
+        if os.environ.get("JPDSE_BUCKET_MB"):  # A/B measurements
+            bucket_bytes = int(float(os.environ["JPDSE_BUCKET_MB"]) * (1 << 20))
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.tail_elems = max(0, tail_bytes // 4)
         self.tail_bucket_elems = max(1, tail_bucket_bytes // 4)
