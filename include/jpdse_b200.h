@@ -181,6 +181,13 @@ int jpdse_instnorm_backward_apply(const void* dy, const void* raw, const double*
 int jpdse_instnorm_backward_reduce_act(const void* g, int g_pad, const void* skip, const void* raw,
                                        const double* stats, void* dy, double* sums, int batch, int height,
                                        int width, int channels, int relu, float slope, float eps, void* stream);
+/* reduce + apply in ONE launch for small feature maps (height * width <= 2048, e.g. the 1024-channel bottleneck of a
+ * 1024x512 image): one CTA owns all pixels of (image, 8 channels), the sums are a block reduction and dy stays in
+ * registers. Same arguments as the pair; dy (optional, dense bf16 (B,H,W,C)) receives the masked gradient when the caller
+ * needs it (the ResnetBlock skip connection). Returns JPDSE_ERR_UNSUPPORTED for larger maps. */
+int jpdse_instnorm_backward_fused(const void* g, int g_pad, const void* skip, const void* raw, const double* stats,
+                                  void* dy, void* dx, int dx_pad, int batch, int height, int width, int channels,
+                                  int relu, float slope, float eps, void* stream);
 /* Head: nn.Tanh backward (networks.py:246). grad_out / out: float32 NCHW (B,channels<=8,H,W);
  * d_pre: bf16 (B,H+12,W+12,8) = grad_out * (1 - out^2), zero border 6, channels >= `channels` zero;
  * dbias: float32 (channels) += sum over (B,H,W) of d_pre (zeroed by the caller). */

@@ -70,6 +70,8 @@ SIGNATURES = {
     "jpdse_s2hvq_decode": (c_int, [c_void_p, c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "jpdse_instnorm_backward_reduce_act": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                                    c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
+    "jpdse_instnorm_backward_fused": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                              c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "jpdse_d_input": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "jpdse_d_input_ids": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                   c_int, c_int, c_int, c_int, c_void_p]),

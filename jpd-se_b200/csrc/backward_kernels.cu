@@ -272,6 +272,173 @@ instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
   }
 }
 
+// ------------------------------------------------------------------------------------------ fused reduce + apply
+// Small feature maps (H*W <= 8 * kBwdThreads: the 1024-channel bottleneck at 1024x512 images is 32 x 64 = 2048 pixels):
+// ONE CTA owns all pixels of (image, 8 channels), so the two sums of the InstanceNorm backward are a block reduction and
+// the masked gradient dy never goes to memory between the two halves -- it stays in the thread's registers. One launch
+// instead of reduce + apply, no atomics, no sums buffer: reads g (+ skip) and raw once, writes dx once (and dy only when
+// the caller needs it: the ResnetBlock skip connection).
+constexpr int kFusedMaxPix = 8;  // pixels per thread
+
+template <bool kRelu, bool kSkip>
+__global__ void __launch_bounds__(kBwdThreads, 2)
+instnorm_backward_fused_kernel(const __nv_bfloat16* __restrict__ g, int gpad, const __nv_bfloat16* __restrict__ skip,
+                               const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
+                               __nv_bfloat16* __restrict__ dy_out, __nv_bfloat16* __restrict__ dx, int zpad, int H, int W, int C,
+                               float eps, float slope) {
+  __shared__ float s_red[kBwdThreads / 32][16];
+  __shared__ float s_tot[16];
+  const int vpp = C >> 3;
+  const int vec = blockIdx.x;
+  const int b = blockIdx.y;
+  const int npix = H * W;
+  const int Wg = W + 2 * gpad, Hg = H + 2 * gpad;
+  const int Wz = W + 2 * zpad, Hz = H + 2 * zpad;
+  const double inv_n = 1.0 / (static_cast<double>(H) * W);
+  float mean[8], rstd[8];
+  load_mean_rstd(stats, b, C, vec, inv_n, eps, mean, rstd);
+  const uint4* g4 = reinterpret_cast<const uint4*>(g) + static_cast<size_t>(b) * Hg * Wg * vpp;
+  const uint4* skip4 = reinterpret_cast<const uint4*>(skip) + static_cast<size_t>(b) * npix * vpp;
+  const uint4* raw4 = reinterpret_cast<const uint4*>(raw) + static_cast<size_t>(b) * npix * vpp;
+  uint4* dy4 = reinterpret_cast<uint4*>(dy_out) + static_cast<size_t>(b) * npix * vpp;
+  uint4* dx4 = reinterpret_cast<uint4*>(dx) + static_cast<size_t>(b) * Hz * Wz * vpp;
+  // ---- phase 1: every load of this thread's pixels is issued before anything is consumed
+  uint4 xr[kFusedMaxPix], gv[kFusedMaxPix], sk[kFusedMaxPix];
+#pragma unroll
+  for (int u = 0; u < kFusedMaxPix; ++u) {
+    const int pp = threadIdx.x + u * kBwdThreads;
+    xr[u] = gv[u] = sk[u] = make_uint4(0, 0, 0, 0);
+    if (pp < npix) {
+      const int h = pp / W, w = pp - h * W;
+      xr[u] = __ldg(raw4 + static_cast<size_t>(pp) * vpp + vec);
+      gv[u] = __ldg(g4 + (static_cast<size_t>(h + gpad) * Wg + (w + gpad)) * vpp + vec);
+      if (kSkip) sk[u] = __ldg(skip4 + static_cast<size_t>(pp) * vpp + vec);
+    }
+  }
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  uint4 dyv[kFusedMaxPix];
+#pragma unroll
+  for (int u = 0; u < kFusedMaxPix; ++u) {
+    const int pp = threadIdx.x + u * kBwdThreads;
+    dyv[u] = make_uint4(0, 0, 0, 0);
+    if (pp < npix) {
+      float acc[8];
+      unpack8(gv[u], acc);
+      if (gpad > 0) {  // reflect-pad fold-back: border pixels only
+        const int h = pp / W, w = pp - h * W;
+        int qh[3], qw[3];
+        const int nh = fold_sources(h, H, gpad, qh), nw = fold_sources(w, W, gpad, qw);
+        if (nh * nw > 1) {
+          for (int a = 0; a < nh; ++a)
+            for (int c = (a == 0 ? 1 : 0); c < nw; ++c) {
+              float f[8];
+              unpack8(__ldg(g4 + (static_cast<size_t>(qh[a]) * Wg + qw[c]) * vpp + vec), f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+        }
+      }
+      if (kSkip) {
+        float f[8];
+        unpack8(sk[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+      float x[8];
+      unpack8(xr[u], x);
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float xh0 = (x[j] - mean[j]) * rstd[j], xh1 = (x[j + 1] - mean[j + 1]) * rstd[j + 1];
+        float d0 = acc[j], d1 = acc[j + 1];
+        if (kRelu) {
+          d0 = xh0 > 0.f ? d0 : (slope == 0.f ? 0.f : slope * d0);
+          d1 = xh1 > 0.f ? d1 : (slope == 0.f ? 0.f : slope * d1);
+        }
+        const uint32_t pk = bwd_pack_bf16x2(d0, d1);
+        ow[j >> 1] = pk;
+        d0 = __uint_as_float(pk << 16);  // sums over the bf16-rounded gradient, like the two-kernel path
+        d1 = __uint_as_float(pk & 0xffff0000u);
+        s1[j] += d0;
+        s1[j + 1] += d1;
+        s2[j] = fmaf(d0, xh0, s2[j]);
+        s2[j + 1] = fmaf(d1, xh1, s2[j + 1]);
+      }
+      dyv[u] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      if (dy_out != nullptr) dy4[static_cast<size_t>(pp) * vpp + vec] = dyv[u];
+    }
+  }
+  // ---- block reduction of the 16 sums (fixed order: bit-reproducible from run to run)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float a = s1[j], c = s2[j];
+    for (int o = 16; o >= 1; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+      s_red[warp][j] = a;
+      s_red[warp][8 + j] = c;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+    for (int wv = 0; wv < kBwdThreads / 32; ++wv) t += s_red[wv][threadIdx.x];
+    s_tot[threadIdx.x] = t * static_cast<float>(inv_n);
+  }
+  __syncthreads();
+  float m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m1[j] = s_tot[j];
+    m2[j] = s_tot[8 + j];
+  }
+  // ---- phase 2: dx = rstd * (dy - mean(dy) - xhat * mean(dy * xhat)), written with its zero border
+#pragma unroll
+  for (int u = 0; u < kFusedMaxPix; ++u) {
+    const int pp = threadIdx.x + u * kBwdThreads;
+    if (pp < npix) {
+      const int h = pp / W, w = pp - h * W;
+      float d[8], x[8];
+      unpack8(dyv[u], d);
+      unpack8(xr[u], x);
+      uint32_t ow[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float xh0 = (x[j] - mean[j]) * rstd[j], xh1 = (x[j + 1] - mean[j + 1]) * rstd[j + 1];
+        ow[j >> 1] = bwd_pack_bf16x2(rstd[j] * (d[j] - m1[j] - xh0 * m2[j]), rstd[j + 1] * (d[j + 1] - m1[j + 1] - xh1 * m2[j + 1]));
+      }
+      dx4[(static_cast<size_t>(h + zpad) * Wz + (w + zpad)) * vpp + vec] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+  }
+  if (zpad > 0) {
+    const int nborder = Hz * Wz - npix;
+    for (int i = threadIdx.x; i < nborder; i += kBwdThreads) {
+      // border pixels in stored order: top rows, bottom rows, then the left / right columns of the interior rows
+      int ph, pw;
+      const int top = zpad * Wz;
+      if (i < top) {
+        ph = i / Wz;
+        pw = i - ph * Wz;
+      } else if (i < 2 * top) {
+        const int k = i - top;
+        ph = H + zpad + k / Wz;
+        pw = k % Wz;
+      } else {
+        const int k = i - 2 * top;
+        ph = zpad + k / (2 * zpad);
+        const int c = k % (2 * zpad);
+        pw = c < zpad ? c : W + c;
+      }
+      dx4[(static_cast<size_t>(ph) * Wz + pw) * vpp + vec] = make_uint4(0, 0, 0, 0);
+    }
+  }
+}
+
 // one thread per STORED pixel of d_pre (B, H+12, W+12, 8)
 __global__ void __launch_bounds__(256)
 tanh_backward_nchw_kernel(const float* __restrict__ gout, const float* __restrict__ out, __nv_bfloat16* __restrict__ dpre,
@@ -387,6 +554,38 @@ extern "C" int jpdse_instnorm_backward_reduce_act(const void* g, int g_pad, cons
   else
     instnorm_backward_reduce_kernel<false, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, dp, sums, height, width, channels, eps, iters, slope);
   return check_launch("instnorm_backward_reduce_kernel");
+}
+
+extern "C" int jpdse_instnorm_backward_fused(const void* g, int g_pad, const void* skip, const void* raw, const double* stats,
+                                             void* dy, void* dx, int dx_pad, int batch, int height, int width, int channels,
+                                             int relu, float slope, float eps, void* stream_v) {
+  if (g == nullptr || raw == nullptr || stats == nullptr || dx == nullptr)
+    return fail(JPDSE_ERR_INVALID, "instnorm_backward_fused: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0 || dx_pad < 0 || channels % 8)
+    return fail(JPDSE_ERR_INVALID, "instnorm_backward_fused: bad sizes");
+  if (height * width > kFusedMaxPix * kBwdThreads)
+    return fail(JPDSE_ERR_UNSUPPORTED, "instnorm_backward_fused: %d x %d pixels exceed the %d one CTA holds (use the reduce + "
+                "apply pair)", width, height, kFusedMaxPix * kBwdThreads);
+  if (g_pad < 0 || 2 * g_pad >= height || 2 * g_pad >= width) return fail(JPDSE_ERR_INVALID, "instnorm_backward_fused: bad pad");
+  if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(skip) | reinterpret_cast<uintptr_t>(raw) |
+       reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dx)) & 15)
+    return fail(JPDSE_ERR_INVALID, "instnorm_backward_fused: pointers must be 16-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  dim3 grid(channels / 8, batch);
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(g);
+  const __nv_bfloat16* sp = static_cast<const __nv_bfloat16*>(skip);
+  const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(raw);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(dy);
+  __nv_bfloat16* xp = static_cast<__nv_bfloat16*>(dx);
+  if (relu && skip)
+    instnorm_backward_fused_kernel<true, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, yp, xp, dx_pad, height, width, channels, eps, slope);
+  else if (relu)
+    instnorm_backward_fused_kernel<true, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, yp, xp, dx_pad, height, width, channels, eps, slope);
+  else if (skip)
+    instnorm_backward_fused_kernel<false, true><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, yp, xp, dx_pad, height, width, channels, eps, slope);
+  else
+    instnorm_backward_fused_kernel<false, false><<<grid, kBwdThreads, 0, stream>>>(gp, g_pad, sp, rp, stats, yp, xp, dx_pad, height, width, channels, eps, slope);
+  return check_launch("instnorm_backward_fused_kernel");
 }
 
 extern "C" int jpdse_instnorm_backward_apply(const void* dy, const void* raw, const double* stats, const double* sums, void* dx,

@@ -160,6 +160,7 @@ class GeneratorPlan:
             # stream writes dx_{k-1}
             self.dx_buf = [torch.zeros(dx_elems + 2048, dtype=torch.bfloat16, device=device) for _ in range(2)]
             self.overlap_wgrad = os.environ.get("JPDSE_WGRAD_STREAM", "1") != "0"
+            self.fused_norm_backward = os.environ.get("JPDSE_FUSED_NORM_BACKWARD", "1") != "0"
             self._wgrad_stream = torch.cuda.Stream(device=device)
             self._wgrad_ws = None  # float32 scratch of the weight-gradient kernels on that stream
             self.d_pre = torch.zeros(B * (H + 12) * (W + 12) * 8 + 2048, dtype=torch.bfloat16, device=device)
@@ -454,13 +455,18 @@ class GeneratorPlan:
             sums = self._stats(si, c, self.bwd_sums)
             if self.capture is not None:
                 self.capture[L.name] = {"g": g.clone(), "g_pad": g_pad, "skip": None if skip is None else skip.clone()}
-            ops.instnorm_backward_reduce(g, g_pad, skip, L.raw, L.stats, dy, sums, B, h, w, c, L.relu)
             z = 2 if L.conv.kind == CONV3X3_PAD1 else 0
             slot = step & 1
             if dx_free[slot] is not None:
                 main.wait_event(dx_free[slot])
             dx = self._view(self.dx_buf[slot], B, h + 2 * z, w + 2 * z, c)
-            ops.instnorm_backward_apply(dy, L.raw, L.stats, sums, dx, z, B, h, w, c)
+            if h * w <= ops.FUSED_NORM_BACKWARD_MAX_PIXELS and self.fused_norm_backward:
+                # small maps (the 1024-channel bottleneck): reduce + apply in ONE launch, dy stays in registers and is only
+                # written where the ResnetBlock skip connection needs it
+                ops.instnorm_backward_fused(g, g_pad, skip, L.raw, L.stats, dy if L.residual else None, dx, z, B, h, w, c, L.relu)
+            else:
+                ops.instnorm_backward_reduce(g, g_pad, skip, L.raw, L.stats, dy, sums, B, h, w, c, L.relu)
+                ops.instnorm_backward_apply(dy, L.raw, L.stats, sums, dx, z, B, h, w, c)
             dw = new(L.name + ".weight", weight_shapes[L.name])
 
             def layer_grad(L=L, dx=dx, z=z, dw=dw):

@@ -239,6 +239,26 @@ def instnorm_backward_apply(dy, raw, stats, sums, dx, dx_pad, batch, height, wid
     return dx
 
 
+FUSED_NORM_BACKWARD_MAX_PIXELS = 2048
+
+
+def instnorm_backward_fused(g, g_pad, skip, raw, stats, dy, dx, dx_pad, batch, height, width, channels, relu, slope=0.0, eps=1e-5):
+    """InstanceNorm backward reduce + apply in one launch (height * width <= FUSED_NORM_BACKWARD_MAX_PIXELS); dy optional."""
+    lib = _lib.load()
+    _need(g, "g", torch.bfloat16)
+    _need(raw, "raw", torch.bfloat16)
+    _need(stats, "stats", torch.float64)
+    _need(dx, "dx", torch.bfloat16)
+    if skip is not None:
+        _need(skip, "skip", torch.bfloat16)
+    if dy is not None:
+        _need(dy, "dy", torch.bfloat16)
+    check(lib.jpdse_instnorm_backward_fused(_ptr(g), g_pad, _ptr(skip), _ptr(raw), _ptr(stats), _ptr(dy), _ptr(dx), dx_pad, batch,
+                                            height, width, channels, int(bool(relu)), float(slope), eps, _stream()))
+    _count()
+    return dx
+
+
 def instnorm_backward_reduce_act(g, g_pad, skip, raw, stats, dy, sums, batch, height, width, channels, slope, eps=1e-5):
     """InstanceNorm backward reduce with a LeakyReLU(slope) mask (PatchGAN layers 1-3)."""
     lib = _lib.load()

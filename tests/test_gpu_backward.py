@@ -709,3 +709,42 @@ def test_binarizing_generator_training(cuda):
         net(x.to(cuda))
     with torch.no_grad():
         assert net(x.to(cuda)).shape == (B, 3, H, W)
+
+
+@pytest.mark.parametrize("C,H,W,gpad,relu,use_skip,want_dy", [(1024, 32, 64, 1, True, False, False), (1024, 32, 64, 1, False, True, True),
+                                                          (256, 20, 36, 0, True, False, True), (64, 9, 13, 3, True, True, False)])
+def test_fused_instnorm_backward_equals_reduce_plus_apply(cuda, C, H, W, gpad, relu, use_skip, want_dy):
+    """jpdse_instnorm_backward_fused (one CTA per (image, 8 channels), small maps) against the reduce + apply pair and
+    against torch autograd of InstanceNorm2d (+ReLU) (+ReflectionPad2d fold-back) on the same operands."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + H)
+    B, z = 2, 2
+    raw = _bf(torch.randn(B, C, H, W, generator=g) * 1.5 + 0.2).requires_grad_(True)
+    y = F.instance_norm(raw, eps=1e-5)
+    if relu:
+        y = F.relu(y)
+    yp = F.pad(y, (gpad, gpad, gpad, gpad), mode="reflect") if gpad else y
+    gy = _bf(torch.randn(yp.shape, generator=g))
+    sk = _bf(torch.randn(B, C, H, W, generator=g)) if use_skip else None
+    ((yp * gy).sum() + ((y * sk).sum() if use_skip else 0.0)).backward()
+    raws = _nhwc(raw.detach()).to(cuda)
+    st = torch.stack((raw.detach().double().sum(dim=(2, 3)), (raw.detach().double() ** 2).sum(dim=(2, 3))), -1).to(cuda).contiguous()
+    gs = _nhwc(gy).to(cuda)
+    sks = _nhwc(sk).to(cuda) if use_skip else None
+    dx_f = torch.full((B, H + 2 * z, W + 2 * z, C), 5.0, dtype=torch.bfloat16, device=cuda)
+    dy_f = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=cuda) if want_dy else None
+    ops.instnorm_backward_fused(gs, gpad, sks, raws, st, dy_f, dx_f, z, B, H, W, C, relu)
+    dy_p = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=cuda)
+    sums = torch.zeros(B, C, 2, dtype=torch.float64, device=cuda)
+    ops.instnorm_backward_reduce(gs, gpad, sks, raws, st, dy_p, sums, B, H, W, C, relu)
+    dx_p = torch.empty_like(dx_f)
+    ops.instnorm_backward_apply(dy_p, raws, st, sums, dx_p, z, B, H, W, C)
+    if want_dy:
+        assert torch.equal(dy_f, dy_p)  # the masked gradient is the same arithmetic
+    scale = float(raw.grad.abs().max())
+    inner = dx_f.float().cpu()[:, z:-z, z:-z].permute(0, 3, 1, 2)
+    assert float((inner - raw.grad).abs().max()) <= 2.0 ** -6 * scale
+    assert float((dx_f.float() - dx_p.float()).abs().max()) <= 2.0 ** -7 * scale
+    ring = dx_f.float().cpu().clone()
+    ring[:, z:-z, z:-z] = 0
+    assert float(ring.abs().max()) == 0.0  # zero border written
