@@ -503,8 +503,12 @@ def main():
     trainer = trainers.get_trainer(opt)(opt, "test")
     netG = trainer.model.netG
     B, H, W = args.batch, args.height, args.width
-    # the image shards of this rank (image-sharded inference: rank r owns every world-th batch; per-rank seeds)
-    lab8, ins16, img8, img_f32 = synth_inputs_compact(B, H, W, seed=1234 + rank)
+    # Image-sharded inference: the job is world*B images, image i -> rank i mod N (jpd-se_b200/sharding.py),
+    # every image generated from its own seed (1234 + i), so an image's output does not depend on N or on its batch slot.
+    sharding = importlib.import_module("jpd-se_b200.sharding")
+    my_images = sharding.shard_indices(world * B, rank, world)
+    parts = [synth_inputs_compact(1, H, W, seed=1234 + i) for i in my_images]
+    lab8, ins16, img8, img_f32 = (torch.cat([p_[k] for p_ in parts], 0) for k in range(4))
     d_in = (lab8.to(dev), ins16.to(dev), img8.to(dev))
     plan = netG.plan_for(B, H, W, dev)  # batch >= 8: two half-batch plans on two streams, captured into one CUDA graph
 
@@ -519,6 +523,8 @@ def main():
         elapsed_ms, launches = device_resident(plan, d_in, args.steps, args.warmup, barrier, sampler)
         clocks = sampler.summary() if sampler else None
         out_dev0 = plan.out[0].detach().cpu() if rank == 0 else None  # image 0 of the timed batch, for the parity object
+        # the ONLY exchange of the inference path: one gather of a per-image result (here a checksum), outside the timed region
+        checks = sharding.gather_results(plan.out.double().mean(dim=(1, 2, 3)), world * B, rank, world)
 
         # ------------------------------------------------------------ roofline kernel: same K steps, instrumented
         # CUDA events around every res-block conv launch need the launches to be eager and un-overlapped, so this pass
@@ -617,6 +623,9 @@ def main():
                                    "CUDA graph on two streams)" % (len(res_events), args.steps),
                          "traffic": ncu_traffic(res_batch, H, W),
                          "whole_forward_tflops": FWD_FLOPS_PER_IMAGE * scale * B / (ms_per_step * 1e-3) / 1e12}}
+    line["sharding"] = {"images": world * B, "assignment": "image i -> rank i mod N, seed 1234 + i (jpd-se_b200/sharding.py); no "
+                        "data-path collective, one gather of per-image results after the timed region",
+                        "per_image_output_mean_head": [float(v) for v in checks[:4].tolist()]}
     if fullres is not None:
         line["fullres"] = fullres
     if train is not None:
