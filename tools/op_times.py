@@ -19,7 +19,7 @@ import jpdse_b200  # noqa: E402,F401
 from jpdse_b200 import ops  # noqa: E402
 
 KIND = {0: "3x3pad1", 1: "3x3s2", 2: "convT", 3: "7x7", 4: "1x1", 5: "3x3full", 6: "7x7full", 7: "4x4s2", 8: "4x4s1", 9: "4x4s2dgrad",
-        10: "4x4s1full"}
+        10: "4x4s1full", 11: "3x3narrow"}
 records = []
 
 
@@ -63,7 +63,7 @@ def main():
 
     def run_d():
         f = fake.clone().requires_grad_(True)
-        l_gan, l_fm, l_real, l_fake = model.netD.fused_losses(input_label, f, real)
+        l_gan, l_fm, l_real, l_fake = model.netD.fused_losses(None, f, real, ids=(x["label"], x["instance"]), num_labels=35)
         (l_gan + 10.0 * l_fm).backward()
         for p in model.netD.parameters():
             p.grad = None
