@@ -450,3 +450,42 @@ def test_discriminator_guards(cuda):
         netD(x)
     with pytest.raises(jpdse_b200.JpdseError):
         first[0][-1].sum().backward()
+
+
+def test_discriminator_and_vgg_losses_at_the_training_size(cuda):
+    """BASELINE.json configs[3] image size (1024x512), batch 1: the four discriminator losses (operands built from the ids,
+    fake and real as one batch) and the VGG19 loss against the fp32 CPU oracle, and d(loss_G terms)/d(fake) against the
+    oracle's autograd. Feature maps here are 257x513, 129x257, 65x129, 66x130, 67x131 and 256x512 ... : the odd sizes the
+    reference's PatchGAN produces at its real resolution."""
+    from oracle import generator_oracle as orc
+    nw = _networks()
+    torch.manual_seed(7)
+    netD = nw.define_D(39, 64, 3, "instance", False, 2, True, gpu_ids=[])
+    sd = {k: v.detach().clone() for k, v in netD.state_dict().items()}
+    torch.manual_seed(3)
+    vl = nw.VGGLoss([])
+    sdv = {k: v.detach().clone() for k, v in vl.vgg.state_dict().items()}
+    netD, vl = netD.to(cuda), vl.to(cuda)
+    import bench
+    l8, i16, _u8, real = bench.synth_inputs_compact(1, 512, 1024, seed=9)
+    g = torch.Generator().manual_seed(2)
+    fake = (real + 0.1 * torch.randn(real.shape, generator=g)).clamp(-1, 1)
+    input_label = torch.from_numpy(orc.build_input(l8.float().numpy(), i16.int().numpy(), real.numpy(), 35))[:, :36].contiguous()
+    torch.set_num_threads(os.cpu_count() or 1)
+    fo = fake.clone().requires_grad_(True)
+    o_gan, o_fm, o_real, o_fake = dorc.discriminator_losses(sd, input_label, fo, real, 3, 2)
+    o_vgg = dorc.vgg_loss(sdv, fo, real)
+    (o_gan + 10.0 * o_fm + 10.0 * o_vgg).backward()
+    f = fake.clone().to(cuda).requires_grad_(True)
+    l_gan, l_fm, l_real, l_fake = netD.fused_losses(None, f, real.to(cuda), ids=(l8.to(cuda), i16.to(cuda)), num_labels=35)
+    l_vgg = vl(f, real.to(cuda))
+    (l_gan + 10.0 * l_fm + 10.0 * l_vgg).backward()
+    torch.cuda.synchronize()
+    for name, got, want in (("G_GAN", l_gan, o_gan), ("G_GAN_Feat", l_fm, o_fm), ("D_real", l_real, o_real), ("D_fake", l_fake, o_fake),
+                            ("G_VGG", l_vgg, o_vgg)):
+        print("%-10s ours %.5f oracle %.5f" % (name, float(got), float(want)))
+        assert abs(float(got) - float(want)) <= 0.02 * abs(float(want)) + 1e-4, (name, float(got), float(want))
+    c = _cos(f.grad.cpu(), fo.grad)
+    ratio = float(f.grad.cpu().norm() / fo.grad.norm())
+    print("d(G_GAN + 10 G_GAN_Feat + 10 G_VGG)/d(fake) at 1024x512: cosine %.5f norm ratio %.4f" % (c, ratio))
+    assert c >= 0.97 and 0.95 <= ratio <= 1.05
