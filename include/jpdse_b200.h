@@ -96,8 +96,23 @@ enum jpdse_conv_kind {
   /* 3x3 stride 1 on an input padded by 1 with FEW channels (the VGG19's RGB input conv, networks.py:479): x is       */
   /* (B,H+2,W+2,Cin) with Cin*2 bytes a multiple of 16 and 3*Cin <= 64; the 3*Cin contiguous elements under a filter  */
   /* row are one K block (K = 3 x 64 instead of 9 x 64). The buffer must extend 128 B past its last pixel.            */
-  JPDSE_CONV3X3_PAD1_NARROW = 11
+  JPDSE_CONV3X3_PAD1_NARROW = 11,
+  /* ---- ABI version 3 */
+  /* JPDSE_CONV3X3_FULL on a gradient stored in the SHARED-BORDER layout (see JPDSE_PAD_SHARED; in_pad must be 2):   */
+  /* the whole batch is ONE flat run of positions with row pitch W+2 = the output width, so the GEMM's M dimension   */
+  /* is exactly the B*(H+2)*(W+2) output pixels (the per-image form computes (H+2)*(W+4) positions per image and      */
+  /* rounds every image up to a tile: 152 tiles instead of 144 for the 1024-channel ResnetBlocks at batch 2 -- the    */
+  /* difference between one wave and two on 148 SMs). y is the same dense (B,H+2,W+2,Cout) tensor.                    */
+  JPDSE_CONV3X3_FULL_SHARED = 12
 };
+/* SHARED-BORDER layout of a zero-bordered gradient tensor, selected by OR-ing this flag into the pad argument
+ * (pad = p | JPDSE_PAD_SHARED) of jpdse_instnorm_backward_apply / jpdse_instnorm_backward_fused (dx_pad) and
+ * jpdse_conv_wgrad (dy_pad, JPDSE_CONV3X3_PAD1 only): rows have a pitch of W+p positions -- the p zero positions behind a
+ * row are the right border of that row AND the left border of the next -- and images a stride of (H+p) rows -- the p
+ * zero rows behind an image are its bottom border and the next image's top border. Pixel (b,i,j) lives at position
+ * b*(H+p)*(W+p) + (i+p)*(W+p) + (j+p); the buffer holds B*(H+p)*(W+p) + p*(W+p) + p positions of C channels (the
+ * producers write all of them, zeros included) and should extend 128 further positions (tile over-read, never stored). */
+#define JPDSE_PAD_SHARED 0x100
 enum jpdse_conv_epilogue {
   JPDSE_EPI_RAW_STATS = 0,      /* y = bf16 NHWC raw conv output, stats += (sum, sumsq) per (b,c)    */
   JPDSE_EPI_BIAS_TANH_NCHW = 1, /* y = float32 NCHW tanh(conv + bias)            (networks.py:246)   */

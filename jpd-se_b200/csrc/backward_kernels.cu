@@ -198,8 +198,11 @@ instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
   const int vec = threadIdx.x % vpp;
   const int psub = threadIdx.x / vpp;
   const int b = blockIdx.y;
-  const int Wz = W + 2 * zpad, Hz = H + 2 * zpad;
-  const int npix = Hz * Wz;
+  // JPDSE_PAD_SHARED: pitch W + pad, image stride (H + pad) rows; the last image also owns the trailing zero run
+  const bool shared = (zpad & JPDSE_PAD_SHARED) != 0;
+  zpad &= JPDSE_PAD_SHARED - 1;
+  const int Wz = shared ? W + zpad : W + 2 * zpad, Hz = shared ? H + zpad : H + 2 * zpad;
+  const int npix = Hz * Wz + ((shared && b == static_cast<int>(gridDim.y) - 1) ? zpad * Wz + zpad : 0);
   const double inv_n = 1.0 / (static_cast<double>(H) * W);
   float mean[8], rstd[8], m1[8], m2[8];
   load_mean_rstd(stats, b, C, vec, inv_n, eps, mean, rstd);
@@ -213,7 +216,7 @@ instnorm_backward_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
   }
   const uint4* dy4 = reinterpret_cast<const uint4*>(dy) + static_cast<size_t>(b) * H * W * vpp;
   const uint4* raw4 = reinterpret_cast<const uint4*>(raw) + static_cast<size_t>(b) * H * W * vpp;
-  uint4* dx4 = reinterpret_cast<uint4*>(dx) + static_cast<size_t>(b) * npix * vpp;
+  uint4* dx4 = reinterpret_cast<uint4*>(dx) + static_cast<size_t>(b) * Hz * Wz * vpp;
   auto finish = [&](int pp, bool inside, const uint4& dv, const uint4& xv) {
     uint4 o = make_uint4(0, 0, 0, 0);
     if (inside) {
@@ -293,7 +296,9 @@ instnorm_backward_fused_kernel(const __nv_bfloat16* __restrict__ g, int gpad, co
   const int b = blockIdx.y;
   const int npix = H * W;
   const int Wg = W + 2 * gpad, Hg = H + 2 * gpad;
-  const int Wz = W + 2 * zpad, Hz = H + 2 * zpad;
+  const bool shared = (zpad & JPDSE_PAD_SHARED) != 0;
+  zpad &= JPDSE_PAD_SHARED - 1;
+  const int Wz = shared ? W + zpad : W + 2 * zpad, Hz = shared ? H + zpad : H + 2 * zpad;
   const double inv_n = 1.0 / (static_cast<double>(H) * W);
   float mean[8], rstd[8];
   load_mean_rstd(stats, b, C, vec, inv_n, eps, mean, rstd);
@@ -415,7 +420,14 @@ instnorm_backward_fused_kernel(const __nv_bfloat16* __restrict__ g, int gpad, co
       dx4[(static_cast<size_t>(h + zpad) * Wz + (w + zpad)) * vpp + vec] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
   }
-  if (zpad > 0) {
+  if (shared) {
+    // every stored position of this image that is not an interior pixel (the last image: plus the trailing zero run)
+    const int stored = Hz * Wz + (b == static_cast<int>(gridDim.y) - 1 ? zpad * Wz + zpad : 0);
+    for (int i = threadIdx.x; i < stored; i += kBwdThreads) {
+      const int ph = i / Wz, pw = i - ph * Wz;
+      if (ph < zpad || ph >= H + zpad || pw < zpad) dx4[static_cast<size_t>(i) * vpp + vec] = make_uint4(0, 0, 0, 0);
+    }
+  } else if (zpad > 0) {
     const int nborder = Hz * Wz - npix;
     for (int i = threadIdx.x; i < nborder; i += kBwdThreads) {
       // border pixels in stored order: top rows, bottom rows, then the left / right columns of the interior rows
@@ -600,7 +612,9 @@ extern "C" int jpdse_instnorm_backward_apply(const void* dy, const void* raw, co
     return fail(JPDSE_ERR_INVALID, "instnorm_backward_apply: pointers must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   const int vpp = channels / 8, ppi = kBwdThreads / vpp;
-  const int npix = (height + 2 * dx_pad) * (width + 2 * dx_pad);
+  const int zp = dx_pad & (JPDSE_PAD_SHARED - 1);
+  const int npix = (dx_pad & JPDSE_PAD_SHARED) ? (height + zp) * (width + zp) + zp * (width + zp) + zp
+                                               : (height + 2 * zp) * (width + 2 * zp);
   const int iters = pick_iters(npix, ppi, batch);
   const int per_block = ppi * iters;
   int gx = (npix + per_block - 1) / per_block;

@@ -609,6 +609,7 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
   g->path = kPathIgemm;
   switch (d->kind) {
     case JPDSE_CONV3X3_FULL:
+    case JPDSE_CONV3X3_FULL_SHARED:
       if (d->cin % 64) return fail(JPDSE_ERR_UNSUPPORTED, "conv full: cin must be a multiple of 64 (got %d)", d->cin);
       if (d->in_pad != 2) return fail(JPDSE_ERR_INVALID, "CONV3X3_FULL needs in_pad == 2");
       g->out_h = g->gemm_h = d->in_h + 2;
@@ -717,7 +718,8 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
   // the tile count doubles (an N = 128 MMA costs about half an N = 256 one, so a lone tile also finishes sooner).
   // (A wave-quantisation-aware choice for the flat data-gradient kinds was tried and lost: N = 128 doubles the unique
   // A traffic and falls back to per-lane stores there.)
-  if (g->bn == 256 && g->path == kPathIgemm && d->kind != JPDSE_CONV3X3_FULL && d->kind != JPDSE_CONV4X4_S1_FULL) {
+  if (g->bn == 256 && g->path == kPathIgemm && d->kind != JPDSE_CONV3X3_FULL && d->kind != JPDSE_CONV3X3_FULL_SHARED &&
+      d->kind != JPDSE_CONV4X4_S1_FULL) {
     const long long m_tiles = (static_cast<long long>(d->batch) * g->gemm_h * g->gemm_w + 127) / 128;
     if (m_tiles * (g->rows / 256) * 4 < static_cast<long long>(num_sms()) * 3) g->bn = 128;
   }
@@ -994,12 +996,12 @@ extern "C" int jpdse_conv_pack_weights(const jpdse_conv_desc* d, const float* w,
         pack3x3_fwd_kernel<64><<<dim3(d->cout, d->cin / 64), 32, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_packed), d->cin);
       return check_launch("pack3x3_fwd_kernel");
     }
-    if (fast && d->kind == JPDSE_CONV3X3_FULL) {
+    if (fast && (d->kind == JPDSE_CONV3X3_FULL || d->kind == JPDSE_CONV3X3_FULL_SHARED)) {
       pack3x3_full_kernel<<<dim3(d->cout / 16, d->cin / 64), 256, 0, st>>>(w, static_cast<__nv_bfloat16*>(w_packed), d->cin, d->cout);
       return check_launch("pack3x3_full_kernel");
     }
   }
-  PackParams q{d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt, g.path,
+  PackParams q{d->kind == JPDSE_CONV3X3_FULL_SHARED ? JPDSE_CONV3X3_FULL : d->kind, d->cin, d->cin_real, d->cout, g.rows, g.ktot, g.cpt, g.path,
                (d->cout_real > 0 && d->cout_real <= d->cout) ? d->cout_real : d->cout};
   const size_t total = static_cast<size_t>(g.rows) * g.ktot;
   int blocks = static_cast<int>((total + 255) / 256);
@@ -1028,9 +1030,19 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  const bool flat = d->kind == JPDSE_CONV3X3_FULL || d->kind == JPDSE_CONV7X7_FULL || d->kind == JPDSE_CONV4X4_S1_FULL;
+  const bool shared = d->kind == JPDSE_CONV3X3_FULL_SHARED;
+  const bool flat = d->kind == JPDSE_CONV3X3_FULL || d->kind == JPDSE_CONV7X7_FULL || d->kind == JPDSE_CONV4X4_S1_FULL || shared;
   p.batch = d->batch;
-  if (flat) {
+  if (shared) {
+    // the whole batch is one run of positions, pitch = output width: position m IS output pixel m of the dense
+    // (B, H+2, W+2, Cout) result -- the kernel sees one image of B*(H+2) rows
+    p.batch = 1;
+    p.flat_pitch = g.out_w;
+    p.tile_h = 1;
+    p.tile_w = 128;
+    p.tiles_h = 1;
+    p.tiles_w = static_cast<int>((static_cast<long long>(d->batch) * g.out_h * g.out_w + 127) / 128);
+  } else if (flat) {
     // M runs over flat positions y*pitch + x of the zero-bordered input; pitch = stored width
     p.flat_pitch = d->in_w + 2 * d->in_pad;
     const long long last = static_cast<long long>(g.out_h - 1) * p.flat_pitch + g.out_w;  // positions needed
@@ -1048,7 +1060,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   }
   p.n_tiles = g.rows / g.bn;
   p.chunks_per_tap = g.cpt;
-  p.out_h = g.out_h;
+  p.out_h = shared ? d->batch * g.out_h : g.out_h;
   p.out_w = g.out_w;
   p.os_h = p.os_w = 1;
   p.ldc = d->cout;
@@ -1198,7 +1210,14 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     strides[0] = C * 2; strides[1] = L * C * 2;
     box[0] = 64; box[1] = 128; box[2] = 1;
     p.a_rank = 3; p.dim_w = 1; p.dim_h = 1; p.dim_b = 2;
-    if (d->kind == JPDSE_CONV3X3_FULL) {
+    if (shared) {
+      // JPDSE_PAD_SHARED layout: B*(H+2)*(W+2) + 2*(W+2) + 2 stored positions, pitch W+2
+      const uint64_t P = W + 2;
+      dims[0] = C; dims[1] = B * (H + 2) * P + 2 * P + 2; dims[2] = 1;
+      strides[1] = dims[1] * C * 2;
+      p.ntaps = 9;
+      for (int t = 0; t < 9; ++t) p.tap_off[t][1] = (t / 3) * static_cast<int>(P) + (t % 3);
+    } else if (d->kind == JPDSE_CONV3X3_FULL) {
       dims[0] = C;
       p.ntaps = 9;
       for (int t = 0; t < 9; ++t) p.tap_off[t][1] = (t / 3) * static_cast<int>(Wp) + (t % 3);

@@ -355,7 +355,10 @@ static int next_pow2(int v) {
 // only if the border exists)
 static void plain_view(uint64_t* dims, uint64_t* strides, uint32_t* box, size_t* base_off, int C, int H, int W, int B,
                        int pad, int oy, int ox, int view_h, int view_w, int kw_cols, int kh_rows) {
-  const uint64_t Wp = W + 2 * pad, Hp = H + 2 * pad;
+  // pad | JPDSE_PAD_SHARED: pitch W + pad, image stride (H + pad) rows (include/jpdse_b200.h)
+  const bool shared = (pad & JPDSE_PAD_SHARED) != 0;
+  pad &= JPDSE_PAD_SHARED - 1;
+  const uint64_t Wp = shared ? W + pad : W + 2 * pad, Hp = shared ? H + pad : H + 2 * pad;
   dims[0] = C; dims[1] = view_w; dims[2] = view_h; dims[3] = B;
   strides[0] = static_cast<uint64_t>(C) * 2; strides[1] = Wp * C * 2; strides[2] = Hp * Wp * C * 2;
   box[0] = 64; box[1] = kw_cols; box[2] = kh_rows; box[3] = 1;
@@ -384,6 +387,8 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
   int rc = conv_geom(d, &g);
   if (rc != JPDSE_OK) return rc;
   if (dy_pad < 0) return fail(JPDSE_ERR_INVALID, "conv_wgrad: dy_pad < 0");
+  if ((dy_pad & JPDSE_PAD_SHARED) && d->kind != JPDSE_CONV3X3_PAD1)
+    return fail(JPDSE_ERR_UNSUPPORTED, "conv_wgrad: the shared-border gradient layout is only built for JPDSE_CONV3X3_PAD1");
   memset(w, 0, sizeof(*w));
   WgParams& p = w->p;
   WgFinalize& f = w->f;

@@ -24,7 +24,8 @@ import os
 import torch
 
 from . import ops
-from ._lib import (CONV1X1, CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_FULL, CONV7X7_PAD3, CONVT3X3_S2,
+from ._lib import (CONV1X1, CONV3X3_FULL, CONV3X3_FULL_SHARED, CONV3X3_PAD1, CONV3X3_S2, CONV7X7_FULL, CONV7X7_PAD3,
+                   CONVT3X3_S2, PAD_SHARED,
                    EPI_BIAS_TANH_NCHW, EPI_RAW, EPI_RAW_STATS, EPI_SIGN_NCHW, JpdseError)
 
 
@@ -59,6 +60,7 @@ class GeneratorPlan:
         self.B, self.H, self.W = batch, height, width
         self.device = device
         self.training = training
+        self.shared_border = os.environ.get("JPDSE_SHARED_BORDER", "1") != "0"  # ResnetBlock gradient layout (backward)
         self.c_in_pad = _round_up(input_nc, 8)
         B, H, W = batch, height, width
 
@@ -87,8 +89,11 @@ class GeneratorPlan:
             c2 = ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, B, h, w, 1, c, c, c, device)
             self.convs[n1], self.convs[n2] = c1, c2
             if training:
-                self.dgrads[n1] = ops.Conv(CONV3X3_FULL, EPI_RAW, B, h, w, 2, c, c, c, device)
-                self.dgrads[n2] = ops.Conv(CONV3X3_FULL, EPI_RAW, B, h, w, 2, c, c, c, device)
+                # data gradients of the ResnetBlock convs read dx in the shared-border layout (JPDSE_PAD_SHARED): M is exactly
+                # the B*(h+2)*(w+2) output pixels -- 144 tiles instead of 152 at batch 2, one wave on 148 SMs instead of two
+                full = CONV3X3_FULL_SHARED if self.shared_border else CONV3X3_FULL
+                self.dgrads[n1] = ops.Conv(full, EPI_RAW, B, h, w, 2, c, c, c, device)
+                self.dgrads[n2] = ops.Conv(full, EPI_RAW, B, h, w, 2, c, c, c, device)
             self.res.append((n1, c1, n2, c2))
             idx += 1
         self.up = []
@@ -459,7 +464,12 @@ class GeneratorPlan:
             slot = step & 1
             if dx_free[slot] is not None:
                 main.wait_event(dx_free[slot])
-            dx = self._view(self.dx_buf[slot], B, h + 2 * z, w + 2 * z, c)
+            if z and self.shared_border:
+                # B*(h+2)*(w+2) + 2*(w+2) + 2 positions of c channels; the kernels only see the pointer
+                dx = self.dx_buf[slot][:(B * (h + z) * (w + z) + z * (w + z) + z) * c].view(-1, c)
+                z |= PAD_SHARED
+            else:
+                dx = self._view(self.dx_buf[slot], B, h + 2 * z, w + 2 * z, c)
             if h * w <= ops.FUSED_NORM_BACKWARD_MAX_PIXELS and self.fused_norm_backward:
                 # small maps (the 1024-channel bottleneck): reduce + apply in ONE launch, dy stays in registers and is only
                 # written where the ResnetBlock skip connection needs it

@@ -9,7 +9,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (CONV1X1, CONV3X3_FULL, CONV3X3_PAD1, CONV3X3_S2, CONV4X4_S1, CONV4X4_S1_FULL, CONV4X4_S2,
+from ._lib import (CONV1X1, CONV3X3_FULL, CONV3X3_FULL_SHARED, CONV3X3_PAD1, CONV3X3_S2, CONV4X4_S1, CONV4X4_S1_FULL, CONV4X4_S2,
                    CONV4X4_S2_DGRAD, CONV7X7_FULL, CONV7X7_PAD3, CONVT3X3_S2, EPI_BIAS_ACT, EPI_BIAS_NCHW,
                    EPI_BIAS_TANH_NCHW, EPI_RAW, EPI_RAW_STATS, EPI_SIGN_NCHW, ConvDesc, JpdseError, check)
 
@@ -137,7 +137,8 @@ class Conv:
         self.launches = self.lib.jpdse_conv_launch_count(ctypes.byref(self.desc))
         self.kind, self.epilogue = kind, epilogue
         self.out_hw = {CONV3X3_S2: (in_h // 2, in_w // 2), CONVT3X3_S2: (in_h * 2, in_w * 2),
-                       CONV3X3_FULL: (in_h + 2, in_w + 2), CONV7X7_FULL: (in_h + 6, in_w + 6),
+                       CONV3X3_FULL: (in_h + 2, in_w + 2), CONV3X3_FULL_SHARED: (in_h + 2, in_w + 2),
+                       CONV7X7_FULL: (in_h + 6, in_w + 6),
                        CONV4X4_S2: (in_h // 2 + 1, in_w // 2 + 1), CONV4X4_S1: (in_h + 1, in_w + 1),
                        CONV4X4_S2_DGRAD: out_hw, CONV4X4_S1_FULL: (in_h - 1, in_w - 1)}.get(kind, (in_h, in_w))
         self.out_pad = out_pad

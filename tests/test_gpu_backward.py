@@ -748,3 +748,76 @@ def test_fused_instnorm_backward_equals_reduce_plus_apply(cuda, C, H, W, gpad, r
     ring = dx_f.float().cpu().clone()
     ring[:, z:-z, z:-z] = 0
     assert float(ring.abs().max()) == 0.0  # zero border written
+
+
+def _to_shared(t_nhwc, p):
+    """(B,H,W,C) -> the JPDSE_PAD_SHARED layout as a flat (positions, C) tensor: pitch W+p, image stride (H+p) rows."""
+    B, H, W, C = t_nhwc.shape
+    P, S = W + p, (H + p) * (W + p)
+    flat = torch.zeros(B * S + p * P + p + 256, C, dtype=t_nhwc.dtype, device=t_nhwc.device)
+    for b in range(B):
+        rows = flat[b * S + p * P + p: b * S + p * P + p + H * P].view(H, P, C)
+        rows[:, :W] = t_nhwc[b]
+    return flat
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 64, 1024), (1, 8, 16, 64), (3, 12, 20, 128), (4, 32, 64, 256)])
+def test_shared_border_gradient_layout(cuda, B, H, W, C):
+    """JPDSE_PAD_SHARED / JPDSE_CONV3X3_FULL_SHARED (the ResnetBlock gradients of the backward walk): the InstanceNorm
+    backward kernels write the layout (every stored position, zeros included), and the data-gradient conv and the weight
+    gradient read it -- each BIT-IDENTICAL to the per-image bordered form on the same operands."""
+    ops = _ops()
+    from jpdse_b200._lib import CONV3X3_FULL, CONV3X3_FULL_SHARED, CONV3X3_PAD1, EPI_RAW, EPI_RAW_STATS, PAD_SHARED
+    g = torch.Generator().manual_seed(B * 1000 + C + W)
+    z = 2
+    P, S = W + z, (H + z) * (W + z)
+    stored = B * S + z * P + z
+    # ---- producers
+    raw = _bf(torch.randn(B, C, H, W, generator=g) * 1.5 + 0.2)
+    raws = _nhwc(raw).to(cuda)
+    st = torch.stack((raw.double().sum(dim=(2, 3)), (raw.double() ** 2).sum(dim=(2, 3))), -1).to(cuda).contiguous()
+    gs = _nhwc(_bf(torch.randn(B, C, H + 2, W + 2, generator=g))).to(cuda)
+    dy = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=cuda)
+    sums = torch.zeros(B, C, 2, dtype=torch.float64, device=cuda)
+    ops.instnorm_backward_reduce(gs, 1, None, raws, st, dy, sums, B, H, W, C, True)
+    dx_ref = torch.full((B, H + 2 * z, W + 2 * z, C), 5.0, dtype=torch.bfloat16, device=cuda)
+    ops.instnorm_backward_apply(dy, raws, st, sums, dx_ref, z, B, H, W, C)
+    want = _to_shared(dx_ref[:, z:-z, z:-z], z)
+    dx_sh = torch.full_like(want, 5.0)
+    ops.instnorm_backward_apply(dy, raws, st, sums, dx_sh, z | PAD_SHARED, B, H, W, C)
+    assert torch.equal(dx_sh[:stored], want[:stored])
+    assert float((dx_sh[stored:].float() - 5.0).abs().max()) == 0.0  # nothing written behind the layout
+    if H * W <= ops.FUSED_NORM_BACKWARD_MAX_PIXELS:
+        dx_ref_f = torch.full_like(dx_ref, 5.0)
+        ops.instnorm_backward_fused(gs, 1, None, raws, st, None, dx_ref_f, z, B, H, W, C, True)
+        dx_sh_f = torch.full_like(want, 5.0)
+        ops.instnorm_backward_fused(gs, 1, None, raws, st, None, dx_sh_f, z | PAD_SHARED, B, H, W, C, True)
+        assert torch.equal(dx_sh_f[:stored], _to_shared(dx_ref_f[:, z:-z, z:-z], z)[:stored])
+        assert float((dx_sh_f[stored:].float() - 5.0).abs().max()) == 0.0
+    # ---- consumers
+    w = _bf(torch.randn(C, C, 3, 3, generator=g) * 0.05).to(cuda)
+    flat = torch.zeros(dx_ref.numel() + 2048, dtype=torch.bfloat16, device=cuda)
+    flat[: dx_ref.numel()] = dx_ref.reshape(-1)
+    dx_b = flat[: dx_ref.numel()].view(dx_ref.shape)
+    full = ops.Conv(CONV3X3_FULL, EPI_RAW, B, H, W, 2, C, C, C, cuda)
+    full.pack(w)
+    out_ref = torch.full((B, H + 2, W + 2, C), float("nan"), dtype=torch.bfloat16, device=cuda)
+    full.forward(dx_b, out_ref)
+    shared = ops.Conv(CONV3X3_FULL_SHARED, EPI_RAW, B, H, W, 2, C, C, C, cuda)
+    shared.pack(w)
+    out_sh = torch.full((B * (H + 2) * (W + 2) + 64, C), float("nan"), dtype=torch.bfloat16, device=cuda)
+    shared.forward(dx_sh, out_sh)
+    torch.cuda.synchronize()
+    assert torch.equal(out_sh[: B * (H + 2) * (W + 2)].view(out_ref.shape), out_ref)
+    assert torch.isnan(out_sh[B * (H + 2) * (W + 2):].float()).all()  # no store behind the last output pixel
+    fwd = ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, B, H, W, 1, C, C, C, cuda)
+    x_in = _nhwc(_bf(torch.randn(B, C, H + 2, W + 2, generator=g))).to(cuda)
+    xf = torch.zeros(x_in.numel() + 2048, dtype=torch.bfloat16, device=cuda)
+    xf[: x_in.numel()] = x_in.reshape(-1)
+    x_in = xf[: x_in.numel()].view(x_in.shape)
+    dw_ref = torch.empty(C, C, 3, 3, device=cuda)
+    dw_sh = torch.empty(C, C, 3, 3, device=cuda)
+    fwd.wgrad(x_in, dx_b, z, dw_ref)
+    fwd.wgrad(x_in, dx_sh, z | PAD_SHARED, dw_sh)
+    torch.cuda.synchronize()
+    assert torch.equal(dw_sh, dw_ref)
