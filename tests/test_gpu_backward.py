@@ -820,4 +820,5 @@ def test_shared_border_gradient_layout(cuda, B, H, W, C):
     fwd.wgrad(x_in, dx_b, z, dw_ref)
     fwd.wgrad(x_in, dx_sh, z | PAD_SHARED, dw_sh)
     torch.cuda.synchronize()
-    assert torch.equal(dw_sh, dw_ref)
+    # (split-K shapes add their partial sums with fp32 atomics in arrival order: equal up to fp32 summation order)
+    assert float((dw_sh - dw_ref).abs().max()) <= 1e-5 * float(dw_ref.abs().max())
