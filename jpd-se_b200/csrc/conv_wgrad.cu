@@ -44,7 +44,13 @@ constexpr int kWgMaxGroups = 16;  // 4x4 PatchGAN convs: one tap per group when 
 constexpr int kWgBox = 64 * 64 * 2;          // one {64 channels, 64 pixels} box, bytes
 constexpr int kWgStageBytes = 6 * kWgBox;    // 2 A boxes + up to 4 B boxes
 constexpr int kWgStages = 4;
+// "tall" items (WgParams::tall): M = 256 = both TMEM accumulators of one item, 4 A boxes + 4 B boxes a stage, three
+// stages in the same shared memory. 64 KB of operands feed 8 MMAs instead of 48 KB feeding 4: the kernel is bound by
+// the L2 -> SM fabric (profiles/r2_ncu_full_wgrad_b2_raw.csv: 11.6 TB/s, tensor pipe 48 %), so bytes per MMA is the lever.
+constexpr int kWgTallStageBytes = 8 * kWgBox;
+constexpr int kWgTallStages = 3;
 constexpr int kWgSmemBytes = 1024 + kWgStages * kWgStageBytes + 256;
+static_assert(kWgTallStages * kWgTallStageBytes <= kWgStages * kWgStageBytes, "tall stages must fit the same allocation");
 
 struct WgView {
   int rank, dim_w, dim_h, dim_b;
@@ -64,6 +70,7 @@ struct WgParams {
   short a_ch[kWgMaxGroups][2], b_ch[kWgMaxGroups][4];    // workspace row / column offset of the box
   int m_tot, n_tot;      // workspace extents: ws[tap][m_tot][n_tot]
   int direct;            // 1: no split-K -> every workspace element has exactly one writer: plain stores, no memset
+  int tall;              // 1: M = 256 per item (m tiles of 256 P channels; A boxes 2, 3 = boxes 0, 1 + 128 channels)
   float* ws;
 };
 
@@ -134,7 +141,10 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
   const int per_split = p.n_groups * p.m_tiles * p.n_tiles;
   const int items = per_split * p.splits;
   const int bn = 64 * p.nb;
-  const uint32_t stage_tx = static_cast<uint32_t>((2 + p.nb) * kWgBox);
+  const int n_a = p.tall ? 4 : 2;  // A boxes per stage
+  const int n_stages = p.tall ? kWgTallStages : kWgStages;
+  const int stage_bytes = p.tall ? kWgTallStageBytes : kWgStageBytes;
+  const uint32_t stage_tx = static_cast<uint32_t>((n_a + p.nb) * kWgBox);
 
   if (warp == kWgProducerWarp) {
     if (elect_one()) {
@@ -172,16 +182,21 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           const int pw = rw * p.kw_cols;
           const int ph = rh * p.kh_rows;
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * kWgStageBytes;
+          uint8_t* st = smem + stage * stage_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             wg_load_box(&tm_a, p.a.rank, &full_bar[stage], st + j * kWgBox, ao[j][0], ao[j][1], ao[j][2], ao[j][3], ao[j][4], pw, ph, b);
+          if (p.tall) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              wg_load_box(&tm_a, p.a.rank, &full_bar[stage], st + (2 + j) * kWgBox, ao[j][0] + 128, ao[j][1], ao[j][2], ao[j][3], ao[j][4], pw, ph, b);
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             if (j < p.nb)
-              wg_load_box(&tm_b, p.b.rank, &full_bar[stage], st + (2 + j) * kWgBox, bo[j][0], bo[j][1], bo[j][2], bo[j][3], bo[j][4], pw, ph, b);
-          if (++stage == kWgStages) {
+              wg_load_box(&tm_b, p.b.rank, &full_bar[stage], st + (n_a + j) * kWgBox, bo[j][0], bo[j][1], bo[j][2], bo[j][3], bo[j][4], pw, ph, b);
+          if (++stage == n_stages) {
             stage = 0;
             phase ^= 1;
           }
@@ -208,6 +223,41 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         const int s = item / per_split;
         const int kb0 = static_cast<int>(static_cast<long long>(kb_total) * s / p.splits);
         const int kb1 = static_cast<int>(static_cast<long long>(kb_total) * (s + 1) / p.splits);
+        if (p.tall) {
+          // both accumulators belong to this item: rows 0..127 in columns 0..255, rows 128..255 in columns 256..511
+          mbar_wait(&tempty_bar[0], acc_phase ^ 1);
+          mbar_wait(&tempty_bar[1], acc_phase ^ 1);
+          tc_fence_after();
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+            const uint64_t adesc0 = umma_desc_mn_sw128(sa);
+            const uint64_t adesc1 = umma_desc_mn_sw128(sa + 2 * kWgBox);
+            const uint64_t bdesc = umma_desc_mn_sw128(sa + 4 * kWgBox);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t accum = (kb != kb0 || k != 0) ? 1u : 0u;
+              umma_bf16<1>(tmem_base, adesc0 + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128), idesc, accum);
+              umma_bf16<1>(tmem_base + 256u, adesc1 + static_cast<uint64_t>(k * 128), bdesc + static_cast<uint64_t>(k * 128), idesc, accum);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) {
+              umma_commit(&tfull_bar[0]);
+              umma_commit(&tfull_bar[1]);
+            }
+            if (++stage == n_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          if (kb1 <= kb0) {
+            umma_commit(&tfull_bar[0]);
+            umma_commit(&tfull_bar[1]);
+          }
+          acc_phase ^= 1;
+          continue;
+        }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * 256);
@@ -243,7 +293,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     uint32_t acc_phase = 0;
     int item_i = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++item_i) {
-      if ((item_i & 1) != group) continue;
+      if (!p.tall && (item_i & 1) != group) continue;  // tall items: group g drains rows 128 g .. 128 g + 127 of every item
       const int s = item / per_split;
       int rem = item - s * per_split;
       const int nt = rem % p.n_tiles;
@@ -255,7 +305,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       mbar_wait_parked(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int a_tap = p.a_tap[g][ja];
-      const int m = mt * p.m_out_stride + p.a_ch[g][ja] + (row & 63);
+      const int m = mt * p.m_out_stride + (p.tall ? group * 128 : 0) + p.a_ch[g][ja] + (row & 63);
       if (kb1 > kb0) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
         for (int ch = 0; ch < 2 * p.nb; ++ch) {
@@ -578,6 +628,20 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
     p.m_tiles = (pc + 127) / 128;
     p.a_tile_stride = 128;
     p.m_out_stride = 128;
+    {
+      // tall items (M = 256) wherever P has the channels for them and the K loop is long enough to amortise the
+      // un-overlapped drain of both accumulators (>= 24 k-blocks per item even after a split across the machine)
+      const char* e = getenv("JPDSE_WGRAD_TALL");  // "0": the M = 128 form everywhere (read per call: tests toggle it)
+      const int kb_all = B * p.nbh * p.nbw;
+      const int tall_items = p.n_groups * (pc / 256) * p.n_tiles;
+      const int tall_splits = tall_items >= num_sms() ? 1 : num_sms() / tall_items;
+      if (!(e && e[0] == '0') && pc % 256 == 0 && kb_all / (tall_splits > 0 ? tall_splits : 1) >= 24) {
+        p.tall = 1;
+        p.m_tiles = pc / 256;
+        p.a_tile_stride = 256;
+        p.m_out_stride = 256;
+      }
+    }
     for (int gi = 0; gi < p.n_groups; ++gi)
       for (int j = 0; j < 2; ++j) {
         const bool valid = pc >= 128 || j == 0;
@@ -594,7 +658,12 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
   const int per_split = p.n_groups * p.m_tiles * p.n_tiles;
   const int kb_total = B * p.nbh * p.nbw;
   int splits = 1;
-  if (per_split < num_sms()) {
+  if (p.tall) {
+    // never more items than SMs: a tall item has no second accumulator to hide its drain behind
+    splits = per_split >= num_sms() ? 1 : num_sms() / per_split;
+    if (splits > kb_total / 8) splits = kb_total / 8;
+    if (splits < 1) splits = 1;
+  } else if (per_split < num_sms()) {
     splits = (num_sms() + per_split - 1) / per_split;
     if (splits > kb_total / 8) splits = kb_total / 8;  // keep >= 8 k-blocks per item
     if (splits < 1) splits = 1;

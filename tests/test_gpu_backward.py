@@ -46,6 +46,8 @@ def _nhwc(t, pad=0, c_pad=None, mode="constant"):
     ("stem", 2, 8, 16, 40, 64), ("stem", 1, 64, 128, 40, 64), ("stem", 2, 70, 96, 40, 64),
     ("head", 2, 8, 16, 64, 3), ("head", 1, 64, 128, 64, 3), ("head", 2, 70, 100, 64, 3),
     ("conv3x3", 2, 6, 10, 64, 64), ("convs2", 2, 12, 40, 64, 128), ("convt", 1, 6, 10, 128, 64), ("conv3x3", 1, 9, 97, 128, 256),
+    # "tall" items (M = 256, both accumulators of one item): the ResnetBlock shape of a batch-2 step and split-K forms
+    ("conv3x3", 2, 32, 64, 1024, 1024), ("convs2", 2, 128, 256, 256, 512), ("convt", 2, 64, 128, 512, 256),
 ])
 def test_conv_wgrad(cuda, case):
     ops = _ops()
