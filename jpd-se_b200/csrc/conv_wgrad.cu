@@ -633,9 +633,9 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
       // un-overlapped drain of both accumulators (>= 24 k-blocks per item even after a split across the machine)
       const char* e = getenv("JPDSE_WGRAD_TALL");  // "0": the M = 128 form everywhere (read per call: tests toggle it)
       const int kb_all = B * p.nbh * p.nbw;
-      const int tall_items = p.n_groups * (pc / 256) * p.n_tiles;
-      const int tall_splits = tall_items >= num_sms() ? 1 : num_sms() / tall_items;
-      if (!(e && e[0] == '0') && pc % 256 == 0 && kb_all / (tall_splits > 0 ? tall_splits : 1) >= 24) {
+      const int tall_items = p.n_groups * (pc / 256) * p.n_tiles;  // 0 when P has fewer than 256 channels
+      const int tall_splits = (tall_items == 0 || tall_items >= num_sms()) ? 1 : num_sms() / tall_items;
+      if (!(e && e[0] == '0') && pc >= 256 && pc % 256 == 0 && kb_all / tall_splits >= 24) {
         p.tall = 1;
         p.m_tiles = pc / 256;
         p.a_tile_stride = 256;

@@ -387,7 +387,9 @@ class _DiscriminatorLossG(torch.autograd.Function):
                     L = plan.scales[i][j]
                     ops.l1_pair(s.feat[i][j][:h], s.feat[i][j][h:], acc[i * n_feat + j: i * n_feat + j + 1])
                     numel.append(float(h * L.cout * L.out_h * L.out_w))
-        w = torch.tensor([1.0 / (plan.num_D * n_) for n_ in numel], dtype=torch.float64, device=plan.device)
+        w = getattr(plan, '_fm_weights', None)  # per-plan constant: no host -> device copy inside the step
+        if w is None:
+            w = plan._fm_weights = torch.tensor([1.0 / (plan.num_D * n_) for n_ in numel], dtype=torch.float64, device=plan.device)
         ctx.numel = numel
         return loss_gan, (acc * w).sum().float()
 

@@ -103,18 +103,28 @@ class Pix2PixHDTrainer(BaseTrainer):
             ddp.allreduce_grads(self.model.netD.parameters())
             self.optimizer_D.step()
         else:
-            # Same two updates, other issue order: the discriminator's gradients depend on nothing the generator update
+            # Same two updates, other streams: the discriminator's gradients depend on nothing the generator update
             # touches (both losses come from ONE forward, and the fused route's loss_G.backward() deposits no netD
             # gradients to drop), so loss_D.backward() and the all-reduce of its 22 MB of gradients are enqueued FIRST, on
             # their own stream, and run beside the generator's backward + Adam; the discriminator's Adam step comes last.
+            # (JPDSE_D_BACKWARD_FIRST=0 issues the generator's backward first -- same streams, same results; measured
+            # 18.30 vs 18.17 ms per step, so the discriminator stays first.)
             main = torch.cuda.current_stream(loss_G.device)
-            self.optimizer_D.zero_grad()
             d_stream.wait_stream(main)
-            with torch.cuda.stream(d_stream):
-                loss_D.backward()
-                ddp.allreduce_grads(self.model.netD.parameters())
+            d_first = os.environ.get('JPDSE_D_BACKWARD_FIRST', '1') != '0'
+            self.optimizer_D.zero_grad()
+
+            def d_backward():
+                with torch.cuda.stream(d_stream):
+                    loss_D.backward()
+                    ddp.allreduce_grads(self.model.netD.parameters())
+
+            if d_first:
+                d_backward()
             self.optimizer_G.zero_grad()
             loss_G.backward()  # generator gradients come back already averaged over the ranks
+            if not d_first:
+                d_backward()
             self.optimizer_G.step()
             main.wait_stream(d_stream)
             self.optimizer_D.step()

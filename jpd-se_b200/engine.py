@@ -61,6 +61,7 @@ class GeneratorPlan:
         self.device = device
         self.training = training
         self.shared_border = os.environ.get("JPDSE_SHARED_BORDER", "1") != "0"  # ResnetBlock gradient layout (backward)
+        self.dgrad_first = os.environ.get("JPDSE_DGRAD_FIRST", "1") != "0"      # launch order of the two gradients of a conv
         self.c_in_pad = _round_up(input_nc, 8)
         B, H, W = batch, height, width
 
@@ -412,14 +413,21 @@ class GeneratorPlan:
             self._wgrad_ws = torch.empty((need + 3) // 4, dtype=torch.float32, device=dev)
         ws = self._wgrad_ws
 
-        def weight_grad(fn):
-            """Enqueue fn (wgrad + emit) behind everything the main stream has issued so far; returns the event the
-            main stream must wait on before it overwrites fn's inputs (None when not overlapping)."""
+        def mark():
+            """Event on the main stream: 'everything issued so far' (None when not overlapping)."""
             if side is None:
-                fn()
                 return None
             ev = torch.cuda.Event()
             ev.record(main)
+            return ev
+
+        def weight_grad(fn, ready=None):
+            """Enqueue fn (wgrad + emit) behind `ready` (default: everything the main stream has issued so far); returns
+            the event the main stream must wait on before it overwrites fn's inputs (None when not overlapping)."""
+            if side is None:
+                fn()
+                return None
+            ev = ready if ready is not None else mark()
             side.wait_event(ev)
             with torch.cuda.stream(side), ops.stream_cached():
                 fn()
@@ -483,13 +491,22 @@ class GeneratorPlan:
                 L.conv.wgrad(L.x_in, dx, z, dw, workspace=ws)
                 emit(L.name + ".weight", dw)
 
-            dx_free[slot] = weight_grad(layer_grad)
             if si == 0:
+                dx_free[slot] = weight_grad(layer_grad)
                 break  # the stem's input (labels + decoded image) needs no gradient
+            # Both gradients of this conv only wait for dx. The data gradient is LAUNCHED first: it is the one the chain
+            # waits for, and the weight gradient (75 registers, one CTA per SM) then shares the SMs with the next layer's
+            # InstanceNorm backward, which the data gradient (136 registers) cannot. Launched the other way round the
+            # weight gradient took the SMs first and sat on the critical path (profiles/r2_timeline_g_b2.txt).
+            ready = mark() if self.dgrad_first else None
+            if not self.dgrad_first:
+                dx_free[slot] = weight_grad(layer_grad)
             gi ^= 1
             oh, ow = L.dgrad.out_hw
             g = self._view(self.g_buf[gi], B, oh, ow, L.dgrad.cout)
             L.dgrad.forward(dx, g)
+            if self.dgrad_first:
+                dx_free[slot] = weight_grad(layer_grad, ready)
             if self.capture is not None:
                 self.capture[L.name]["g_in"] = g.clone()  # gradient w.r.t. this layer's input as the conv saw it
             if self.binarizer is not None and L.x_in is self.codes_nhwc:

@@ -598,4 +598,16 @@ def distortion_u8(a, b, mode="l1", mean=(0.5, 0.5, 0.5), std=(1.0, 1.0, 1.0)):
                                   _dvec(std, C), _stream()))
     _count(2)
     # tensor / tensor: a true IEEE division (torch turns tensor / python-scalar into a multiply by the reciprocal)
-    return acc[0].double() / torch.tensor(float(a.numel()), dtype=torch.float64, device=a.device)
+    return acc[0].double() / _const_f64(float(a.numel()), a.device)
+
+
+_const_cache = {}
+
+
+def _const_f64(value, device):
+    """0-dim float64 device constant, built once per (value, device): torch.tensor(..., device=cuda) blocks the host."""
+    key = (value, str(device))
+    t = _const_cache.get(key)
+    if t is None:
+        t = _const_cache[key] = torch.tensor(value, dtype=torch.float64, device=device)
+    return t
