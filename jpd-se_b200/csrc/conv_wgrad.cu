@@ -354,18 +354,37 @@ struct WgFinalize {
 
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ ws, float* __restrict__ dw, WgFinalize f) {
   if (f.mode == 0) {
-    // one thread per (m, n): coalesced reads along n in every tap plane, `taps` consecutive floats written
+    // a block owns 256 consecutive (m, n) pairs: coalesced reads along n in every tap plane, a transpose through shared
+    // memory (row pitch `taps` is odd or 16: 9 is conflict-free), then the block's 256 * taps output floats -- one
+    // contiguous run of dw -- leave as float4 rows (scalar 36-byte-strided stores ran this kernel at half the HBM rate)
+    __shared__ __align__(16) float s_t[256 * 16];
     const size_t mn_total = static_cast<size_t>(f.m_real) * f.n_real;
     const size_t plane = static_cast<size_t>(f.m_tot) * f.n_tot;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < mn_total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-      const int n = static_cast<int>(i % f.n_real), m = static_cast<int>(i / f.n_real);
-      const float* src = ws + static_cast<size_t>(m) * f.n_tot + n;
-      float* dst = dw + i * f.taps;
-      for (int t = 0; t < f.taps; ++t) {
-        const float v = src[t * plane];
-        dst[t] = f.accumulate ? dst[t] + v : v;
+    const int taps = f.taps;
+    for (size_t i0 = static_cast<size_t>(blockIdx.x) * 256; i0 < mn_total; i0 += static_cast<size_t>(gridDim.x) * 256) {
+      const size_t i = i0 + threadIdx.x;
+      if (i < mn_total) {
+        const int n = static_cast<int>(i % f.n_real), m = static_cast<int>(i / f.n_real);
+        const float* src = ws + static_cast<size_t>(m) * f.n_tot + n;
+        for (int t = 0; t < taps; ++t) s_t[threadIdx.x * taps + t] = src[t * plane];
       }
+      __syncthreads();
+      const size_t left = mn_total - i0;
+      const int count = static_cast<int>(left < 256 ? left : 256) * taps;  // floats of this block's run
+      float* dst = dw + i0 * taps;  // i0 * taps * 4 bytes is a multiple of 1024
+      if ((count & 3) == 0) {
+        for (int j = threadIdx.x * 4; j < count; j += 256 * 4) {
+          float4 v = *reinterpret_cast<const float4*>(s_t + j);
+          if (f.accumulate) {
+            const float4 o = *reinterpret_cast<const float4*>(dst + j);
+            v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+          }
+          *reinterpret_cast<float4*>(dst + j) = v;
+        }
+      } else {
+        for (int j = threadIdx.x; j < count; j += 256) dst[j] = f.accumulate ? dst[j] + s_t[j] : s_t[j];
+      }
+      __syncthreads();
     }
     return;
   }
@@ -723,6 +742,8 @@ extern "C" int jpdse_conv_wgrad(const jpdse_conv_desc* d, const void* x, const v
   rc = check_launch("wgrad_kernel");
   if (rc != JPDSE_OK) return rc;
   w.f.accumulate = accumulate ? 1 : 0;
+  if (w.f.mode == 0 && w.f.taps > 16) return fail(JPDSE_ERR_UNSUPPORTED, "conv_wgrad: finalize stages at most 16 taps");
+  if (w.f.mode == 0 && (reinterpret_cast<uintptr_t>(dw) & 15)) return fail(JPDSE_ERR_INVALID, "conv_wgrad: dw must be 16-byte aligned");
   const size_t total = static_cast<size_t>(w.f.m_real) * w.f.n_real * (w.f.mode == 0 ? 1 : 49);
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > num_sms() * 16) blocks = num_sms() * 16;
