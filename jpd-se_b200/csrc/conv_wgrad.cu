@@ -676,14 +676,11 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
   // split K so that the launch fills the machine
   const int per_split = p.n_groups * p.m_tiles * p.n_tiles;
   const int kb_total = B * p.nbh * p.nbw;
+  // Never more items than SMs (rounded DOWN): 8 items per split and 19 splits were 152 items -- a second wave of four
+  // items as long as the first (the 7x7 stem: 762 us, the longest kernel of the backward pass); 18 splits are one wave.
   int splits = 1;
-  if (p.tall) {
-    // never more items than SMs: a tall item has no second accumulator to hide its drain behind
-    splits = per_split >= num_sms() ? 1 : num_sms() / per_split;
-    if (splits > kb_total / 8) splits = kb_total / 8;
-    if (splits < 1) splits = 1;
-  } else if (per_split < num_sms()) {
-    splits = (num_sms() + per_split - 1) / per_split;
+  if (per_split < num_sms()) {
+    splits = num_sms() / per_split;
     if (splits > kb_total / 8) splits = kb_total / 8;  // keep >= 8 k-blocks per item
     if (splits < 1) splits = 1;
   }
