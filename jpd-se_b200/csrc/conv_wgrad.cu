@@ -64,13 +64,13 @@ struct WgParams {
   int a_tile_stride, b_tile_stride;      // TMA channel-coordinate step per m / n tile
   int m_out_stride, n_out_stride;        // workspace row / column step per m / n tile
   WgView a, b;
-  int a_off[kWgMaxGroups][2][5];
+  int a_off[kWgMaxGroups][4][5];   // boxes 2, 3: tall items only
   int b_off[kWgMaxGroups][4][5];
-  short a_tap[kWgMaxGroups][2], b_tap[kWgMaxGroups][4];  // output tap contribution, < 0 = box unused
-  short a_ch[kWgMaxGroups][2], b_ch[kWgMaxGroups][4];    // workspace row / column offset of the box
+  short a_tap[kWgMaxGroups][4], b_tap[kWgMaxGroups][4];  // output tap contribution, < 0 = box unused
+  short a_ch[kWgMaxGroups][4], b_ch[kWgMaxGroups][4];    // workspace row / column offset of the box
   int m_tot, n_tot;      // workspace extents: ws[tap][m_tot][n_tot]
   int direct;            // 1: no split-K -> every workspace element has exactly one writer: plain stores, no memset
-  int tall;              // 1: M = 256 per item (m tiles of 256 P channels; A boxes 2, 3 = boxes 0, 1 + 128 channels)
+  int tall;              // 1: M = 256 per item = four A boxes (generic: 256 P channels; stem: four filter rows)
   float* ws;
 };
 
@@ -160,9 +160,9 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
         const int kb0 = static_cast<int>(static_cast<long long>(kb_total) * s / p.splits);
         const int kb1 = static_cast<int>(static_cast<long long>(kb_total) * (s + 1) / p.splits);
         // per-item box coordinates in registers
-        int ao[2][5], bo[4][5];
+        int ao[4][5], bo[4][5];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < 4; ++j) {
 #pragma unroll
           for (int q = 0; q < 5; ++q) ao[j][q] = p.a_off[g][j][q];
           ao[j][0] += mt * p.a_tile_stride;
@@ -190,7 +190,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           if (p.tall) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              wg_load_box(&tm_a, p.a.rank, &full_bar[stage], st + (2 + j) * kWgBox, ao[j][0] + 128, ao[j][1], ao[j][2], ao[j][3], ao[j][4], pw, ph, b);
+              wg_load_box(&tm_a, p.a.rank, &full_bar[stage], st + (2 + j) * kWgBox, ao[2 + j][0], ao[2 + j][1], ao[2 + j][2], ao[2 + j][3], ao[2 + j][4], pw, ph, b);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -288,7 +288,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
     const int group = warp >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int ja = row >> 6;
+    const int ja = (row >> 6) + (p.tall ? 2 * group : 0);  // tall items: group g drains A boxes 2g, 2g + 1
     const int acc = group;
     uint32_t acc_phase = 0;
     int item_i = 0;
@@ -305,7 +305,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       mbar_wait_parked(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int a_tap = p.a_tap[g][ja];
-      const int m = mt * p.m_out_stride + (p.tall ? group * 128 : 0) + p.a_ch[g][ja] + (row & 63);
+      const int m = mt * p.m_out_stride + p.a_ch[g][ja] + (row & 63);
       if (kb1 > kb0) {
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * 256);
         for (int ch = 0; ch < 2 * p.nb; ++ch) {
@@ -502,15 +502,19 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
     w->b_box[0] = 64; w->b_box[1] = p.kw_cols; w->b_box[2] = p.kh_rows; w->b_box[3] = 1;
     w->b_base_off = 0;
     p.b = WgView{4, 1, 2, 3};
-    p.n_groups = 4;
+    // four filter rows per item (tall: 7 boxes feed 8 MMAs) unless switched off: two rows per item, 5 boxes per 4 MMAs
+    const char* e_tall = getenv("JPDSE_WGRAD_TALL");
+    p.tall = (e_tall && e_tall[0] == '0') ? 0 : 1;
+    const int rows_per_item = p.tall ? 4 : 2;
+    p.n_groups = p.tall ? 2 : 4;
     p.m_tiles = 1;
     p.n_tiles = 2;
     p.nb = 3;
     p.b_tile_stride = 192;
     p.n_out_stride = 192;
-    for (int gi = 0; gi < 4; ++gi) {
-      for (int j = 0; j < 2; ++j) {
-        const int kh = 2 * gi + j;
+    for (int gi = 0; gi < p.n_groups; ++gi) {
+      for (int j = 0; j < rows_per_item; ++j) {
+        const int kh = rows_per_item * gi + j;
         p.a_off[gi][j][2] = -(kh < 7 ? kh : 0);
         p.a_tap[gi][j] = kh < 7 ? kh : -1;
         p.a_ch[gi][j] = 0;
@@ -662,8 +666,8 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
       }
     }
     for (int gi = 0; gi < p.n_groups; ++gi)
-      for (int j = 0; j < 2; ++j) {
-        const bool valid = pc >= 128 || j == 0;
+      for (int j = 0; j < 4; ++j) {
+        const bool valid = j < 2 ? (pc >= 128 || j == 0) : p.tall != 0;
         p.a_off[gi][j][0] = valid ? 64 * j : 0;
         p.a_tap[gi][j] = valid ? 0 : -1;
         p.a_ch[gi][j] = static_cast<short>(64 * j);
