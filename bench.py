@@ -267,7 +267,8 @@ def train_measure(args, dev, local, rank, world, barrier):
             "trainer_step_ms": step_ms, "trainer_step_images_per_s": world * B / (step_ms * 1e-3),
             "allreduce": "none (1 GPU)" if world == 1 else "730 MB fp32 generator gradients, bucketed, overlapped with backward (NCCL)",
             "vgg_weights": "random (JPDSE_VGG_RANDOM=1: the pretrained checkpoint is not available offline; same FLOPs)",
-            "note": "generator forward/backward = jpdse_b200 kernels; netD, VGG, losses, Adam = PyTorch"}
+            "note": "generator, PatchGAN discriminator (GAN + feature-matching losses) and VGG19 loss forward/backward = jpdse_b200 "
+                    "kernels; Adam (torch.optim, fused) and the scalar loss arithmetic = PyTorch"}
 
 
 def cudnn_measure(B, H, W, dev):
