@@ -180,30 +180,29 @@ build_input_nchw_kernel(const void* __restrict__ label, int label_dtype, const v
 // of the 156 B of the reference's float32 (B,39,H,W) tensor. One thread per OUTPUT pixel builds the c_pad channels
 // (8 x 16-byte stores); the one-hot / edge channels are shared by two images (fake and real): both outputs are written in
 // one pass. The pooled one-hot is count / taps and the pooled image sum / taps in the tap order of ATen's kernel.
-__global__ void __launch_bounds__(256)
+constexpr int kDIdsPixels = 128;  // output pixels (of one row) per block
+constexpr int kDIdsMaxVec = 8;    // c_pad <= 64
+
+__global__ void __launch_bounds__(kDIdsPixels)
 d_input_ids_kernel(const void* __restrict__ label, int label_dtype, const void* __restrict__ inst, int inst_dtype,
                    const float* __restrict__ img_a, __nv_bfloat16* __restrict__ out_a, const float* __restrict__ img_b,
                    __nv_bfloat16* __restrict__ out_b, int B, int H, int W, int Ho, int Wo, int L, int c_pad, int pool, int out_pad) {
-  // thread = (output pixel, 8-channel vector): the c_pad / 8 threads of a pixel write one contiguous run of c_pad * 2
-  // bytes per image, so a warp's store is whole 128-byte lines (one thread per pixel wrote 16 bytes at a 128-byte stride:
-  // 1.4 TB/s). The ids under the pooling window are re-read by the threads of the pixel (L1 broadcast); only the vectors
-  // holding the edge / image channels load those.
+  // One thread per output pixel builds its c_pad channels (for both images) as rows of shared memory; the block then
+  // writes its 128 pixels -- one contiguous run of 128 * c_pad * 2 bytes per image -- with coalesced 16-byte stores, like
+  // build_input_nhwc_kernel. (Per-thread global stores of 16 bytes at a 128-byte stride ran at 1.4 TB/s; a thread per
+  // (pixel, vector) without the staging at 0.8 TB/s.) grid = (row pieces, output rows, images).
+  __shared__ uint4 s_a[kDIdsPixels * (kDIdsMaxVec + 1)];
+  __shared__ uint4 s_b[kDIdsPixels * (kDIdsMaxVec + 1)];
+  (void)B;
   const int vpp = c_pad >> 3;
+  const int pitch = vpp + 1;  // odd pitch in 16-byte units: conflict-free row writes
   const size_t plane = static_cast<size_t>(H) * W;
-  const size_t oplane = static_cast<size_t>(Ho) * Wo;
-  const size_t total = static_cast<size_t>(B) * oplane * vpp;
   const int Wst = Wo + 2 * out_pad;
   const size_t ost = static_cast<size_t>(Ho + 2 * out_pad) * Wst;
-  for (size_t idx = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(idx % vpp);
-    const size_t op = idx / vpp;
-    const int b = static_cast<int>(op / oplane);
-    const size_t ohw = op % oplane;
-    const int oy = static_cast<int>(ohw / Wo), ox = static_cast<int>(ohw % Wo);
-    const int c0 = 8 * k;
-    const bool has_labels = c0 < L;                       // one-hot channels in this vector
-    const bool has_rest = c0 + 8 > L && c0 < L + 4;       // edge / image channels in this vector
+  const int oy = blockIdx.y, b = blockIdx.z;
+  const int ox0 = blockIdx.x * kDIdsPixels;
+  const int ox = ox0 + threadIdx.x;
+  if (ox < Wo) {
     int labs[9];
     float edge = 0.f, ia[3] = {0.f, 0.f, 0.f}, ib[3] = {0.f, 0.f, 0.f};
     int cnt = 0;
@@ -212,14 +211,12 @@ d_input_ids_kernel(const void* __restrict__ label, int label_dtype, const void* 
     const size_t ibase = static_cast<size_t>(b) * 3 * plane;
     if (!pool) {
       const size_t hw = static_cast<size_t>(oy) * W + ox;
-      if (has_labels) labs[0] = load_label(label, label_dtype, static_cast<size_t>(b) * plane + hw, L);
-      if (has_rest) {
-        edge = load_edge(inst, inst_dtype, static_cast<size_t>(b) * plane, oy, ox, H, W) ? 1.f : 0.f;
+      labs[0] = load_label(label, label_dtype, static_cast<size_t>(b) * plane + hw, L);
+      edge = load_edge(inst, inst_dtype, static_cast<size_t>(b) * plane, oy, ox, H, W) ? 1.f : 0.f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          ia[c] = __ldg(img_a + ibase + c * plane + hw);
-          if (img_b != nullptr) ib[c] = __ldg(img_b + ibase + c * plane + hw);
-        }
+      for (int c = 0; c < 3; ++c) {
+        ia[c] = __ldg(img_a + ibase + c * plane + hw);
+        if (img_b != nullptr) ib[c] = __ldg(img_b + ibase + c * plane + hw);
       }
       cnt = 1;
     } else {
@@ -232,14 +229,12 @@ d_input_ids_kernel(const void* __restrict__ label, int label_dtype, const void* 
           const int x = 2 * ox + dx;
           if (x < 0 || x >= W) continue;
           const size_t hw = static_cast<size_t>(y) * W + x;
-          if (has_labels) labs[(dy + 1) * 3 + dx + 1] = load_label(label, label_dtype, static_cast<size_t>(b) * plane + hw, L);
-          if (has_rest) {
-            edge += load_edge(inst, inst_dtype, static_cast<size_t>(b) * plane, y, x, H, W) ? 1.f : 0.f;
+          labs[(dy + 1) * 3 + dx + 1] = load_label(label, label_dtype, static_cast<size_t>(b) * plane + hw, L);
+          edge += load_edge(inst, inst_dtype, static_cast<size_t>(b) * plane, y, x, H, W) ? 1.f : 0.f;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              ia[c] += __ldg(img_a + ibase + c * plane + hw);
-              if (img_b != nullptr) ib[c] += __ldg(img_b + ibase + c * plane + hw);
-            }
+          for (int c = 0; c < 3; ++c) {
+            ia[c] += __ldg(img_a + ibase + c * plane + hw);
+            if (img_b != nullptr) ib[c] += __ldg(img_b + ibase + c * plane + hw);
           }
           ++cnt;
         }
@@ -252,33 +247,47 @@ d_input_ids_kernel(const void* __restrict__ label, int label_dtype, const void* 
       ia[c] = ia[c] / fc;
       ib[c] = ib[c] / fc;
     }
-    float va[8], vb[8];
-    bool differs = false;
+    for (int k = 0; k < vpp; ++k) {
+      float va[8], vb[8];
+      bool differs = false;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = c0 + j;
-      float v = 0.f, w2 = 0.f;
-      if (c < L) {
-        int n = 0;
+      for (int j = 0; j < 8; ++j) {
+        const int c = 8 * k + j;
+        float v = 0.f, w2 = 0.f;
+        if (c < L) {
+          if (!pool) {
+            v = w2 = (labs[0] == c) ? 1.f : 0.f;
+          } else {
+            int n = 0;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) n += (labs[t] == c) ? 1 : 0;
-        v = w2 = static_cast<float>(n) / fc;
-      } else if (c == L) {
-        v = w2 = edge;
-      } else if (c < L + 4) {
-        v = ia[c - L - 1];
-        w2 = ib[c - L - 1];
-        differs = true;
+            for (int t = 0; t < 9; ++t) n += (labs[t] == c) ? 1 : 0;
+            v = w2 = n ? static_cast<float>(n) / fc : 0.f;  // at most 9 of the L channels take the division
+          }
+        } else if (c == L) {
+          v = w2 = edge;
+        } else if (c < L + 4) {
+          v = ia[c - L - 1];
+          w2 = ib[c - L - 1];
+          differs = true;
+        }
+        va[j] = v;
+        vb[j] = w2;
       }
-      va[j] = v;
-      vb[j] = w2;
-    }
-    const size_t o = (static_cast<size_t>(b) * ost + static_cast<size_t>(oy + out_pad) * Wst + ox + out_pad) * c_pad + c0;
-    const uint4 pa = make_uint4(pack_bf16x2(va[0], va[1]), pack_bf16x2(va[2], va[3]), pack_bf16x2(va[4], va[5]), pack_bf16x2(va[6], va[7]));
-    *reinterpret_cast<uint4*>(out_a + o) = pa;
-    if (out_b != nullptr)
-      *reinterpret_cast<uint4*>(out_b + o) =
+      const uint4 pa = make_uint4(pack_bf16x2(va[0], va[1]), pack_bf16x2(va[2], va[3]), pack_bf16x2(va[4], va[5]), pack_bf16x2(va[6], va[7]));
+      s_a[threadIdx.x * pitch + k] = pa;
+      s_b[threadIdx.x * pitch + k] =
           differs ? make_uint4(pack_bf16x2(vb[0], vb[1]), pack_bf16x2(vb[2], vb[3]), pack_bf16x2(vb[4], vb[5]), pack_bf16x2(vb[6], vb[7])) : pa;
+    }
+  }
+  __syncthreads();
+  const int npx = Wo - ox0 < kDIdsPixels ? Wo - ox0 : kDIdsPixels;
+  const size_t o = (static_cast<size_t>(b) * ost + static_cast<size_t>(oy + out_pad) * Wst + ox0 + out_pad) * c_pad;
+  uint4* da = reinterpret_cast<uint4*>(out_a + o);
+  uint4* db = out_b != nullptr ? reinterpret_cast<uint4*>(out_b + o) : nullptr;
+  for (int i = threadIdx.x; i < npx * vpp; i += kDIdsPixels) {
+    const int px = i / vpp, k = i - px * vpp;
+    da[i] = s_a[px * pitch + k];
+    if (db != nullptr) db[i] = s_b[px * pitch + k];
   }
 }
 
@@ -931,11 +940,10 @@ extern "C" int jpdse_d_input_ids(const void* label, int label_dtype, const void*
   if ((reinterpret_cast<uintptr_t>(out_a) | reinterpret_cast<uintptr_t>(out_b)) & 15)
     return fail(JPDSE_ERR_INVALID, "d_input_ids: outputs must be 16-byte aligned");
   const int Ho = pool ? (height - 1) / 2 + 1 : height, Wo = pool ? (width - 1) / 2 + 1 : width;
-  const size_t total = static_cast<size_t>(batch) * Ho * Wo * (c_pad / 8);
-  size_t blocks = (total + 255) / 256;
-  const size_t cap = static_cast<size_t>(num_sms()) * 32;
-  if (blocks > cap) blocks = cap;
-  d_input_ids_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  if (Ho > 65535 || batch > 65535) return fail(JPDSE_ERR_UNSUPPORTED, "d_input_ids: more than 65535 rows / images");
+  if (c_pad > 8 * kDIdsMaxVec) return fail(JPDSE_ERR_UNSUPPORTED, "d_input_ids: c_pad > %d", 8 * kDIdsMaxVec);
+  const dim3 blocks((Wo + kDIdsPixels - 1) / kDIdsPixels, Ho, batch);
+  d_input_ids_kernel<<<blocks, kDIdsPixels, 0, static_cast<cudaStream_t>(stream)>>>(
       label, label_dtype, instance, inst_dtype, image_a, static_cast<__nv_bfloat16*>(out_a), image_b,
       static_cast<__nv_bfloat16*>(out_b), batch, height, width, Ho, Wo, num_labels, c_pad, pool ? 1 : 0, out_pad);
   return check_launch("d_input_ids_kernel");
