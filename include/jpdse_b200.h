@@ -29,7 +29,7 @@ extern "C" {
 #define JPDSE_ERR_CUDA (-2)
 #define JPDSE_ERR_UNSUPPORTED (-3)
 
-/* ABI version of this header; bumped on any signature change. */
+/* ABI version of this header (3); bumped on any signature, enum or layout-flag change. */
 int jpdse_abi_version(void);
 /* Message of the last error on this thread ("" if none). Never NULL. */
 const char* jpdse_last_error(void);
