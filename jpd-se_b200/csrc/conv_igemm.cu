@@ -51,6 +51,25 @@ constexpr int kNumProducers = 1;
 constexpr int kMmaWarp = kProducerWarp + kNumProducers;
 static_assert(kThreads == 32 * (kMmaWarp + 1), "warp roles and block size out of step");
 
+// Row mode (igemm_kernel<64, 1> / <64, 0>; the VGG19's 64 -> 64 conv at full resolution and the data gradients of its
+// first block). The generic K loop fetches one 128-pixel A box AND one weight box per filter tap: 9 x (16 + 8) KB = 216 KB
+// per 128 x 64 output tile against 1152 tensor-pipe cycles -- 4900 cycles on the L2 -> SM fabric, 0.46 PFLOP/s. Here
+//   * the nine 64 x 64 weight tiles (72 KB) are loaded ONCE per CTA and stay in shared memory;
+//   * a k-block is a FILTER ROW: one box of 128 + 2 pixels, and the three kw taps are three MMAs whose A descriptors
+//     start 0 / 1 / 2 pixel rows (128 bytes) into it (a SWIZZLE_128B operand may start at any 128-byte row with
+//     base_offset 0: tools/umma_shift_test.cu) -- for the flat data-gradient kinds positions are contiguous, so the same
+//     shift works there;
+// i.e. 3 x 16.25 KB = 49 KB per tile. The ring holds four 17 KB stages behind the weights; the output staging and the
+// barriers keep their places (72 KB + 4 x 17 KB <= 6 x 24 KB). full_bar[kRowWBar] (a stage index the ring does not use)
+// is the weights' barrier.
+constexpr int kRowStages = 4;
+constexpr int kRowWBytes = 9 * 64 * kBlockK * 2;         // 73,728
+constexpr int kRowABox = (kTileM + 2) * kBlockK * 2;     // 16,640: what one A box brings
+constexpr int kRowAStage = 17 * 1024;                    // 1024-aligned stage pitch
+constexpr int kRowWBar = 4;
+static_assert(kRowWBytes + kRowStages * kRowAStage <= 6 * (kABytes + 64 * kBlockK * 2), "row mode must fit the BN = 64 stage area");
+static_assert(kRowABox <= kRowAStage && kRowWBytes % 1024 == 0, "row-mode stage layout");
+
 struct IgemmParams {
   // tile grid
   int batch, tiles_h, tiles_w, n_tiles;
@@ -77,6 +96,7 @@ struct IgemmParams {
   int check_out;   // 1: rows whose output coordinate falls outside out_h x out_w are neither stored nor counted
                    //    (data gradient of the 4x4 stride-2 conv onto an odd-sized input)
   float slope;     // JPDSE_EPI_BIAS_ACT: LeakyReLU negative slope (0 = ReLU)
+  int rowmode;     // 1 (BN = 64, 64 input channels, 3x3 stride 1): row-stationary K loop -- see kRow* below
   void* out;
   double* stats;
   const float* bias;
@@ -170,6 +190,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       uint32_t it = 0;  // global k-block counter: stage = it % kStages, phase = (it / kStages) & 1
       long long dbg_prod = 0;
       const long long dbg_t0 = p.dbg ? clock64() : 0;
+      const bool row = BN == 64 && p.rowmode;
+      const uint32_t n_stages = row ? kRowStages : Cfg::kStages;
+      if (row && my == 0 && blockIdx.x < total_tiles) {
+        // resident weights: nine {64 k, 64 n} boxes, tap-major as the packed matrix has them
+        mbar_arrive_expect_tx(&full_bar[kRowWBar], kRowWBytes);
+        for (int t = 0; t < 9; ++t) tma_load_2d(&tm_b, &full_bar[kRowWBar], smem + t * (64 * kBlockK * 2), t * kBlockK, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles;
         int mt = tile / p.n_tiles;
@@ -200,14 +227,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           const int c0t = p.tap_off[t][0];
           for (int ch = 0; ch < p.chunks_per_tap; ++ch, ++kb, ++it) {
             if ((it % kNumProducers) != my) continue;
-            const uint32_t stage = it % Cfg::kStages;
-            const uint32_t phase = (it / Cfg::kStages) & 1u;
+            const uint32_t stage = it % n_stages;
+            const uint32_t phase = (it / n_stages) & 1u;
             const long long tw0 = p.dbg ? clock64() : 0;
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (p.dbg) dbg_prod += clock64() - tw0;
-            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sa = row ? smem + kRowWBytes + stage * kRowAStage : smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + kABytes;
-            mbar_arrive_expect_tx(&full_bar[stage], (p.dbg_flags & 32) ? kABytes : Cfg::kStageBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], row ? kRowABox : ((p.dbg_flags & 32) ? kABytes : Cfg::kStageBytes));
             const int c0 = c0t + ch * kBlockK;
             if (p.a_rank == 3)
               tma_load_3d(&tm_a, &full_bar[stage], sa, c0, c1, c2);
@@ -215,7 +242,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
               tma_load_4d(&tm_a, &full_bar[stage], sa, c0, c1, c2, c3);
             else
               tma_load_5d(&tm_a, &full_bar[stage], sa, c0, c1, c2, c3, c4);
-            if (!(p.dbg_flags & 32)) tma_load_2d(&tm_b, &full_bar[stage], sb, p.b_k_offset + kb * kBlockK, nt * BN);
+            if (!row && !(p.dbg_flags & 32)) tma_load_2d(&tm_b, &full_bar[stage], sb, p.b_k_offset + kb * kBlockK, nt * BN);
           }
         }
       }
@@ -235,6 +262,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
       uint32_t acc_phase = 0;
       long long dbg_full = 0, dbg_tempty = 0;
       const long long dbg_t0 = p.dbg ? clock64() : 0;
+      const bool row = BN == 64 && p.rowmode;
+      const int n_stages = row ? kRowStages : Cfg::kStages;
+      if (row && blockIdx.x < total_tiles) {
+        mbar_wait(&full_bar[kRowWBar], 0);  // the resident weights have landed
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const long long tw0 = p.dbg ? clock64() : 0;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -246,6 +279,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ C
           mbar_wait(&full_bar[stage], phase);
           if (p.dbg) dbg_full += clock64() - tw1;
           tc_fence_after();
+          if (row) {
+            // k-block = filter row kb: A = the 130-pixel box, shifted by kw pixel rows; B = resident tile (kb, kw)
+            const uint32_t sa = smem_u32(smem + kRowWBytes + stage * kRowAStage);
+            const uint32_t sw = smem_u32(smem) + static_cast<uint32_t>(kb * 3) * (64 * kBlockK * 2);
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+              const uint64_t adesc = umma_smem_desc_sw128(sa + kw * 128);
+              const uint64_t bdesc = umma_smem_desc_sw128(sw + kw * (64 * kBlockK * 2));
+#pragma unroll
+              for (int k = 0; k < kBlockK / kUmmaK; ++k)
+                umma_bf16<1>(d_tmem, adesc + static_cast<uint64_t>(k * 2), bdesc + static_cast<uint64_t>(k * 2), idesc,
+                             (kb | kw | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
+            if (++stage == n_stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t adesc = umma_smem_desc_sw128(sa);
           const uint64_t bdesc = umma_smem_desc_sw128(sa + kABytes);
@@ -1060,6 +1114,15 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   }
   p.n_tiles = g.rows / g.bn;
   p.chunks_per_tap = g.cpt;
+  {
+    // row mode (resident weights, one 130-pixel box per filter row; see kRow* above): 64 -> 64 channel 3x3 stride-1 convs
+    // whose tile is one 128-pixel piece of a row (PAD1) or of the flat position run (the data-gradient kinds)
+    const char* e = getenv("JPDSE_ROW_MODE");  // "0": the generic tap-by-tap K loop (read per call: tests toggle it)
+    const bool on = !(e != nullptr && e[0] == '0');
+    const bool shape = g.bn == 64 && g.rows == 64 && d->cin == 64 && g.cpt == 1 && g.ktot == 9 * 64;
+    const bool tiles = (d->kind == JPDSE_CONV3X3_PAD1 && p.tile_h == 1 && p.tile_w == 128) || d->kind == JPDSE_CONV3X3_FULL || shared;
+    p.rowmode = (on && shape && tiles) ? 1 : 0;
+  }
   p.out_h = shared ? d->batch * g.out_h : g.out_h;
   p.out_w = g.out_w;
   p.os_h = p.os_w = 1;
@@ -1217,10 +1280,20 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       strides[1] = dims[1] * C * 2;
       p.ntaps = 9;
       for (int t = 0; t < 9; ++t) p.tap_off[t][1] = (t / 3) * static_cast<int>(P) + (t % 3);
+      if (p.rowmode) {
+        p.ntaps = 3;
+        box[1] = 130;
+        for (int t = 0; t < 3; ++t) p.tap_off[t][1] = t * static_cast<int>(P);
+      }
     } else if (d->kind == JPDSE_CONV3X3_FULL) {
       dims[0] = C;
       p.ntaps = 9;
       for (int t = 0; t < 9; ++t) p.tap_off[t][1] = (t / 3) * static_cast<int>(Wp) + (t % 3);
+      if (p.rowmode) {
+        p.ntaps = 3;
+        box[1] = 130;
+        for (int t = 0; t < 3; ++t) p.tap_off[t][1] = t * static_cast<int>(Wp);
+      }
     } else if (d->kind == JPDSE_CONV4X4_S1_FULL) {
       // dx[y, x] = sum_{kh', kw'} dy_padded[y + 1 + kh', x + 1 + kw'] * W[3-kh'][3-kw'] (dy stored with a zero border of 2)
       dims[0] = C;
@@ -1243,6 +1316,14 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       for (int t = 0; t < 9; ++t) {
         p.tap_off[t][1] = t % 3;
         p.tap_off[t][2] = t / 3;
+      }
+      if (p.rowmode) {
+        p.ntaps = 3;
+        box[1] = 130;  // the tile's 128 pixels + the two neighbours the kw = 1, 2 taps reach
+        for (int t = 0; t < 3; ++t) {
+          p.tap_off[t][1] = 0;
+          p.tap_off[t][2] = t;
+        }
       }
       break;
     }

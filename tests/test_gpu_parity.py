@@ -734,3 +734,70 @@ def test_second_device_in_the_same_process(cuda):
             import copy
             outs.append(copy.deepcopy(net).to("cuda:%d" % dev)(x.to("cuda:%d" % dev)).cpu())
     assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("kind_name,B,H,W", [("pad1", 2, 6, 256), ("pad1", 1, 3, 200), ("pad1_act", 2, 5, 128), ("pad1_act", 1, 4, 330),
+                                             ("full", 2, 8, 16), ("full", 1, 20, 300), ("full_shared", 2, 12, 40),
+                                             ("full_shared", 3, 9, 130)])
+def test_row_mode_equals_tap_by_tap(cuda, monkeypatch, kind_name, B, H, W):
+    """Row mode of the implicit-GEMM kernel (64 -> 64 channels: weights resident in shared memory, one 130-pixel A box per
+    filter row, the kw taps as shifted descriptors -- the VGG19's first block) against the generic tap-by-tap K loop
+    (JPDSE_ROW_MODE=0): the same MMAs in the same order, so the outputs are BIT-IDENTICAL; and against torch."""
+    ops = _ops()
+    from jpdse_b200._lib import (CONV3X3_FULL, CONV3X3_FULL_SHARED, CONV3X3_PAD1, EPI_BIAS_ACT, EPI_RAW, EPI_RAW_STATS)
+    g = torch.Generator().manual_seed(B * 100 + W)
+    w = _bf(torch.randn(64, 64, 3, 3, generator=g) * 0.05)
+    bias = torch.randn(64, generator=g) * 0.1
+
+    def run():
+        if kind_name.startswith("pad1"):
+            act = kind_name == "pad1_act"
+            x = _bf(torch.randn(B, 64, H + 2, W + 2, generator=torch.Generator().manual_seed(5)))
+            xd = torch.zeros(B * (H + 2) * (W + 2) * 64 + 4096, dtype=torch.bfloat16, device=cuda)
+            xd[: x.numel()] = x.permute(0, 2, 3, 1).reshape(-1).to(cuda)
+            xd = xd[: x.numel()].view(B, H + 2, W + 2, 64)
+            if act:
+                cv = ops.Conv(CONV3X3_PAD1, EPI_BIAS_ACT, B, H, W, 1, 64, 64, 64, cuda, out_pad=1, slope=0.0)
+                cv.pack(w.to(cuda), bias.to(cuda))
+                y = torch.zeros(B, H + 2, W + 2, 64, dtype=torch.bfloat16, device=cuda)
+                cv.forward(xd, y)
+                ref = F.relu(F.conv2d(x, w, bias))
+                got = y[:, 1:-1, 1:-1]
+            else:
+                cv = ops.Conv(CONV3X3_PAD1, EPI_RAW_STATS, B, H, W, 1, 64, 64, 64, cuda)
+                cv.pack(w.to(cuda))
+                y = torch.full((B, H, W, 64), float("nan"), dtype=torch.bfloat16, device=cuda)
+                st = torch.zeros(B, 64, 2, dtype=torch.float64, device=cuda)
+                cv.forward(xd, y, st)
+                ref = F.conv2d(x, w)
+                got = y
+            torch.cuda.synchronize()
+            return y.clone(), got.float().cpu().permute(0, 3, 1, 2), ref
+        dy = _bf(torch.randn(B, 64, H, W, generator=torch.Generator().manual_seed(6)))
+        xp = torch.zeros(B, 64, H + 2, W + 2, requires_grad=True)
+        F.conv2d(xp, w).backward(dy)
+        ref = xp.grad
+        dyn = dy.permute(0, 2, 3, 1).contiguous().to(cuda)
+        if kind_name == "full":
+            cv = ops.Conv(CONV3X3_FULL, EPI_RAW, B, H, W, 2, 64, 64, 64, cuda)
+            buf = torch.zeros(B * (H + 4) * (W + 4) * 64 + 4096, dtype=torch.bfloat16, device=cuda)
+            xv = buf[: B * (H + 4) * (W + 4) * 64].view(B, H + 4, W + 4, 64)
+            xv[:, 2:-2, 2:-2] = dyn
+        else:
+            cv = ops.Conv(CONV3X3_FULL_SHARED, EPI_RAW, B, H, W, 2, 64, 64, 64, cuda)
+            P, S = W + 2, (H + 2) * (W + 2)
+            xv = torch.zeros(B * S + 2 * P + 2 + 256, 64, dtype=torch.bfloat16, device=cuda)
+            for b in range(B):
+                xv[b * S + 2 * P + 2: b * S + 2 * P + 2 + H * P].view(H, P, 64)[:, :W] = dyn[b]
+        cv.pack(w.to(cuda))
+        y = torch.full((B, H + 2, W + 2, 64), float("nan"), dtype=torch.bfloat16, device=cuda)
+        cv.forward(xv, y)
+        torch.cuda.synchronize()
+        return y.clone(), y.float().cpu().permute(0, 3, 1, 2), ref
+
+    y_row, got, ref = run()
+    assert not torch.isnan(got).any()
+    assert float((got - ref).abs().max()) <= float(ref.abs().max()) * 2.0 ** -7
+    monkeypatch.setenv("JPDSE_ROW_MODE", "0")
+    y_tap, _, _ = run()
+    assert torch.equal(y_row, y_tap)
