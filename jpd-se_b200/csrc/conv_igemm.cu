@@ -1085,7 +1085,21 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   const bool shared = d->kind == JPDSE_CONV3X3_FULL_SHARED;
-  const bool flat = d->kind == JPDSE_CONV3X3_FULL || d->kind == JPDSE_CONV7X7_FULL || d->kind == JPDSE_CONV4X4_S1_FULL || shared;
+  // The PatchGAN's stride-1 4x4 convs run on 131 / 67-pixel-wide grids: one-row tiles of 128 pixels waste half of every
+  // second tile (131 = 128 + 3) or half of every tile (67 of 128). Over flat positions of the zero-bordered input
+  // (pitch W+4: 3 dead columns per row) the same kernel wastes 2-4 %; taken when it saves more than 10 % of the tiles.
+  bool flat_s1 = false;
+  if (d->kind == JPDSE_CONV4X4_S1) {
+    const char* e = getenv("JPDSE_FLAT_S1");  // "0": rectangular tiles (read per call: tests toggle it)
+    int th = 0, tw = 0;
+    pick_tile(g.gemm_w, &th, &tw);
+    const long long rect = static_cast<long long>((g.gemm_h + th - 1) / th) * ((g.gemm_w + tw - 1) / tw);
+    const long long pitch = d->in_w + 2 * d->in_pad;
+    const long long flat_tiles = ((g.out_h - 1) * pitch + g.out_w + 127) / 128;
+    flat_s1 = !(e != nullptr && e[0] == '0') && flat_tiles * 10 < rect * 9;
+  }
+  const bool flat = d->kind == JPDSE_CONV3X3_FULL || d->kind == JPDSE_CONV7X7_FULL || d->kind == JPDSE_CONV4X4_S1_FULL || shared ||
+                    flat_s1;
   p.batch = d->batch;
   if (shared) {
     // the whole batch is one run of positions, pitch = output width: position m IS output pixel m of the dense
@@ -1299,6 +1313,11 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
       dims[0] = C;
       p.ntaps = 16;
       for (int t = 0; t < 16; ++t) p.tap_off[t][1] = (1 + t / 4) * static_cast<int>(Wp) + (1 + t % 4);
+    } else if (d->kind == JPDSE_CONV4X4_S1) {
+      // y[oy, ox] = sum_{kh, kw} x_stored[oy + kh, ox + kw] * W[kh][kw] (x stored with its zero border of 2)
+      dims[0] = C;
+      p.ntaps = 16;
+      for (int t = 0; t < 16; ++t) p.tap_off[t][1] = (t / 4) * static_cast<int>(Wp) + (t % 4);
     } else {
       dims[0] = 64;  // 7*C window elements (+ zero-weight tail) under a filter row
       p.ntaps = 7;

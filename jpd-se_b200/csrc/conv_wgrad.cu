@@ -488,6 +488,21 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
   }
   p.kw_cols = grid_w >= 64 ? 64 : next_pow2(grid_w);
   p.kh_rows = 64 / p.kw_cols;
+  if (d->kind == JPDSE_CONV4X4_S2 || d->kind == JPDSE_CONV4X4_S1) {
+    // the PatchGAN's grids (513, 257, 131, 67 ... wide) are never a whole number of 64-pixel row pieces: take the
+    // 64-pixel box shape (64x1 ... 8x8) that covers the grid with the least overhang (67 wide: 48 % -> 22 % dead pixels)
+    const char* e = getenv("JPDSE_WGRAD_BOX");  // "0": always 64 x 1
+    long long best = -1;
+    for (int kw = 64; kw >= 8 && !(e != nullptr && e[0] == '0'); kw >>= 1) {
+      const int kh = 64 / kw;
+      const long long area = static_cast<long long>((grid_w + kw - 1) / kw) * kw * ((grid_h + kh - 1) / kh) * kh;
+      if (best < 0 || area < best) {
+        best = area;
+        p.kw_cols = kw;
+        p.kh_rows = kh;
+      }
+    }
+  }
   p.nbw = (grid_w + p.kw_cols - 1) / p.kw_cols;
   p.nbh = (grid_h + p.kh_rows - 1) / p.kh_rows;
 
