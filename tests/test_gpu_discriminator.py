@@ -489,3 +489,45 @@ def test_discriminator_and_vgg_losses_at_the_training_size(cuda):
     ratio = float(f.grad.cpu().norm() / fo.grad.norm())
     print("d(G_GAN + 10 G_GAN_Feat + 10 G_VGG)/d(fake) at 1024x512: cosine %.5f norm ratio %.4f" % (c, ratio))
     assert c >= 0.97 and 0.95 <= ratio <= 1.05
+
+
+@pytest.mark.parametrize("B,H,W,cin,cout", [(2, 66, 130, 256, 512), (1, 33, 65, 128, 128), (2, 34, 66, 512, 1)])
+def test_flat_tiles_and_box_shapes_equal_the_rectangular_forms(cuda, monkeypatch, B, H, W, cin, cout):
+    """The PatchGAN's stride-1 convs over flat positions (JPDSE_FLAT_S1) and the per-grid weight-gradient pixel boxes
+    (JPDSE_WGRAD_BOX) against the rectangular-tile / 64x1-box forms on the same operands: the forward is the same MMAs in
+    the same order (bit-identical output), the weight gradient the same sum in another blocking (fp32 summation order)."""
+    ops = _ops()
+    from jpdse_b200._lib import CONV4X4_S1, EPI_BIAS_NCHW, EPI_RAW_STATS
+    g = torch.Generator().manual_seed(W + cout)
+    x = _stored(_bf(torch.randn(B, cin, H, W, generator=g)), 2, cin).to(cuda)
+    w = _bf(torch.randn(cout, cin, 4, 4, generator=g) * 0.05).to(cuda)
+    bias = (torch.randn(cout, generator=g) * 0.1).to(cuda)
+    dy = _stored(_bf(torch.randn(B, cout, H + 1, W + 1, generator=g)), 2, (cout + 63) // 64 * 64).to(cuda)
+
+    def run():
+        if cout == 1:
+            cv = ops.Conv(CONV4X4_S1, EPI_BIAS_NCHW, B, H, W, 2, cin, cin, cout, cuda)
+            cv.pack(w, bias)
+            y = torch.full((B, 1, H + 1, W + 1), float("nan"), device=cuda)
+            cv.forward(x, y)
+            st = None
+        else:
+            cv = ops.Conv(CONV4X4_S1, EPI_RAW_STATS, B, H, W, 2, cin, cin, cout, cuda)
+            cv.pack(w)
+            y = torch.full((B, H + 1, W + 1, cout), float("nan"), dtype=torch.bfloat16, device=cuda)
+            st = torch.zeros(B, cout, 2, dtype=torch.float64, device=cuda)
+            cv.forward(x, y, st)
+        dw = torch.empty(cout, cin, 4, 4, device=cuda)
+        cv.wgrad(x, dy, 2, dw)
+        torch.cuda.synchronize()
+        return y, st, dw
+
+    y1, st1, dw1 = run()
+    monkeypatch.setenv("JPDSE_FLAT_S1", "0")
+    monkeypatch.setenv("JPDSE_WGRAD_BOX", "0")
+    y0, st0, dw0 = run()
+    assert not torch.isnan(y1.float()).any()
+    assert torch.equal(y1, y0)
+    if st1 is not None:
+        assert torch.allclose(st1, st0, rtol=1e-6, atol=1e-4)
+    assert float((dw1 - dw0).abs().max()) <= 1e-4 * float(dw0.abs().max())
