@@ -295,7 +295,7 @@ d_input_ids_kernel(const void* __restrict__ label, int label_dtype, const void* 
 constexpr int kNormThreads = 256;
 constexpr int kNormIters = 16;
 
-template <bool kRelu, bool kResidual>
+template <bool kRelu, bool kResidual, int kIters = kNormIters>
 __global__ void __launch_bounds__(kNormThreads)
 instnorm_apply_kernel(const __nv_bfloat16* __restrict__ raw, const double* __restrict__ stats,
                       const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int H, int W, int C,
@@ -357,10 +357,10 @@ instnorm_apply_kernel(const __nv_bfloat16* __restrict__ raw, const double* __res
   // Loads are issued FOUR pixels at a time before anything is consumed: with a bounds check (a possible `break`) between
   // the iterations the compiler cannot hoist the next pixel's loads above the current pixel's arithmetic, and every
   // thread then has a single 16-byte load in flight (the kernel sat at 0.46-0.68 of the HBM peak).
-  for (int pix0 = blockIdx.x * (ppi * kNormIters); pix0 < npix; pix0 += gridDim.x * (ppi * kNormIters)) {
-    if (pix0 + ppi * kNormIters <= npix) {
+  for (int pix0 = blockIdx.x * (ppi * kIters); pix0 < npix; pix0 += gridDim.x * (ppi * kIters)) {
+    if (pix0 + ppi * kIters <= npix) {
 #pragma unroll
-      for (int it0 = 0; it0 < kNormIters; it0 += 4) {
+      for (int it0 = 0; it0 < kIters; it0 += 4) {
         uint4 x[4], rs[4];
         int pp[4];
 #pragma unroll
@@ -374,7 +374,7 @@ instnorm_apply_kernel(const __nv_bfloat16* __restrict__ raw, const double* __res
         for (int u = 0; u < 4; ++u) finish(x[u], rs[u], pp[u]);
       }
     } else {
-      for (int it = 0; it < kNormIters; ++it) {
+      for (int it = 0; it < kIters; ++it) {
         const int pp = pix0 + it * ppi + psub;
         if (pp >= npix) break;
         const uint4 x = __ldg(raw4 + src_of(pp) * vpp + vec);
@@ -716,11 +716,49 @@ extern "C" int jpdse_instnorm_apply(const void* raw, const double* stats, const 
   const int wave = (num_sms() * per_sm) / batch > 0 ? (num_sms() * per_sm) / batch : 1;
   // measured on B200 (batch 16): the single-wave grid wins for C >= 128 (0.275 -> 0.241 ms at C = 128, 0.063 -> 0.051
   // at C = 1024) and loses for the two full-resolution C = 64 layers (0.43 -> 0.455 ms), which keep one CTA per chunk
-  if (channels >= 128 && gx > wave) gx = wave;
+  int iters = kNormIters;
+  if (channels >= 128 && gx > wave) {
+    // One resident wave, and every CTA ONE chunk where a chunk of 20 ... 32 pixel groups makes that possible: with the
+    // fixed 16 the 2244 padded pixels of a 1024-channel map are 71 chunks on 55 CTAs per image -- a quarter of the CTAs
+    // run two chunks while the rest wait (JPDSE_NORM_BALANCE=0 keeps that form).
+    static int balance = -1;
+    if (balance < 0) {
+      const char* e = getenv("JPDSE_NORM_BALANCE");
+      balance = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    const int need = (npix + wave * ppi - 1) / (wave * ppi);  // pixel groups per CTA for one chunk each
+    if (balance && need > 16 && need <= 32) {
+      iters = (need + 3) / 4 * 4;
+      gx = (npix + ppi * iters - 1) / (ppi * iters);
+    } else {
+      gx = wave;
+    }
+  }
   dim3 grid(gx, batch);
   const __nv_bfloat16* r = static_cast<const __nv_bfloat16*>(raw);
   const __nv_bfloat16* rs = static_cast<const __nv_bfloat16*>(residual);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (iters != kNormIters) {
+#define JPDSE_NORM_LAUNCH(IT)                                                                                                   \
+  do {                                                                                                                          \
+    if (relu && residual)                                                                                                       \
+      instnorm_apply_kernel<true, true, IT><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);  \
+    else if (relu)                                                                                                              \
+      instnorm_apply_kernel<true, false, IT><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps); \
+    else if (residual)                                                                                                          \
+      instnorm_apply_kernel<false, true, IT><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps); \
+    else                                                                                                                        \
+      instnorm_apply_kernel<false, false, IT><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps); \
+  } while (0)
+    switch (iters) {
+      case 20: JPDSE_NORM_LAUNCH(20); break;
+      case 24: JPDSE_NORM_LAUNCH(24); break;
+      case 28: JPDSE_NORM_LAUNCH(28); break;
+      default: JPDSE_NORM_LAUNCH(32); break;
+    }
+#undef JPDSE_NORM_LAUNCH
+    return check_launch("instnorm_apply_kernel");
+  }
   if (relu && residual)
     instnorm_apply_kernel<true, true><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
   else if (relu)

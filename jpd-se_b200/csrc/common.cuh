@@ -2,6 +2,7 @@
 #pragma once
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 
 #include "../../include/jpdse_b200.h"
@@ -30,7 +31,14 @@ inline int num_sms() {
   if (n[dev] == 0) {
     int v = 0;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    n[dev] = v > 0 ? v : 148;
+    v = v > 0 ? v : 148;
+    // JPDSE_RESERVE_SMS=n (experiment; read once per process): size every grid for n fewer SMs, so that a concurrent
+    // library kernel (NCCL under the overlapped gradient all-reduce) has SMs of its own instead of delaying the
+    // statically scheduled persistent CTAs that would have run there
+    const char* e = getenv("JPDSE_RESERVE_SMS");
+    const int r = e ? atoi(e) : 0;
+    if (r > 0 && r < v) v -= r;
+    n[dev] = v;
   }
   return n[dev];
 }
