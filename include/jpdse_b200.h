@@ -272,6 +272,15 @@ int jpdse_maxpool2x2(const void* x, void* y, int batch, int height, int width, i
                      int out_pad, void* stream);
 int jpdse_maxpool2x2_backward(const void* x, const void* g, int g_pad, void* dx, int batch, int height,
                               int width, int channels, int in_pad, void* stream);
+/* The PatchGAN's 1-channel output conv (nn.Conv2d(512, 1, kernel 4, stride 1, padding 2), networks.py:447) as a 1x1 GEMM:
+ * z[b][t][p] = sum_c x[b][p][c] * w[t][c] for the 16 taps t over EVERY stored pixel p of the zero-bordered input
+ * (JPDSE_CONV1X1 with 16 outputs, JPDSE_EPI_BIAS_NCHW, zero bias: the activation is read once instead of once per tap),
+ * then  out[b,0,y,x] = bias + sum_{kh,kw} z[b][kh*4+kw][y+kh][x+kw]  (jpdse_patch_out_gather; z is float32
+ * (B,16,H+4,W+4), out float32 (B,1,H+1,W+1)). Backward: dz[b][p][t] = dout[b, py-kh, px-kw] (jpdse_patch_out_scatter:
+ * bf16 (B,H+4,W+4,c_pad), channels >= 16 zero) is at once the P operand of the weight gradient and the input of the data
+ * gradient, both 1x1 GEMMs. height / width are the conv's INPUT size H, W. */
+int jpdse_patch_out_gather(const float* z, const float* bias, float* out, int batch, int height, int width, void* stream);
+int jpdse_patch_out_scatter(const float* dout, void* dz, int batch, int height, int width, int c_pad, void* stream);
 /* Stored bf16 (B,H+2*pad,W+2*pad,c_stored) -> float32 NCHW (B,channels,H,W) (feature maps handed back to PyTorch). */
 int jpdse_nhwc_pad_to_nchw_f32(const void* x, float* y, int batch, int channels, int height, int width, int pad,
                                int c_stored, void* stream);

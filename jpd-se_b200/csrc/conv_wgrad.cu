@@ -488,7 +488,7 @@ static int wgrad_plan(const jpdse_conv_desc* d, int dy_pad, WgPlan* w) {
   }
   p.kw_cols = grid_w >= 64 ? 64 : next_pow2(grid_w);
   p.kh_rows = 64 / p.kw_cols;
-  if (d->kind == JPDSE_CONV4X4_S2 || d->kind == JPDSE_CONV4X4_S1) {
+  if (d->kind == JPDSE_CONV4X4_S2 || d->kind == JPDSE_CONV4X4_S1 || d->kind == JPDSE_CONV1X1) {
     // the PatchGAN's grids (513, 257, 131, 67 ... wide) are never a whole number of 64-pixel row pieces: take the
     // 64-pixel box shape (64x1 ... 8x8) that covers the grid with the least overhang (67 wide: 48 % -> 22 % dead pixels)
     const char* e = getenv("JPDSE_WGRAD_BOX");  // "0": always 64 x 1

@@ -652,6 +652,75 @@ extern "C" int jpdse_maxpool2x2_backward(const void* x, const void* g, int g_pad
   return check_launch("maxpool2x2_backward_kernel");
 }
 
+// ------------------------------------------------------------------------------------------ 1-channel output conv
+namespace jpdse {
+// out[b,y,x] = bias + sum_t z[b][t][(y + t/4) * Ws + x + t%4]: one thread per output pixel, 16 plane-coalesced loads
+__global__ void __launch_bounds__(256)
+patch_out_gather_kernel(const float* __restrict__ z, const float* __restrict__ bias, float* __restrict__ out, int B, int H, int W) {
+  const int Ho = H + 1, Wo = W + 1, Ws = W + 4;
+  const size_t plane = static_cast<size_t>(H + 4) * Ws;
+  const size_t total = static_cast<size_t>(B) * Ho * Wo;
+  const float b0 = bias != nullptr ? __ldg(bias) : 0.f;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = static_cast<int>(i % Wo);
+    const int y = static_cast<int>((i / Wo) % Ho);
+    const int b = static_cast<int>(i / (static_cast<size_t>(Wo) * Ho));
+    const float* zb = z + static_cast<size_t>(b) * 16 * plane + static_cast<size_t>(y) * Ws + x;
+    float acc = 0.f;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) acc += __ldg(zb + t * plane + (t >> 2) * Ws + (t & 3));
+    out[i] = acc + b0;
+  }
+}
+
+// dz[b][py][px][t] = dout[b][py - t/4][px - t%4] (0 outside, and for the channels t >= 16): thread = (stored pixel, 8-ch vector)
+__global__ void __launch_bounds__(256)
+patch_out_scatter_kernel(const float* __restrict__ dout, __nv_bfloat16* __restrict__ dz, int B, int H, int W, int c_pad) {
+  const int Ho = H + 1, Wo = W + 1, Hs = H + 4, Ws = W + 4;
+  const int vpp = c_pad >> 3;
+  const size_t total = static_cast<size_t>(B) * Hs * Ws * vpp;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % vpp);
+    const size_t pix = i / vpp;
+    const int px = static_cast<int>(pix % Ws);
+    const int py = static_cast<int>((pix / Ws) % Hs);
+    const int b = static_cast<int>(pix / (static_cast<size_t>(Ws) * Hs));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int t = 8 * k + j;
+      const int y = py - (t >> 2), x = px - (t & 3);
+      v[j] = (t < 16 && y >= 0 && y < Ho && x >= 0 && x < Wo) ? __ldg(dout + (static_cast<size_t>(b) * Ho + y) * Wo + x) : 0.f;
+    }
+    reinterpret_cast<uint4*>(dz)[i] = make_uint4(d_pack2(v[0], v[1]), d_pack2(v[2], v[3]), d_pack2(v[4], v[5]), d_pack2(v[6], v[7]));
+  }
+}
+
+}  // namespace jpdse
+using namespace jpdse;
+
+extern "C" int jpdse_patch_out_gather(const float* z, const float* bias, float* out, int batch, int height, int width, void* stream) {
+  if (z == nullptr || out == nullptr) return fail(JPDSE_ERR_INVALID, "patch_out_gather: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0) return fail(JPDSE_ERR_INVALID, "patch_out_gather: bad sizes");
+  const size_t total = static_cast<size_t>(batch) * (height + 1) * (width + 1);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > static_cast<size_t>(num_sms()) * 16) blocks = static_cast<size_t>(num_sms()) * 16;
+  patch_out_gather_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, bias, out, batch, height, width);
+  return check_launch("patch_out_gather_kernel");
+}
+
+extern "C" int jpdse_patch_out_scatter(const float* dout, void* dz, int batch, int height, int width, int c_pad, void* stream) {
+  if (dout == nullptr || dz == nullptr) return fail(JPDSE_ERR_INVALID, "patch_out_scatter: NULL pointer");
+  if (batch <= 0 || height <= 0 || width <= 0 || c_pad < 16 || c_pad % 8) return fail(JPDSE_ERR_INVALID, "patch_out_scatter: bad sizes");
+  if (reinterpret_cast<uintptr_t>(dz) & 15) return fail(JPDSE_ERR_INVALID, "patch_out_scatter: dz must be 16-byte aligned");
+  const size_t total = static_cast<size_t>(batch) * (height + 4) * (width + 4) * (c_pad / 8);
+  size_t blocks = (total + 255) / 256;
+  if (blocks > static_cast<size_t>(num_sms()) * 16) blocks = static_cast<size_t>(num_sms()) * 16;
+  patch_out_scatter_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dout, static_cast<__nv_bfloat16*>(dz), batch, height, width, c_pad);
+  return check_launch("patch_out_scatter_kernel");
+}
+
 extern "C" int jpdse_nhwc_pad_to_nchw_f32(const void* x, float* y, int batch, int channels, int height, int width, int pad,
                                           int c_stored, void* stream) {
   if (x == nullptr || y == nullptr) return fail(JPDSE_ERR_INVALID, "nhwc_pad_to_nchw_f32: NULL pointer");

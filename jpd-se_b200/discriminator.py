@@ -20,10 +20,12 @@ What is computed follows what the caller needs: the discriminator's own loss nee
 gradient; the generator's GAN / feature-matching losses need the gradient w.r.t. the image channels of the input and --
 because ``optimizer_D.zero_grad()`` discards them (ctu/trainers/pix2pixHD_trainer.py:73) -- no parameter gradients.
 """
+import os
+
 import torch
 
 from . import ops
-from ._lib import (CONV4X4_S1, CONV4X4_S1_FULL, CONV4X4_S2, CONV4X4_S2_DGRAD, EPI_BIAS_ACT, EPI_BIAS_NCHW, EPI_RAW,
+from ._lib import (CONV1X1, CONV4X4_S1, CONV4X4_S1_FULL, CONV4X4_S2, CONV4X4_S2_DGRAD, EPI_BIAS_ACT, EPI_BIAS_NCHW, EPI_RAW,
                    EPI_RAW_STATS, JpdseError)
 
 SLOPE = 0.2  # nn.LeakyReLU(0.2, True), networks.py:430-445
@@ -44,7 +46,7 @@ class _Slot:
 
     def __init__(self):
         self.generation = -1
-        self.x_in, self.raw, self.feat, self.stats, self.final = [], [], [], [], []
+        self.x_in, self.raw, self.feat, self.stats, self.final, self.z = [], [], [], [], [], []
 
 
 class DiscriminatorPlan:
@@ -63,6 +65,7 @@ class DiscriminatorPlan:
             raise JpdseError("a pair plan holds an even number of images")
         self.pair, self.half = pair, batch // 2
         self.c_in = 64
+        self.patch_gemm = os.environ.get("JPDSE_PATCH_OUT_GEMM", "1") != "0"
         B = batch
         widths = [ndf]
         for _ in range(1, n_layers + 1):
@@ -98,6 +101,17 @@ class DiscriminatorPlan:
                     L.dgrad = ops.Conv(CONV4X4_S1_FULL, EPI_RAW, B, L.out_h, L.out_w, PAD, cst, L.cout, cin, device,
                                        cout_real=cin_real)
                 L.dgrad_half = None
+                if L.final and self.patch_gemm:
+                    # the 1-channel output conv as 1x1 GEMMs over the stored pixels (include/jpdse_b200.h, jpdse_patch_out_*):
+                    # the 512-channel activation is read once instead of once per tap
+                    # (the stored pixels of an image are contiguous: to the two GEMMs that run over ALL of them the image is one
+                    # row of (lh+4)*(lw+4) pixels -- whole 128-pixel tiles instead of one and a bit per 134-pixel row)
+                    npx = (lh + 2 * PAD) * (lw + 2 * PAD)
+                    L.z_conv = ops.Conv(CONV1X1, EPI_BIAS_NCHW, B, 1, npx, 0, cin, cin_real, 16, device)
+                    L.z_wconv = ops.Conv(CONV1X1, EPI_RAW, B, 1, npx, 0, cin, cin_real, 64, device)
+                    L.dz_dgrad = ops.Conv(CONV1X1, EPI_RAW, B, lh, lw, PAD, 64, 16, cin, device)
+                    L.dz_dgrad_half = ops.Conv(CONV1X1, EPI_RAW, self.half, lh, lw, PAD, 64, 16, cin, device) if pair else None
+                    L.zero_bias = torch.zeros(16, dtype=torch.float32, device=device)
                 if pair:
                     if L.stride == 2:
                         L.dgrad_half = ops.Conv(CONV4X4_S2_DGRAD, EPI_RAW, self.half, L.out_h, L.out_w, PAD, cst, L.cout, cin,
@@ -132,6 +146,8 @@ class DiscriminatorPlan:
             s.stats.append(stats)
             Lf = layers[-1]
             s.final.append(torch.empty((B, 1, Lf.out_h, Lf.out_w), dtype=torch.float32, device=dev))
+            s.z.append(torch.empty((B, 16, Lf.in_h + 2 * PAD, Lf.in_w + 2 * PAD), dtype=torch.float32, device=dev)
+                       if self.patch_gemm else None)
         return s
 
     def _buf(self, name, shape, dtype=torch.bfloat16, zero=False):
@@ -155,6 +171,14 @@ class DiscriminatorPlan:
             for L in layers:
                 w = state_dict[L.key + ".weight"].detach().to(self.device).contiguous().float()
                 b = state_dict[L.key + ".bias"].detach().to(self.device).contiguous().float()
+                if L.final and self.patch_gemm:
+                    L.z_conv.pack(w[0].permute(1, 2, 0).reshape(16, L.cin_real, 1, 1).contiguous(), L.zero_bias)
+                    wt = w[0].reshape(L.cin_real, 16, 1, 1).contiguous()
+                    L.dz_dgrad.pack(wt)
+                    if L.dz_dgrad_half is not None:
+                        L.dz_dgrad_half.pack(wt)
+                    L.bias_dev = b
+                    continue
                 L.conv.pack(w, None if L.norm else b)  # a bias in front of an InstanceNorm cancels exactly
                 L.dgrad.pack(w)
                 if L.dgrad_half is not None:
@@ -212,7 +236,10 @@ class DiscriminatorPlan:
             for i, layers in enumerate(self.scales):
                 x = s.x_in[i]
                 for j, L in enumerate(layers):
-                    if L.final:
+                    if L.final and self.patch_gemm:
+                        L.z_conv.forward(x, s.z[i])
+                        ops.patch_out_gather(s.z[i], L.bias_dev, s.final[i], self.B, L.in_h, L.in_w)
+                    elif L.final:
                         L.conv.forward(x, s.final[i])
                     elif not L.norm:
                         L.conv.forward(x, s.feat[i][j])
@@ -263,6 +290,28 @@ class DiscriminatorPlan:
                     L = layers[j]
                     x = s.x_in[i] if j == 0 else s.feat[i][j - 1]
                     dgrad = L.dgrad_half if first_half else L.dgrad
+                    if L.final and self.patch_gemm:
+                        if final_grads[i] is None:
+                            continue
+                        # gradient of the 16 tap planes: the P operand of the weight gradient AND the data gradient's input
+                        dz = self._buf("dz%s%d" % (tag, i), (B, L.in_h + 2 * PAD, L.in_w + 2 * PAD, 64))
+                        ops.patch_out_scatter(final_grads[i].contiguous(), dz, B, L.in_h, L.in_w)
+                        if need_params:
+                            self._bias_grad(param_grads, L.key + ".bias", final_grads[i].sum().reshape(1), accumulate)
+                            dw64 = self._buf("dw64_%d" % i, (64, L.cin_real, 1, 1), torch.float32)
+                            L.z_wconv.wgrad(x, dz, 0, dw64)
+                            dw_new = dw64[:16, :, 0, 0].t().reshape(1, L.cin_real, 4, 4)
+                            key = L.key + ".weight"
+                            if accumulate and key in param_grads:
+                                param_grads[key] += dw_new
+                            else:
+                                param_grads[key] = dw_new.contiguous()
+                        if j > 0 or need_input:
+                            g = self._buf("g%s%d_%d" % (tag, i, j), (B, L.in_h, L.in_w, L.cin))
+                            (L.dz_dgrad_half if first_half else L.dz_dgrad).forward(dz, g)
+                        else:
+                            g = None
+                        continue
                     if L.final:
                         if final_grads[i] is None:
                             continue

@@ -352,6 +352,32 @@ def instnorm_apply_act(raw, stats, out, batch, height, width, channels, out_pad,
     return out
 
 
+def patch_out_gather(z, bias, out, batch, height, width):
+    """out (B,1,H+1,W+1) = bias + the 16 tap planes of z (B,16,H+4,W+4) summed at their offsets; see jpdse_patch_out_gather."""
+    lib = _lib.load()
+    _need(z, "z", torch.float32)
+    _need(out, "out", torch.float32)
+    if bias is not None:
+        _need(bias, "bias", torch.float32)
+    if tuple(z.shape) != (batch, 16, height + 4, width + 4) or tuple(out.shape) != (batch, 1, height + 1, width + 1):
+        raise JpdseError("patch_out_gather: z %s / out %s do not match (%d, %d, %d)" % (tuple(z.shape), tuple(out.shape), batch, height, width))
+    check(lib.jpdse_patch_out_gather(_ptr(z), _ptr(bias), _ptr(out), batch, height, width, _stream()))
+    _count()
+    return out
+
+
+def patch_out_scatter(dout, dz, batch, height, width):
+    """dz (B,H+4,W+4,c_pad) bf16 = the gradient of the 16 tap planes from dout (B,1,H+1,W+1); see jpdse_patch_out_scatter."""
+    lib = _lib.load()
+    _need(dout, "dout", torch.float32)
+    _need(dz, "dz", torch.bfloat16)
+    if tuple(dout.shape) != (batch, 1, height + 1, width + 1) or tuple(dz.shape[:3]) != (batch, height + 4, width + 4):
+        raise JpdseError("patch_out_scatter: dout %s / dz %s do not match (%d, %d, %d)" % (tuple(dout.shape), tuple(dz.shape), batch, height, width))
+    check(lib.jpdse_patch_out_scatter(_ptr(dout), _ptr(dz), batch, height, width, dz.shape[-1], _stream()))
+    _count()
+    return dz
+
+
 def act_backward(g, skip, f, d_pre, dbias, batch, height, width, channels, f_pad, out_pad, slope, g_pad=0):
     lib = _lib.load()
     _need(g, "g", torch.bfloat16)
