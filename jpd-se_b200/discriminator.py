@@ -38,7 +38,7 @@ def _round_up(x, m):
 
 class _DLayer:
     __slots__ = ("key", "conv", "dgrad", "dgrad_half", "stride", "cin", "cin_real", "cout", "in_h", "in_w", "out_h", "out_w",
-                 "norm", "final")
+                 "norm", "final", "z_conv", "z_wconv", "dz_dgrad", "dz_dgrad_half", "zero_bias", "bias_dev")
 
 
 class _Slot:
