@@ -531,3 +531,32 @@ def test_flat_tiles_and_box_shapes_equal_the_rectangular_forms(cuda, monkeypatch
     if st1 is not None:
         assert torch.allclose(st1, st0, rtol=1e-6, atol=1e-4)
     assert float((dw1 - dw0).abs().max()) <= 1e-4 * float(dw0.abs().max())
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 72, 104)])
+def test_output_conv_as_1x1_gemms_equals_the_4x4_conv(cuda, monkeypatch, B, H, W):
+    """The PatchGAN's 1-channel output conv as 1x1 GEMMs over the stored pixels (16 tap planes + gather; backward: scatter +
+    two 1x1 GEMMs; JPDSE_PATCH_OUT_GEMM, the default) against the 4x4 implicit-GEMM conv and its gradient kinds on the same
+    weights and inputs: the four losses, the gradient w.r.t. the fake image and every parameter gradient. Both forms
+    multiply bf16 operands and accumulate in float32; only the summation order differs."""
+    results = []
+    for mode in ("1", "0"):
+        monkeypatch.setenv("JPDSE_PATCH_OUT_GEMM", mode)
+        netD, sd, input_label, fake, real = _setup(cuda, B, H, W, seed=21)
+        f = fake.clone().to(cuda).requires_grad_(True)
+        l_gan, l_fm, l_real, l_fake = netD.fused_losses(input_label.to(cuda), f, real.to(cuda))
+        (l_gan + 10.0 * l_fm).backward(retain_graph=True)
+        gin = f.grad.clone()
+        for p in netD.parameters():
+            p.grad = None
+        ((l_real + l_fake) * 0.5).backward()
+        torch.cuda.synchronize()
+        results.append(([float(l_gan), float(l_fm), float(l_real), float(l_fake)], gin.cpu(),
+                        {k: p.grad.detach().cpu().clone() for k, p in netD.named_parameters()}))
+    (la, ga, pa), (lb, gb, pb) = results
+    for x, y in zip(la, lb):
+        assert abs(x - y) <= 2e-4 * abs(y) + 1e-6, (la, lb)
+    assert _cos(ga, gb) >= 0.9995 and abs(float(ga.norm() / gb.norm()) - 1.0) <= 5e-3
+    for k in pa:
+        if pb[k].numel() > 1 and float(pb[k].abs().max()) > 0:
+            assert _cos(pa[k], pb[k]) >= 0.999, k
