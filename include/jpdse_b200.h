@@ -29,7 +29,7 @@ extern "C" {
 #define JPDSE_ERR_CUDA (-2)
 #define JPDSE_ERR_UNSUPPORTED (-3)
 
-/* ABI version of this header (3); bumped on any signature, enum or layout-flag change. */
+/* ABI version of this header (4); bumped on any signature, enum, layout-flag or entry-point change. */
 int jpdse_abi_version(void);
 /* Message of the last error on this thread ("" if none). Never NULL. */
 const char* jpdse_last_error(void);
@@ -272,7 +272,8 @@ int jpdse_maxpool2x2(const void* x, void* y, int batch, int height, int width, i
                      int out_pad, void* stream);
 int jpdse_maxpool2x2_backward(const void* x, const void* g, int g_pad, void* dx, int batch, int height,
                               int width, int channels, int in_pad, void* stream);
-/* The PatchGAN's 1-channel output conv (nn.Conv2d(512, 1, kernel 4, stride 1, padding 2), networks.py:447) as a 1x1 GEMM:
+/* ---- ABI version 4
+ * The PatchGAN's 1-channel output conv (nn.Conv2d(512, 1, kernel 4, stride 1, padding 2), networks.py:447) as a 1x1 GEMM:
  * z[b][t][p] = sum_c x[b][p][c] * w[t][c] for the 16 taps t over EVERY stored pixel p of the zero-bordered input
  * (JPDSE_CONV1X1 with 16 outputs, JPDSE_EPI_BIAS_NCHW, zero bias: the activation is read once instead of once per tap),
  * then  out[b,0,y,x] = bias + sum_{kh,kw} z[b][kh*4+kw][y+kh][x+kw]  (jpdse_patch_out_gather; z is float32

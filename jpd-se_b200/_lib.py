@@ -25,7 +25,7 @@ class ConvDesc(ctypes.Structure):
  CONV4X4_S2_DGRAD, CONV4X4_S1_FULL, CONV3X3_PAD1_NARROW, CONV3X3_FULL_SHARED) = range(13)
 PAD_SHARED = 0x100  # JPDSE_PAD_SHARED: shared-border layout flag of the gradient pad arguments
 EPI_RAW_STATS, EPI_BIAS_TANH_NCHW, EPI_SIGN_NCHW, EPI_RAW, EPI_BIAS_ACT, EPI_BIAS_NCHW = range(6)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # symbol -> (restype, argtypes); also the list the CPU test checks against the header
 SIGNATURES = {

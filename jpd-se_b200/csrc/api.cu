@@ -21,5 +21,5 @@ int fail(int code, const char* fmt, ...) {
 
 }  // namespace jpdse
 
-extern "C" int jpdse_abi_version(void) { return 3; }
+extern "C" int jpdse_abi_version(void) { return 4; }
 extern "C" const char* jpdse_last_error(void) { return jpdse::last_error_buffer(); }

@@ -27,7 +27,7 @@ def test_library_exports_every_header_symbol():
         assert hasattr(lib, n), "libjpdse_b200.so does not export %s" % n
     # every declared function has a ctypes signature and vice versa
     assert sorted(jpdse_b200._lib.SIGNATURES) == names
-    assert lib.jpdse_abi_version() == jpdse_b200._lib.ABI_VERSION == 3
+    assert lib.jpdse_abi_version() == jpdse_b200._lib.ABI_VERSION == 4
     assert lib.jpdse_last_error() is not None
 
 
