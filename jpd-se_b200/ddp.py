@@ -38,6 +38,12 @@ class GradReducer:
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.tail_elems = max(0, tail_bytes // 4)
         self.tail_bucket_elems = max(1, tail_bucket_bytes // 4)
+        # JPDSE_GRAD_BF16=1 (opt-in): buckets cross the wire as bf16 -- fp32 -> bf16 on the communication stream,
+        # all_reduce(AVG) of half the bytes, bf16 -> fp32 back into the flat buffer. Gradients then carry one bf16
+        # rounding (2^-9 relative) before the average; off by default so that the N-rank step equals the reference's
+        # global-batch step to fp32 summation order.
+        self.bf16 = os.environ.get("JPDSE_GRAD_BF16", "0") == "1"
+        self._half = None
         self.total = 0
         self.flat = None
         self.stream = None
@@ -74,6 +80,8 @@ class GradReducer:
             self.flat = torch.empty(total, dtype=torch.float32, device=ref.device)
         if ref.is_cuda and self.stream is None:
             self.stream = torch.cuda.Stream(device=ref.device)
+        if self.bf16 and ref.is_cuda and (self._half is None or self._half.numel() < total):
+            self._half = torch.empty(total, dtype=torch.bfloat16, device=ref.device)
         self.reset_stats()
 
     def alloc(self, key, shape):
@@ -92,7 +100,10 @@ class GradReducer:
     def finish(self):
         self._launch()
         for w in self._works:
-            w.wait()  # CUDA: the current (compute) stream waits; gloo: blocks
+            if isinstance(w, torch.cuda.Event):
+                torch.cuda.current_stream(self.flat.device).wait_event(w)  # bf16 buckets: converted back on the side stream
+            else:
+                w.wait()  # CUDA: the current (compute) stream waits; gloo: blocks
         self._works = []
         if _world(self.group) > 1 and not self.flat.is_cuda:
             self.flat[: self._offset].div_(_world(self.group))
@@ -112,7 +123,16 @@ class GradReducer:
             ev.record(torch.cuda.current_stream(chunk.device))
             with torch.cuda.stream(self.stream):
                 self.stream.wait_event(ev)
-                self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+                if self.bf16 and self._half is not None:
+                    half = self._half[a:b]
+                    half.copy_(chunk)
+                    dist.all_reduce(half, op=dist.ReduceOp.AVG, group=self.group, async_op=True).wait()  # stream-ordered
+                    chunk.copy_(half)
+                    done = torch.cuda.Event()
+                    done.record(self.stream)
+                    self._works.append(done)
+                else:
+                    self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
         else:
             self._works.append(dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
