@@ -4,8 +4,10 @@
 #include <cuda_bf16.h>
 
 #include <cstdint>
+#include <cstring>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace jpdse {
 
@@ -307,6 +309,9 @@ instnorm_apply_kernel(const __nv_bfloat16* __restrict__ raw, const double* __res
   const int b = blockIdx.y;
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int npix = Hp * Wp;
+  // PDL (JPDSE_PDL=1): this CTA may have been placed while the conv that produces `raw` / `stats` was still running
+  grid_dep_launch_dependents();
+  grid_dep_wait();
 
   float mean[8], rstd[8];
   {
@@ -689,6 +694,26 @@ extern "C" int jpdse_build_input_u8(const void* label, int label_dtype, const vo
                           pad, c_pad, out_nchw, bad_label_count, stream_v);
 }
 
+// plain launch, or (JPDSE_PDL=1) with the programmatic-stream-serialization attribute
+template <typename K, typename... A>
+static void launch_norm(K kernel, dim3 grid, cudaStream_t stream, A... args) {
+  if (jpdse::pdl_enabled()) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(jpdse::kNormThreads);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+  } else {
+    kernel<<<grid, jpdse::kNormThreads, 0, stream>>>(args...);
+  }
+}
+
 extern "C" int jpdse_instnorm_apply(const void* raw, const double* stats, const void* residual, void* out, int batch,
                                     int height, int width, int channels, int pad, int relu, float eps, void* stream_v) {
   if (raw == nullptr || stats == nullptr || out == nullptr) return fail(JPDSE_ERR_INVALID, "instnorm_apply: NULL pointer");
@@ -742,13 +767,13 @@ extern "C" int jpdse_instnorm_apply(const void* raw, const double* stats, const 
 #define JPDSE_NORM_LAUNCH(IT)                                                                                                   \
   do {                                                                                                                          \
     if (relu && residual)                                                                                                       \
-      instnorm_apply_kernel<true, true, IT><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);  \
+      launch_norm(instnorm_apply_kernel<true, true, IT>, grid, stream, r, stats, rs, o, height, width, channels, pad, eps);  \
     else if (relu)                                                                                                              \
-      instnorm_apply_kernel<true, false, IT><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps); \
+      launch_norm(instnorm_apply_kernel<true, false, IT>, grid, stream, r, stats, rs, o, height, width, channels, pad, eps); \
     else if (residual)                                                                                                          \
-      instnorm_apply_kernel<false, true, IT><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps); \
+      launch_norm(instnorm_apply_kernel<false, true, IT>, grid, stream, r, stats, rs, o, height, width, channels, pad, eps); \
     else                                                                                                                        \
-      instnorm_apply_kernel<false, false, IT><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps); \
+      launch_norm(instnorm_apply_kernel<false, false, IT>, grid, stream, r, stats, rs, o, height, width, channels, pad, eps); \
   } while (0)
     switch (iters) {
       case 20: JPDSE_NORM_LAUNCH(20); break;
@@ -760,13 +785,13 @@ extern "C" int jpdse_instnorm_apply(const void* raw, const double* stats, const 
     return check_launch("instnorm_apply_kernel");
   }
   if (relu && residual)
-    instnorm_apply_kernel<true, true><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
+    launch_norm(instnorm_apply_kernel<true, true>, grid, stream, r, stats, rs, o, height, width, channels, pad, eps);
   else if (relu)
-    instnorm_apply_kernel<true, false><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
+    launch_norm(instnorm_apply_kernel<true, false>, grid, stream, r, stats, rs, o, height, width, channels, pad, eps);
   else if (residual)
-    instnorm_apply_kernel<false, true><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
+    launch_norm(instnorm_apply_kernel<false, true>, grid, stream, r, stats, rs, o, height, width, channels, pad, eps);
   else
-    instnorm_apply_kernel<false, false><<<grid, kNormThreads, 0, stream>>>(r, stats, rs, o, height, width, channels, pad, eps);
+    launch_norm(instnorm_apply_kernel<false, false>, grid, stream, r, stats, rs, o, height, width, channels, pad, eps);
   return check_launch("instnorm_apply_kernel");
 }
 

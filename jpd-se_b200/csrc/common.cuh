@@ -43,6 +43,18 @@ inline int num_sms() {
   return n[dev];
 }
 
+// JPDSE_PDL=1 (read once per process): the ResnetBlock conv and the InstanceNorm apply kernel are launched with the
+// programmatic-stream-serialization attribute, so each one's CTAs are placed and run their prologue while the previous
+// kernel drains (the kernels call griddepcontrol.wait before they touch global memory)
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("JPDSE_PDL");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 // One-time per-DEVICE setup (cudaFuncSetAttribute applies to the current device only). The design is one process
 // per GPU, but a process that touches several devices must not inherit "already configured" from the first.
 struct DeviceOnce {

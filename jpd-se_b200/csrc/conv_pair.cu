@@ -98,6 +98,10 @@ pair_conv3x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   cluster_sync_all();  // barrier inits and both TMEM allocations visible to the peer before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL (JPDSE_PDL=1): everything above touched no global memory and ran while the previous kernel drained; from here on
+  // the kernel reads what that kernel wrote. The InstanceNorm kernel behind this conv may place its CTAs now.
+  grid_dep_launch_dependents();
+  grid_dep_wait();
 
   const int kblocks = 9 * p.chunks;
   const int m_pairs = (p.batch * p.tiles_h * p.tiles_w) >> 1;
@@ -335,6 +339,22 @@ int pair_conv_forward(const jpdse_conv_desc* d, const void* x, const void* w_pac
   int grid = num_sms() & ~1;
   const long long total = static_cast<long long>(p.batch) * p.tiles_h * p.tiles_w / 2 * p.n_tiles;
   if (grid > 2 * total) grid = static_cast<int>(2 * total);
+  if (pdl_enabled()) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kPrThreads);
+    cfg.dynamicSmemBytes = kPrSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, pair_conv3x3_kernel, ta, tb, p);
+    if (e != cudaSuccess) return fail(JPDSE_ERR_CUDA, "pair_conv3x3_kernel (PDL launch): %s", cudaGetErrorString(e));
+    return check_launch("pair_conv3x3_kernel");
+  }
   pair_conv3x3_kernel<<<grid, kPrThreads, kPrSmemBytes, stream>>>(ta, tb, p);
   return check_launch("pair_conv3x3_kernel");
 }

@@ -324,6 +324,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// Programmatic dependent launch (PDL). launch_dependents: the next kernel in the stream, if it was launched with the
+// programmatic-serialization attribute, may start scheduling its CTAs now; wait: block until every prerequisite grid has
+// completed and its memory operations are visible. Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
