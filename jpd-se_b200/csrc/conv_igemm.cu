@@ -793,11 +793,29 @@ int conv_geom(const jpdse_conv_desc* d, ConvGeom* g) {
 
 // M tiling: 128 pixels = tile_h rows x tile_w columns of the GEMM pixel grid; tile_w is 128 or, for narrower grids,
 // the next power of two. Grids that are not a whole number of tiles get overhanging edge tiles (IgemmParams::partial).
-static void pick_tile(int gw, int* th, int* tw) {
+static void pick_tile(int gw, int* th, int* tw, int gh = 0) {
   int w = 128;
   if (gw < 128) {
     w = 1;
     while (w < gw) w <<= 1;
+  } else if (gh > 0) {
+    // grids that are not a whole number of 128-pixel row pieces (the PatchGAN's 513 / 257 / 129-wide maps: 128 + 128 + 1
+    // pixels are THREE tiles a row): the 128-pixel tile shape (128x1 ... 16x8) that covers the grid with the least overhang;
+    // ties keep the widest (every power-of-two width keeps 128x1). JPDSE_TILE_SHAPE=0: always 128x1.
+    static int on = -1;
+    if (on < 0) {
+      const char* e = getenv("JPDSE_TILE_SHAPE");
+      on = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    long long best = -1;
+    for (int cw = 128; cw >= 16 && on; cw >>= 1) {
+      const int ch = 128 / cw;
+      const long long area = static_cast<long long>((gw + cw - 1) / cw) * cw * ((gh + ch - 1) / ch) * ch;
+      if (best < 0 || area < best) {
+        best = area;
+        w = cw;
+      }
+    }
   }
   *tw = w;
   *th = 128 / w;
@@ -1092,7 +1110,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
   if (d->kind == JPDSE_CONV4X4_S1) {
     const char* e = getenv("JPDSE_FLAT_S1");  // "0": rectangular tiles (read per call: tests toggle it)
     int th = 0, tw = 0;
-    pick_tile(g.gemm_w, &th, &tw);
+    pick_tile(g.gemm_w, &th, &tw, g.gemm_h);
     const long long rect = static_cast<long long>((g.gemm_h + th - 1) / th) * ((g.gemm_w + tw - 1) / tw);
     const long long pitch = d->in_w + 2 * d->in_pad;
     const long long flat_tiles = ((g.out_h - 1) * pitch + g.out_w + 127) / 128;
@@ -1119,7 +1137,7 @@ extern "C" int jpdse_conv_forward(const jpdse_conv_desc* d, const void* x, const
     p.tiles_h = 1;
     p.tiles_w = static_cast<int>((last + 127) / 128);
   } else {
-    pick_tile(g.gemm_w, &p.tile_h, &p.tile_w);
+    pick_tile(g.gemm_w, &p.tile_h, &p.tile_w, g.gemm_h);
     p.tiles_h = (g.gemm_h + p.tile_h - 1) / p.tile_h;
     p.tiles_w = (g.gemm_w + p.tile_w - 1) / p.tile_w;
     p.gemm_h = g.gemm_h;
